@@ -1,0 +1,742 @@
+// limbo_b200/csrc/abi.cu — extern "C" boundary (include/limbo_b200.h) and the
+// host-side orchestration of the device pipeline.  No torch types, no CPU
+// fallback: every numerical result below comes from the CUDA kernels in this
+// directory.
+#include "../../include/limbo_b200.h"
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+int lb_launch_potf2_block(lb_gp* h, int k, int do_factor);
+int lb_launch_linv(lb_gp* h);
+int lb_launch_symmetrize(lb_gp* h, double* dA);
+int lb_launch_acq_full(cudaStream_t st, int acq_id, double p0, double p1, int64_t M, const double* dMu, int mu_stride,
+    const double* dMeanAtQ, double mean_const, const double* dS2, double* dAcq, double* dBlkVal, long long* dBlkIdx,
+    double* dBestVal, long long* dBestIdx, long long* launches);
+
+static thread_local std::string g_last_cuda_error;
+void lb_set_last_cuda_error(cudaError_t e, const char* file, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e), file, line);
+    g_last_cuda_error = buf;
+    cudaGetLastError(); // clear sticky-less errors
+}
+
+namespace {
+
+struct QueryWs { // per-handle query workspace (guarded by qmutex)
+    double* dQraw = nullptr; size_t qraw_bytes = 0;   // M x D row-major staging
+    double* dQs = nullptr; size_t qs_bytes = 0;       // D x Mp
+    double* dV = nullptr; size_t v_bytes = 0;         // Np x Mc
+    double* dMu = nullptr; size_t mu_bytes = 0;       // M x P
+    double* dS2 = nullptr; size_t s2_bytes = 0;       // M
+    double* dAcq = nullptr; size_t acq_bytes = 0;     // M
+    double* dBlkVal = nullptr; long long* dBlkIdx = nullptr; size_t blk_cap = 0;
+    double* dBest = nullptr; // [0] value ; long long index follows
+    long long* dBestIdx = nullptr;
+    double* dMean = nullptr; size_t mean_bytes = 0;
+};
+
+struct Extra {
+    std::mutex qmutex;
+    QueryWs ws;
+    double* dMisc = nullptr; // small scalars (loglik outputs, grad)
+    cudaStream_t own = nullptr; // the handle's own stream (h->stream may point at a caller's stream)
+};
+
+} // namespace
+
+// The Extra block is stored behind the public struct.
+struct lb_gp_full : lb_gp {
+    Extra ex;
+};
+static inline lb_gp_full* full(const lb_gp* h) { return static_cast<lb_gp_full*>(const_cast<lb_gp*>(h)); }
+
+namespace {
+
+template <typename T>
+int ensure(T** p, size_t* cap, size_t bytes)
+{
+    if (*cap >= bytes && *p) return LB_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc((void**)p, want);
+    if (e != cudaSuccess) {
+        lb_set_last_cuda_error(e, __FILE__, __LINE__);
+        return LB_ERR_ALLOC;
+    }
+    *cap = want;
+    return LB_OK;
+}
+
+// row-major (n x D) -> dimension-major (D x np) with optional per-dimension scale, zero padded
+__global__ void pack_soa_kernel(const double* __restrict__ src, int64_t n, int D, double* __restrict__ dst, int64_t np,
+    KernParams kp, int scaled)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int d = blockIdx.y;
+    if (i >= np) return;
+    double v = (i < n) ? src[i * D + d] : 0.0;
+    if (scaled && kp.id == LB_K_SE_ARD) v *= kp.inv_ell[d];
+    dst[(int64_t)d * np + i] = v;
+}
+
+__global__ void pad_cols_kernel(const double* __restrict__ src, int64_t n, int P, double* __restrict__ dst, int64_t np)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int p = blockIdx.y;
+    if (i >= np) return;
+    dst[(int64_t)p * np + i] = (i < n) ? src[(int64_t)p * n + i] : 0.0;
+}
+
+__global__ void fill_kernel(double* __restrict__ p, int64_t n, double v)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// identity on the padding region rows/cols [n0, np)
+__global__ void identity_pad_kernel(double* __restrict__ A, int64_t np, int64_t n0)
+{
+    int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t tot = np * np;
+    for (; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = idx % np, c = idx / np;
+        if (r >= n0 || c >= n0) A[idx] = (r == c) ? 1.0 : 0.0;
+    }
+}
+
+__global__ void identity_blocks_kernel(double* __restrict__ invD, int b0, int b1)
+{
+    int b = b0 + blockIdx.x;
+    if (b >= b1) return;
+    double* p = invD + (int64_t)b * LB_TILE * LB_TILE;
+    for (int idx = threadIdx.x; idx < LB_TILE * LB_TILE; idx += blockDim.x) p[idx] = ((idx & 127) == (idx >> 7)) ? 1.0 : 0.0;
+}
+
+// copy the N x N leading block of a column-major Np matrix, zeroing the strict upper part if asked
+__global__ void extract_kernel(const double* __restrict__ A, int64_t np, int64_t n, double* __restrict__ dst, int lower_only)
+{
+    int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t tot = n * n;
+    for (; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = idx % n, c = idx / n;
+        double v = A[r + c * np];
+        if (lower_only && r < c) v = 0.0;
+        dst[idx] = v;
+    }
+}
+
+// k(x_i, x_new) for i < n (no noise), zero beyond: kernel.hpp:81-84 with i != j
+__global__ void krow_kernel(const double* __restrict__ Xs, int64_t np, int64_t n, int64_t inew, KernParams kp,
+    double* __restrict__ out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    double z = 0.0;
+    for (int d = 0; d < kp.D; ++d) {
+        double q = Xs[(int64_t)d * np + i] - Xs[(int64_t)d * np + inew];
+        z = fma(q, q, z);
+    }
+    out[i] = (i < n) ? lb_kernel_from_z(kp.id, z, kp.sf2, kp.l) : 0.0;
+}
+
+// finish the incremental row (gp.hpp:591-597): L[n, 0:n] = l^T ; L[n,n] = sqrt(k_nn - l.l)
+__global__ void append_row_kernel(double* __restrict__ L, int64_t np, int64_t n, const double* __restrict__ lvec, double knn,
+    int* __restrict__ info)
+{
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+        double v = lvec[j];
+        L[n + j * np] = v;
+        s = fma(v, v, s);
+    }
+    s = lb_warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        double d = knn - t;
+        if (!(d > 0.0)) atomicCAS(info, 0, (int)(n + 1));
+        L[n + n * np] = sqrt(d);
+    }
+}
+
+void free_ws(QueryWs& w)
+{
+    cudaFree(w.dQraw); cudaFree(w.dQs); cudaFree(w.dV); cudaFree(w.dMu); cudaFree(w.dS2); cudaFree(w.dAcq);
+    cudaFree(w.dBlkVal); cudaFree(w.dBlkIdx); cudaFree(w.dBest); cudaFree(w.dBestIdx); cudaFree(w.dMean);
+    w = QueryWs();
+}
+
+void free_model(lb_gp* h)
+{
+    cudaFree(h->dX); cudaFree(h->dXs); cudaFree(h->dY); cudaFree(h->dL); cudaFree(h->dInvD); cudaFree(h->dAlpha);
+    cudaFree(h->dLinv); cudaFree(h->dKinv); cudaFree(h->dFlags);
+    h->dX = h->dXs = h->dY = h->dL = h->dInvD = h->dAlpha = h->dLinv = h->dKinv = nullptr;
+    h->dFlags = nullptr;
+    h->Np = 0;
+}
+
+int alloc_model(lb_gp* h, int64_t Np, int D, int P)
+{
+    const int64_t T = Np / LB_TILE;
+    LB_CUDA(cudaMalloc(&h->dX, sizeof(double) * D * Np));
+    LB_CUDA(cudaMalloc(&h->dXs, sizeof(double) * D * Np));
+    LB_CUDA(cudaMalloc(&h->dY, sizeof(double) * P * Np));
+    LB_CUDA(cudaMalloc(&h->dAlpha, sizeof(double) * P * Np));
+    LB_CUDA(cudaMalloc(&h->dL, sizeof(double) * Np * Np));
+    LB_CUDA(cudaMalloc(&h->dInvD, sizeof(double) * T * LB_TILE * LB_TILE));
+    LB_CUDA(cudaMalloc(&h->dFlags, sizeof(int) * (T + 8)));
+    h->Np = Np;
+    return LB_OK;
+}
+
+int check_info(lb_gp* h)
+{
+    int info[2] = {0, 0};
+    LB_CUDA(cudaMemcpyAsync(info, h->dInfo, sizeof(info), cudaMemcpyDeviceToHost, h->stream));
+    LB_CUDA(cudaStreamSynchronize(h->stream));
+    if (info[1]) return LB_ERR_TIMEOUT;
+    if (info[0] > 0) return info[0];
+    return LB_OK;
+}
+
+int upload_kernel_scaled(lb_gp* h)
+{
+    if (h->N == 0 && h->Np == 0) return LB_OK;
+    return lb_launch_scale_x(h);
+}
+
+} // namespace
+
+int lb_ensure_scratch(lb_gp* h, size_t bytes)
+{
+    return ensure(&h->dScratch, &h->scratch_bytes, bytes);
+}
+
+extern "C" {
+
+int lb_create(lb_gp** out, int device, int precision)
+{
+    if (!out) return LB_ERR_ARG;
+    if (precision != LB_PREC_FP64) return LB_ERR_UNSUPPORTED;
+    int ndev = 0;
+    LB_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return LB_ERR_ARG;
+    LB_CUDA(cudaSetDevice(device));
+    lb_gp_full* h = new (std::nothrow) lb_gp_full();
+    if (!h) return LB_ERR_ALLOC;
+    h->device = device;
+    h->precision = precision;
+    if (cudaStreamCreateWithFlags(&h->ex.own, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return LB_ERR_CUDA;
+    }
+    h->stream = h->ex.own;
+    h->own_stream = true;
+    if (cudaMalloc(&h->dInfo, 4 * sizeof(int)) != cudaSuccess || cudaMalloc(&h->ex.dMisc, 256 * sizeof(double)) != cudaSuccess) {
+        delete h;
+        return LB_ERR_ALLOC;
+    }
+    cudaMemset(h->dInfo, 0, 4 * sizeof(int));
+    h->kp.id = LB_K_SE_ARD;
+    *out = h;
+    return LB_OK;
+}
+
+int lb_destroy(lb_gp* hh)
+{
+    if (!hh) return LB_OK;
+    lb_gp_full* h = full(hh);
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_model(h);
+    free_ws(h->ex.ws);
+    cudaFree(h->dInfo);
+    cudaFree(h->dScratch);
+    cudaFree(h->ex.dMisc);
+    if (h->ex.own) cudaStreamDestroy(h->ex.own);
+    delete h;
+    return LB_OK;
+}
+
+int lb_set_stream(lb_gp* h, void* s)
+{
+    if (!h) return LB_ERR_ARG;
+    lb_gp_full* f = full(h);
+    LB_CUDA(cudaStreamSynchronize(f->stream));
+    f->stream = s ? (cudaStream_t)s : f->ex.own;
+    return LB_OK;
+}
+
+int lb_sync(lb_gp* h)
+{
+    if (!h) return LB_ERR_ARG;
+    LB_CUDA(cudaStreamSynchronize(h->stream));
+    return LB_OK;
+}
+
+long long lb_launch_count(const lb_gp* h) { return h ? h->launches : 0; }
+int64_t lb_nb_samples(const lb_gp* h) { return h ? h->N : 0; }
+
+static int set_data_common(lb_gp* h, int64_t N, int D, int P, const double* X, const double* Y, bool dev)
+{
+    if (!h || N < 0 || D < 1 || D > LB_MAX_D || P < 1) return LB_ERR_ARG;
+    if (N > 0 && (!X || !Y)) return LB_ERR_ARG;
+    LB_CUDA(cudaSetDevice(h->device));
+    const int64_t Np = std::max<int64_t>(LB_TILE, (N + LB_TILE - 1) / LB_TILE * LB_TILE);
+    if (Np != h->Np || D != h->D || P != h->P) {
+        LB_CUDA(cudaStreamSynchronize(h->stream));
+        free_model(h);
+        int rc = alloc_model(h, Np, D, P);
+        if (rc) return rc;
+    }
+    h->N = N; h->D = D; h->P = P;
+    h->kp.D = D;
+    h->fitted = false; h->linv_valid = false; h->kinv_valid = false;
+    const double* dXr = X;
+    const double* dYr = Y;
+    if (!dev && N > 0) {
+        int rc = lb_ensure_scratch(h, sizeof(double) * (size_t)N * (D + P));
+        if (rc) return rc;
+        LB_CUDA(cudaMemcpyAsync(h->dScratch, X, sizeof(double) * N * D, cudaMemcpyHostToDevice, h->stream));
+        LB_CUDA(cudaMemcpyAsync(h->dScratch + N * D, Y, sizeof(double) * N * P, cudaMemcpyHostToDevice, h->stream));
+        dXr = h->dScratch;
+        dYr = h->dScratch + N * D;
+    }
+    dim3 g1((unsigned)((Np + 255) / 256), (unsigned)D), g2((unsigned)((Np + 255) / 256), (unsigned)P);
+    pack_soa_kernel<<<g1, 256, 0, h->stream>>>(dXr, N, D, h->dX, Np, h->kp, 0);
+    pad_cols_kernel<<<g2, 256, 0, h->stream>>>(dYr, N, P, h->dY, Np);
+    h->launches += 2;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+int lb_set_data(lb_gp* h, int64_t N, int D, int P, const double* X, const double* Y)
+{
+    return set_data_common(h, N, D, P, X, Y, false);
+}
+int lb_set_data_dev(lb_gp* h, int64_t N, int D, int P, const double* dX, const double* dY)
+{
+    return set_data_common(h, N, D, P, dX, dY, true);
+}
+
+int lb_set_kernel(lb_gp* h, int kernel_id, const double* p, int n_hparams, double noise)
+{
+    if (!h || !p) return LB_ERR_ARG;
+    if (kernel_id < 0 || kernel_id > 3) return LB_ERR_UNSUPPORTED;
+    if (h->D <= 0) return LB_ERR_STATE; // need the input dimension first (lb_set_data)
+    const int want = (kernel_id == LB_K_SE_ARD) ? h->D + 1 : 2;
+    if (n_hparams != want) return LB_ERR_ARG;
+    KernParams& kp = h->kp;
+    kp.id = kernel_id;
+    kp.D = h->D;
+    kp.noise = noise;
+    if (kernel_id == LB_K_SE_ARD) { // squared_exp_ard.hpp:96-105
+        for (int d = 0; d < h->D; ++d) kp.inv_ell[d] = 1.0 / std::exp(p[d]);
+        kp.sf2 = std::exp(2.0 * p[h->D]);
+        kp.l = 1.0;
+    }
+    else { // matern_five_halves.hpp:97-102 and siblings
+        kp.l = std::exp(p[0]);
+        kp.sf2 = std::exp(2.0 * p[1]);
+    }
+    h->n_hparams = n_hparams;
+    h->kernel_set = true;
+    h->fitted = false; h->linv_valid = false; h->kinv_valid = false;
+    return LB_OK;
+}
+
+int lb_fit(lb_gp* h)
+{
+    if (!h) return LB_ERR_ARG;
+    if (!h->kernel_set || h->Np == 0) return LB_ERR_STATE;
+    LB_CUDA(cudaSetDevice(h->device));
+    if (h->N == 0) return LB_ERR_STATE; // gp.hpp:90 assert(samples.size() != 0)
+    int rc;
+    if ((rc = lb_launch_scale_x(h))) return rc;
+    if ((rc = lb_launch_kbuild(h, h->dL))) return rc;
+    if ((rc = lb_launch_potrf(h))) return rc;
+    h->fitted = true; h->linv_valid = false; h->kinv_valid = false;
+    if ((rc = lb_launch_solve_alpha(h))) return rc;
+    return check_info(h);
+}
+
+int lb_fit_async(lb_gp* h) // same as lb_fit without the final host sync / info read (bench "value" leg)
+{
+    if (!h) return LB_ERR_ARG;
+    if (!h->kernel_set || h->Np == 0 || h->N == 0) return LB_ERR_STATE;
+    int rc;
+    if ((rc = lb_launch_scale_x(h))) return rc;
+    if ((rc = lb_launch_kbuild(h, h->dL))) return rc;
+    if ((rc = lb_launch_potrf(h))) return rc;
+    h->fitted = true; h->linv_valid = false; h->kinv_valid = false;
+    return lb_launch_solve_alpha(h);
+}
+
+int lb_check_info(lb_gp* h) { return h ? check_info(h) : LB_ERR_ARG; }
+
+// stage timers for bench.py: run only one stage (inputs must already be in place)
+int lb_stage_kbuild(lb_gp* h)
+{
+    if (!h || !h->kernel_set || h->N == 0) return LB_ERR_STATE;
+    int rc;
+    if ((rc = lb_launch_scale_x(h))) return rc;
+    h->fitted = false;
+    return lb_launch_kbuild(h, h->dL);
+}
+int lb_stage_potrf(lb_gp* h)
+{
+    if (!h || h->N == 0) return LB_ERR_STATE;
+    int rc = lb_launch_potrf(h);
+    if (!rc) h->fitted = true;
+    return rc;
+}
+int lb_stage_alpha(lb_gp* h)
+{
+    if (!h || !h->fitted) return LB_ERR_STATE;
+    return lb_launch_solve_alpha(h);
+}
+
+int lb_refit_alpha(lb_gp* h, const double* Y)
+{
+    if (!h || !Y) return LB_ERR_ARG;
+    if (!h->fitted) return LB_ERR_STATE;
+    int rc = lb_ensure_scratch(h, sizeof(double) * (size_t)h->N * h->P);
+    if (rc) return rc;
+    LB_CUDA(cudaMemcpyAsync(h->dScratch, Y, sizeof(double) * h->N * h->P, cudaMemcpyHostToDevice, h->stream));
+    dim3 g2((unsigned)((h->Np + 255) / 256), (unsigned)h->P);
+    pad_cols_kernel<<<g2, 256, 0, h->stream>>>(h->dScratch, h->N, h->P, h->dY, h->Np);
+    h->launches++;
+    if ((rc = lb_launch_solve_alpha(h))) return rc;
+    return check_info(h);
+}
+
+int lb_append(lb_gp* h, const double* x, const double* Yall)
+{
+    if (!h || !x || !Yall) return LB_ERR_ARG;
+    if (!h->kernel_set) return LB_ERR_STATE;
+    LB_CUDA(cudaSetDevice(h->device));
+    if (h->N == 0 || !h->fitted) return LB_ERR_STATE; // first sample goes through lb_set_data + lb_fit
+    const int64_t n = h->N;
+    const int D = h->D, P = h->P;
+    if (n + 1 > h->Np) { // grow by one tile, keep the factor
+        const int64_t oldNp = h->Np, newNp = oldNp + LB_TILE;
+        const int64_t oldT = oldNp / LB_TILE, newT = newNp / LB_TILE;
+        double *nX, *nXs, *nY, *nA, *nL, *nI; int* nF;
+        LB_CUDA(cudaStreamSynchronize(h->stream));
+        LB_CUDA(cudaMalloc(&nX, sizeof(double) * D * newNp));
+        LB_CUDA(cudaMalloc(&nXs, sizeof(double) * D * newNp));
+        LB_CUDA(cudaMalloc(&nY, sizeof(double) * P * newNp));
+        LB_CUDA(cudaMalloc(&nA, sizeof(double) * P * newNp));
+        LB_CUDA(cudaMalloc(&nL, sizeof(double) * newNp * newNp));
+        LB_CUDA(cudaMalloc(&nI, sizeof(double) * newT * LB_TILE * LB_TILE));
+        LB_CUDA(cudaMalloc(&nF, sizeof(int) * (newT + 8)));
+        LB_CUDA(cudaMemsetAsync(nX, 0, sizeof(double) * D * newNp, h->stream));
+        LB_CUDA(cudaMemsetAsync(nY, 0, sizeof(double) * P * newNp, h->stream));
+        LB_CUDA(cudaMemcpy2DAsync(nX, newNp * 8, h->dX, oldNp * 8, oldNp * 8, D, cudaMemcpyDeviceToDevice, h->stream));
+        LB_CUDA(cudaMemcpy2DAsync(nL, newNp * 8, h->dL, oldNp * 8, oldNp * 8, oldNp, cudaMemcpyDeviceToDevice, h->stream));
+        LB_CUDA(cudaMemcpyAsync(nI, h->dInvD, sizeof(double) * oldT * LB_TILE * LB_TILE, cudaMemcpyDeviceToDevice, h->stream));
+        identity_pad_kernel<<<1024, 256, 0, h->stream>>>(nL, newNp, oldNp);
+        identity_blocks_kernel<<<(unsigned)(newT - oldT), 256, 0, h->stream>>>(nI, (int)oldT, (int)newT);
+        h->launches += 2;
+        LB_CUDA(cudaStreamSynchronize(h->stream));
+        cudaFree(h->dX); cudaFree(h->dXs); cudaFree(h->dY); cudaFree(h->dAlpha); cudaFree(h->dL); cudaFree(h->dInvD);
+        cudaFree(h->dFlags); cudaFree(h->dLinv); cudaFree(h->dKinv);
+        h->dX = nX; h->dXs = nXs; h->dY = nY; h->dAlpha = nA; h->dL = nL; h->dInvD = nI; h->dFlags = nF;
+        h->dLinv = h->dKinv = nullptr;
+        h->Np = newNp;
+    }
+    const int64_t Np = h->Np;
+    int rc = lb_ensure_scratch(h, sizeof(double) * (size_t)((n + 1) * P + D + Np));
+    if (rc) return rc;
+    double* dYs = h->dScratch;
+    double* dx = dYs + (n + 1) * P;
+    double* dk = dx + D;
+    LB_CUDA(cudaMemcpyAsync(dYs, Yall, sizeof(double) * (n + 1) * P, cudaMemcpyHostToDevice, h->stream));
+    LB_CUDA(cudaMemcpyAsync(dx, x, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));
+    // X[:, n] = x  (strided D writes)
+    LB_CUDA(cudaMemcpy2DAsync(h->dX + n, Np * 8, dx, 8, 8, D, cudaMemcpyDeviceToDevice, h->stream));
+    h->N = n + 1;
+    dim3 g2((unsigned)((Np + 255) / 256), (unsigned)P);
+    pad_cols_kernel<<<g2, 256, 0, h->stream>>>(dYs, n + 1, P, h->dY, Np);
+    h->launches++;
+    if ((rc = lb_launch_scale_x(h))) return rc;
+    // new kernel row (gp.hpp:583-586), forward solve against the existing factor (gp.hpp:591-594)
+    krow_kernel<<<(unsigned)((Np + 255) / 256), 256, 0, h->stream>>>(h->dXs, Np, n, n, h->kp, dk);
+    h->launches++;
+    if ((rc = lb_launch_trsv(h, dk, 1, true))) return rc;
+    const double knn = h->kp.sf2 + h->kp.noise + 1e-8; // kernel(x,x) with i == j, kernel.hpp:83
+    append_row_kernel<<<1, 256, 0, h->stream>>>(h->dL, Np, n, dk, knn, h->dInfo);
+    h->launches++;
+    if ((rc = lb_launch_potf2_block(h, (int)(n / LB_TILE), 0))) return rc;
+    h->linv_valid = false; h->kinv_valid = false;
+    if ((rc = lb_launch_solve_alpha(h))) return rc;
+    return check_info(h);
+}
+
+static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_dev, double* mu_out, double* s2_out,
+    bool out_dev, int acq_id, const double* acq_params, const double* mean_at_q, double mean_const, double* acq_out,
+    double* best_val, int64_t* best_idx, bool with_acq)
+{
+    if (!hc || M < 0) return LB_ERR_ARG;
+    if (M == 0) return LB_OK;
+    if (!Xq) return LB_ERR_ARG;
+    lb_gp_full* h = full(hc);
+    if (h->D <= 0 || !h->kernel_set) return LB_ERR_STATE;
+    LB_CUDA(cudaSetDevice(h->device));
+    std::lock_guard<std::mutex> lock(h->ex.qmutex);
+    QueryWs& w = h->ex.ws;
+    cudaStream_t st = h->stream;
+    const int D = h->D, P = h->P > 0 ? h->P : 1;
+    const int64_t Mp = (M + LB_TILE - 1) / LB_TILE * LB_TILE;
+    int rc;
+    if ((rc = ensure(&w.dMu, &w.mu_bytes, sizeof(double) * M * P))) return rc;
+    if ((rc = ensure(&w.dS2, &w.s2_bytes, sizeof(double) * M))) return rc;
+    const bool prior = (h->N == 0 || !h->fitted);
+    if (prior && h->N != 0) return LB_ERR_STATE;
+    if (prior) { // gp.hpp:161-163: mu = mean(v) (added by the caller), sigma2 = k(v,v) + noise
+        LB_CUDA(cudaMemsetAsync(w.dMu, 0, sizeof(double) * M * P, st));
+        fill_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(w.dS2, M, h->kp.sf2 + h->kp.noise);
+        h->launches++;
+    }
+    else {
+        const double* dQraw = Xq;
+        if (!xq_dev) {
+            if ((rc = ensure(&w.dQraw, &w.qraw_bytes, sizeof(double) * M * D))) return rc;
+            LB_CUDA(cudaMemcpyAsync(w.dQraw, Xq, sizeof(double) * M * D, cudaMemcpyHostToDevice, st));
+            dQraw = w.dQraw;
+        }
+        // candidate chunks bounded so that V (Np x Mc) stays <= ~4 GiB
+        int64_t Mc = Mp;
+        const int64_t maxcols = std::max<int64_t>(LB_TILE, ((int64_t)4 << 30) / (8 * h->Np) / LB_TILE * LB_TILE);
+        if (Mc > maxcols) Mc = maxcols;
+        if ((rc = ensure(&w.dQs, &w.qs_bytes, sizeof(double) * D * Mc))) return rc;
+        if ((rc = ensure(&w.dV, &w.v_bytes, sizeof(double) * h->Np * Mc))) return rc;
+        for (int64_t m0 = 0; m0 < M; m0 += Mc) {
+            const int64_t mc = std::min(Mc, M - m0);
+            const int64_t mcp = (mc + LB_TILE - 1) / LB_TILE * LB_TILE;
+            dim3 g1((unsigned)((mcp + 255) / 256), (unsigned)D);
+            pack_soa_kernel<<<g1, 256, 0, st>>>(dQraw + m0 * D, mc, D, w.dQs, mcp, h->kp, 1);
+            h->launches++;
+            if ((rc = lb_launch_query(h, st, mc, w.dQs, mcp, w.dV, w.dMu + m0 * P, w.dS2 + m0, &h->launches))) return rc;
+        }
+    }
+    if (with_acq) {
+        const int nblk = (int)((M + 255) / 256);
+        if ((size_t)nblk > w.blk_cap) {
+            cudaFree(w.dBlkVal); cudaFree(w.dBlkIdx);
+            LB_CUDA(cudaMalloc(&w.dBlkVal, sizeof(double) * nblk));
+            LB_CUDA(cudaMalloc(&w.dBlkIdx, sizeof(long long) * nblk));
+            w.blk_cap = nblk;
+        }
+        if (!w.dBest) {
+            LB_CUDA(cudaMalloc(&w.dBest, sizeof(double)));
+            LB_CUDA(cudaMalloc(&w.dBestIdx, sizeof(long long)));
+        }
+        const double* dMean = nullptr;
+        if (mean_at_q) {
+            if (out_dev) dMean = mean_at_q;
+            else {
+                if ((rc = ensure(&w.dMean, &w.mean_bytes, sizeof(double) * M))) return rc;
+                LB_CUDA(cudaMemcpyAsync(w.dMean, mean_at_q, sizeof(double) * M, cudaMemcpyHostToDevice, st));
+                dMean = w.dMean;
+            }
+        }
+        double* dAcq = nullptr;
+        if (acq_out) {
+            if (out_dev) dAcq = acq_out;
+            else {
+                if ((rc = ensure(&w.dAcq, &w.acq_bytes, sizeof(double) * M))) return rc;
+                dAcq = w.dAcq;
+            }
+        }
+        double* dBV = out_dev ? best_val : w.dBest;
+        long long* dBI = out_dev ? (long long*)best_idx : w.dBestIdx;
+        const double p0 = acq_params ? acq_params[0] : 0.0;
+        const double p1 = (acq_params && acq_id == LB_ACQ_EI) ? acq_params[1] : 0.0;
+        if ((rc = lb_launch_acq_full(st, acq_id, p0, p1, M, w.dMu, P, dMean, mean_const, w.dS2, dAcq, w.dBlkVal, w.dBlkIdx,
+                 dBV, dBI, &h->launches)))
+            return rc;
+        if (!out_dev) {
+            if (acq_out) LB_CUDA(cudaMemcpyAsync(acq_out, w.dAcq, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+            long long bi = 0;
+            LB_CUDA(cudaMemcpyAsync(best_val, w.dBest, sizeof(double), cudaMemcpyDeviceToHost, st));
+            LB_CUDA(cudaMemcpyAsync(&bi, w.dBestIdx, sizeof(long long), cudaMemcpyDeviceToHost, st));
+            LB_CUDA(cudaStreamSynchronize(st));
+            *best_idx = (int64_t)bi;
+        }
+    }
+    if (mu_out) {
+        LB_CUDA(cudaMemcpyAsync(mu_out, w.dMu, sizeof(double) * M * P, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    }
+    if (s2_out) {
+        LB_CUDA(cudaMemcpyAsync(s2_out, w.dS2, sizeof(double) * M, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    }
+    if (!out_dev) LB_CUDA(cudaStreamSynchronize(st));
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+int lb_query(const lb_gp* h, int64_t M, const double* Xq, double* mu, double* s2)
+{
+    return query_common(h, M, Xq, false, mu, s2, false, 0, nullptr, nullptr, 0.0, nullptr, nullptr, nullptr, false);
+}
+int lb_query_dev(const lb_gp* h, int64_t M, const double* dXq, double* dMu, double* dS2)
+{
+    return query_common(h, M, dXq, true, dMu, dS2, true, 0, nullptr, nullptr, 0.0, nullptr, nullptr, nullptr, false);
+}
+
+int lb_acq_argmax(const lb_gp* h, int acq_id, const double* acq_params, int64_t M, const double* Xq, const double* mean_at_q,
+    double mean_const, double* acq_out, double* best_val, int64_t* best_idx)
+{
+    if (!best_val || !best_idx || !acq_params || M <= 0) return LB_ERR_ARG;
+    if (acq_id != LB_ACQ_UCB && acq_id != LB_ACQ_EI) return LB_ERR_UNSUPPORTED;
+    return query_common(h, M, Xq, false, nullptr, nullptr, false, acq_id, acq_params, mean_at_q, mean_const, acq_out, best_val,
+        best_idx, true);
+}
+int lb_acq_argmax_dev(const lb_gp* h, int acq_id, const double* acq_params, int64_t M, const double* dXq,
+    const double* dMean_at_q, double mean_const, double* dAcq_out, double* dBest_val, int64_t* dBest_idx)
+{
+    if (!dBest_val || !dBest_idx || !acq_params || M <= 0) return LB_ERR_ARG;
+    if (acq_id != LB_ACQ_UCB && acq_id != LB_ACQ_EI) return LB_ERR_UNSUPPORTED;
+    return query_common(h, M, dXq, true, nullptr, nullptr, true, acq_id, acq_params, dMean_at_q, mean_const, dAcq_out,
+        dBest_val, dBest_idx, true);
+}
+
+int lb_log_lik(lb_gp* hh, double* out)
+{
+    if (!hh || !out) return LB_ERR_ARG;
+    if (!hh->fitted) return LB_ERR_STATE;
+    lb_gp_full* h = full(hh);
+    int rc = lb_launch_loglik(h, h->ex.dMisc);
+    if (rc) return rc;
+    double v[3];
+    LB_CUDA(cudaMemcpyAsync(v, h->ex.dMisc, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    LB_CUDA(cudaStreamSynchronize(h->stream));
+    *out = v[2];
+    return LB_OK;
+}
+
+int lb_compute_inv_kernel(lb_gp* h)
+{
+    if (!h) return LB_ERR_ARG;
+    if (!h->fitted) return LB_ERR_STATE;
+    if (h->kinv_valid) return LB_OK;
+    return lb_launch_kinv(h);
+}
+
+int lb_kernel_grad_log_lik(lb_gp* hh, int optimize_noise, double* grad)
+{
+    if (!hh || !grad) return LB_ERR_ARG;
+    if (!hh->fitted) return LB_ERR_STATE;
+    lb_gp_full* h = full(hh);
+    int rc;
+    if (!h->kinv_valid && (rc = lb_launch_kinv(h))) return rc;
+    const int nh = h->n_hparams + (optimize_noise ? 1 : 0);
+    if (nh > 128) return LB_ERR_ARG;
+    if ((rc = lb_launch_grad(h, optimize_noise, h->ex.dMisc + 8))) return rc;
+    LB_CUDA(cudaMemcpyAsync(grad, h->ex.dMisc + 8, sizeof(double) * nh, cudaMemcpyDeviceToHost, h->stream));
+    LB_CUDA(cudaStreamSynchronize(h->stream));
+    return LB_OK;
+}
+
+int lb_get(lb_gp* h, int what, double* dst)
+{
+    if (!h || !dst) return LB_ERR_ARG;
+    if (h->N == 0) return LB_ERR_STATE;
+    const int64_t N = h->N, Np = h->Np;
+    int rc;
+    if (what == LB_GET_ALPHA) {
+        if (!h->fitted) return LB_ERR_STATE;
+        LB_CUDA(cudaMemcpy2DAsync(dst, N * 8, h->dAlpha, Np * 8, N * 8, h->P, cudaMemcpyDeviceToHost, h->stream));
+        LB_CUDA(cudaStreamSynchronize(h->stream));
+        return LB_OK;
+    }
+    if ((rc = lb_ensure_scratch(h, sizeof(double) * (size_t)(Np * Np + N * N)))) return rc;
+    double* dTmp = h->dScratch;
+    double* dOut = h->dScratch + Np * Np;
+    const double* src = nullptr;
+    int lower = 0;
+    if (what == LB_GET_K) {
+        if (!h->kernel_set) return LB_ERR_STATE;
+        if ((rc = lb_launch_scale_x(h))) return rc;
+        if ((rc = lb_launch_kbuild(h, dTmp))) return rc;
+        src = dTmp;
+    }
+    else if (what == LB_GET_L) {
+        if (!h->fitted) return LB_ERR_STATE;
+        src = h->dL;
+        lower = 1;
+    }
+    else if (what == LB_GET_KINV) {
+        if (!h->fitted) return LB_ERR_STATE;
+        if (!h->kinv_valid && (rc = lb_launch_kinv(h))) return rc;
+        if ((rc = lb_launch_symmetrize(h, h->dKinv))) return rc;
+        src = h->dKinv;
+    }
+    else
+        return LB_ERR_ARG;
+    extract_kernel<<<1024, 256, 0, h->stream>>>(src, Np, N, dOut, lower);
+    h->launches++;
+    LB_CUDA(cudaMemcpyAsync(dst, dOut, sizeof(double) * N * N, cudaMemcpyDeviceToHost, h->stream));
+    LB_CUDA(cudaStreamSynchronize(h->stream));
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+int lb_clone(const lb_gp* src, lb_gp** out)
+{
+    if (!src || !out) return LB_ERR_ARG;
+    lb_gp* h = nullptr;
+    int rc = lb_create(&h, src->device, src->precision);
+    if (rc) return rc;
+    cudaStream_t st = src->stream;
+    h->kp = src->kp; h->kernel_set = src->kernel_set; h->n_hparams = src->n_hparams;
+    h->N = src->N; h->D = src->D; h->P = src->P;
+    if (src->Np > 0) {
+        if ((rc = alloc_model(h, src->Np, src->D, src->P))) { lb_destroy(h); return rc; }
+        const int64_t Np = src->Np, T = Np / LB_TILE;
+        cudaMemcpyAsync(h->dX, src->dX, sizeof(double) * src->D * Np, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(h->dXs, src->dXs, sizeof(double) * src->D * Np, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(h->dY, src->dY, sizeof(double) * src->P * Np, cudaMemcpyDeviceToDevice, st);
+        if (src->fitted) {
+            cudaMemcpyAsync(h->dAlpha, src->dAlpha, sizeof(double) * src->P * Np, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(h->dL, src->dL, sizeof(double) * Np * Np, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(h->dInvD, src->dInvD, sizeof(double) * T * LB_TILE * LB_TILE, cudaMemcpyDeviceToDevice, st);
+            h->fitted = true;
+        }
+        if (cudaStreamSynchronize(st) != cudaSuccess) { lb_destroy(h); return LB_ERR_CUDA; }
+    }
+    *out = h;
+    return LB_OK;
+}
+
+const char* lb_strerror(int code)
+{
+    if (code > 0) return "kernel matrix is not positive definite (value = 1-based index of the failing pivot)";
+    switch (code) {
+    case LB_OK: return "ok";
+    case LB_ERR_ARG: return "invalid argument";
+    case LB_ERR_CUDA: return "CUDA runtime error (see lb_last_cuda_error)";
+    case LB_ERR_STATE: return "call sequence error (data / kernel / fit missing)";
+    case LB_ERR_ALLOC: return "device memory allocation failed";
+    case LB_ERR_UNSUPPORTED: return "unsupported kernel / acquisition / precision";
+    case LB_ERR_TIMEOUT: return "device-side wait timed out";
+    default: return "unknown error";
+    }
+}
+
+const char* lb_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+
+} // extern "C"

@@ -1,0 +1,213 @@
+// limbo_b200/csrc/common.cuh — shared declarations for the sm_100a GP backend.
+//
+// Data layout in HBM:
+//   * every N-sized dimension is padded to Np = roundup(N, 128); the padded
+//     part of K is the identity, so the Cholesky factor, the triangular
+//     solves, K^-1 and log|K| of the padded system restrict exactly to those
+//     of the N x N system and no kernel needs edge predication;
+//   * X  : D x Np "SoA" (dimension-major) so 128-point blocks of one input
+//     dimension are 1 KB contiguous runs (TMA bulk-copy friendly);
+//   * K/L: Np x Np column-major (Eigen::MatrixXd's layout, gp.hpp:553), the
+//     factor overwrites the lower triangle in place;
+//   * invD: T blocks of 128 x 128 (column-major, lower) = inverses of the
+//     diagonal blocks of L, produced by the panel factorisation and reused by
+//     every triangular solve.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#define LB_TILE 128
+
+// ---- status codes (include/limbo_b200.h) ----------------------------------
+#define LB_OK 0
+#define LB_ERR_ARG (-1)
+#define LB_ERR_CUDA (-2)
+#define LB_ERR_STATE (-3)
+#define LB_ERR_ALLOC (-4)
+#define LB_ERR_UNSUPPORTED (-5)
+#define LB_ERR_TIMEOUT (-6)
+
+#define LB_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            lb_set_last_cuda_error(e__, __FILE__, __LINE__);                            \
+            return LB_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+void lb_set_last_cuda_error(cudaError_t e, const char* file, int line);
+
+enum { LB_K_SE_ARD = 0, LB_K_MATERN52 = 1, LB_K_MATERN32 = 2, LB_K_EXP = 3 };
+#define LB_MAX_D 64
+
+// Kernel parameters passed by value to device code.
+struct KernParams {
+    int id;
+    int D;
+    double sf2;      // exp(2 p_last)                    squared_exp_ard.hpp:104
+    double l;        // isotropic length scale            matern_five_halves.hpp:100
+    double noise;    // kernel/kernel.hpp:76-79
+    double inv_ell[LB_MAX_D]; // SE-ARD: 1/exp(p_d)
+};
+
+// ---------------------------------------------------------------------------
+// Device-side kernel functor: value from the (scaled) squared distance.
+//   SE-ARD : z = sum_d ((x_d - y_d)/ell_d)^2  (X is pre-scaled by 1/ell_d)
+//   others : z = sum_d (x_d - y_d)^2          (raw X)
+// Operation order after z follows the reference functors so that the result
+// differs from the Eigen path only by the rounding of z itself.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double lb_kernel_from_z(int id, double z, double sf2, double l)
+{
+    switch (id) {
+    case LB_K_SE_ARD: // squared_exp_ard.hpp:150
+        return sf2 * exp(-0.5 * z);
+    case LB_K_MATERN52: { // matern_five_halves.hpp:104-113
+        double d = sqrt(z);
+        double d_sq = d * d;
+        double l_sq = l * l;
+        double term1 = sqrt(5.0) * d / l;
+        double term2 = 5. * d_sq / (3. * l_sq);
+        return sf2 * (1 + term1 + term2) * exp(-term1);
+    }
+    case LB_K_MATERN32: { // matern_three_halves.hpp:102-108
+        double d = sqrt(z);
+        double term = sqrt(3.0) * d / l;
+        return sf2 * (1 + term) * exp(-term);
+    }
+    default: { // exp.hpp:94-99
+        double r = z / (l * l);
+        return sf2 * exp(-0.5 * r);
+    }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lb_smem_u32(const void* p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// fp64 tensor-core MMA (DMMA).  tcgen05 has no f64 kind; on sm_100a the fp64
+// tensor path is warp-level mma.sync, which ptxas lowers to DMMA.8x8x4.
+//   A frag (16x8, row): a[i]: row = g + 8*(i&1), col = t + 4*(i>>1)
+//   B frag (8x8,  col): b[i]: k = t + 4*i, n = g
+//   C frag (16x8)     : c[i]: row = g + 8*(i>>1), col = 2*t + (i&1)
+// with g = lane>>2, t = lane&3.
+__device__ __forceinline__ void lb_dmma_16x8x8(double (&c)[4], const double (&a)[4], const double (&b)[2])
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+        : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
+}
+
+__device__ __forceinline__ void lb_cp_async16(void* smem_dst, const void* gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(lb_smem_u32(smem_dst)), "l"(gmem_src));
+}
+__device__ __forceinline__ void lb_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void lb_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// mbarrier + TMA 1-D bulk copy (cp.async.bulk -> SASS UBLKCP)
+__device__ __forceinline__ void lb_mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(lb_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void lb_fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+}
+__device__ __forceinline__ void lb_fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;\n" ::);
+}
+__device__ __forceinline__ void lb_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(lb_smem_u32(bar)), "r"(bytes));
+}
+__device__ __forceinline__ void lb_mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(lb_smem_u32(bar)),
+        "r"(parity));
+}
+// bytes must be a multiple of 16; src/dst 16-byte aligned
+__device__ __forceinline__ void lb_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     lb_smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(lb_smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ double lb_warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// Host-side handle
+// ---------------------------------------------------------------------------
+struct lb_gp {
+    int device = 0;
+    int precision = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    int64_t N = 0;   // live samples
+    int64_t Np = 0;  // padded capacity (multiple of 128)
+    int D = 0, P = 0;
+
+    KernParams kp{};
+    bool kernel_set = false;
+    int n_hparams = 0;
+
+    double* dX = nullptr;    // D x Np raw samples (SoA)
+    double* dXs = nullptr;   // D x Np samples scaled for the kernel (SE-ARD: /ell)
+    double* dY = nullptr;    // Np x P  obs_mean (col-major), zero padded
+    double* dL = nullptr;    // Np x Np K then L (col-major)
+    double* dInvD = nullptr; // T x 128 x 128
+    double* dAlpha = nullptr; // Np x P
+    double* dLinv = nullptr; // Np x Np (lazy: L^-1)
+    double* dKinv = nullptr; // Np x Np (lazy: K^-1, lower valid + mirrored)
+    int* dInfo = nullptr;    // [0] first failing pivot (1-based) or 0; [1] solver error
+    int* dFlags = nullptr;   // T+1 ints: trsv progress flags / ticket
+    double* dScratch = nullptr; size_t scratch_bytes = 0;
+
+    bool fitted = false;
+    bool linv_valid = false;
+    bool kinv_valid = false;
+
+    // counters for bench.py ("gpu_launches")
+    long long launches = 0;
+};
+
+// internal entry points (one per .cu)
+int lb_launch_scale_x(lb_gp* h);
+int lb_launch_kbuild(lb_gp* h, double* dK);
+int lb_launch_potrf(lb_gp* h);
+int lb_launch_solve_alpha(lb_gp* h);
+int lb_launch_trsv(lb_gp* h, double* dB, int nrhs, bool forward);
+int lb_launch_query(const lb_gp* h, cudaStream_t st, int64_t M, const double* dXq_soa /*D x Mp*/, int64_t Mp,
+    double* dV /*Np x Mp*/, double* dMu /*Mp x P*/, double* dS2 /*Mp*/, long long* launches);
+int lb_launch_acq(const lb_gp* h, cudaStream_t st, int acq_id, double p0, double p1, int64_t M, const double* dMu0,
+    const double* dS2, double* dAcq, double* dBestVal, long long* dBestIdx, long long* launches);
+int lb_launch_loglik(lb_gp* h, double* dOut /*3 doubles: a, logdet, loglik*/);
+int lb_launch_kinv(lb_gp* h);
+int lb_launch_grad(lb_gp* h, int optimize_noise, double* dGrad);
+int lb_ensure_scratch(lb_gp* h, size_t bytes);

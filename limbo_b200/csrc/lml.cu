@@ -1,0 +1,417 @@
+// limbo_b200/csrc/lml.cu — log marginal likelihood, K^-1 and the kernel
+// hyper-parameter gradient (what model::gp::KernelLFOpt evaluates per Rprop step,
+// model/gp/kernel_lf_opt.hpp:77-92).
+//
+//   GP::compute_log_lik             model/gp.hpp:267-282  -> loglik_kernel
+//   GP::compute_inv_kernel          model/gp.hpp:254-264  -> trtri (block rows, DMMA) + lauum_kernel (DMMA)
+//                                   2N^3/3 flops instead of the reference's 2N^3
+//   GP::compute_kernel_grad_log_lik model/gp.hpp:285-311  -> grad_kernel: one streaming pass over the
+//                                   lower tiles of K^-1, k_ij and d k_ij / d theta recomputed from X
+//                                   (W = alpha alpha^T - K^-1 is never materialised)
+#include "gemm.cuh"
+
+int lb_launch_trsm_lower(const lb_gp* h, cudaStream_t st, double* dV, int64_t Mp, int i_begin, long long* launches);
+
+namespace {
+
+constexpr int DCH = 16;
+
+__global__ void __launch_bounds__(1024)
+loglik_kernel(const double* __restrict__ L, int64_t ld, int64_t N, const double* __restrict__ Y,
+    const double* __restrict__ alpha, int P, double* __restrict__ out)
+{
+    __shared__ double r1[32], r2[32];
+    double s_log = 0.0, s_a = 0.0;
+    for (int64_t i = threadIdx.x; i < N; i += 1024) {
+        s_log += log(L[i + i * ld]);
+        for (int p = 0; p < P; ++p) s_a = fma(Y[i + (int64_t)p * ld], alpha[i + (int64_t)p * ld], s_a);
+    }
+    s_log = lb_warp_sum(s_log);
+    s_a = lb_warp_sum(s_a);
+    if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s_log; r2[threadIdx.x >> 5] = s_a; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v1 = lb_warp_sum(r1[threadIdx.x]);
+        double v2 = lb_warp_sum(r2[threadIdx.x]);
+        if (threadIdx.x == 0) {
+            double logdet = 2.0 * v1; // gp.hpp:274
+            out[0] = v2;
+            out[1] = logdet;
+            out[2] = -0.5 * v2 - 0.5 * logdet - 0.5 * (double)N * log(2.0 * M_PI); // gp.hpp:279
+        }
+    }
+}
+
+__global__ void set_identity_kernel(double* __restrict__ A, int64_t n)
+{
+    int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t tot = n * n;
+    for (; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = idx % n, c = idx / n;
+        A[idx] = (r == c) ? 1.0 : 0.0;
+    }
+}
+
+// Block row i of X = L^-1 (X lower triangular, stored full Np x Np, zero above):
+//   X[i,j] = -inv(L_ii) * sum_{k=j}^{i-1} L[i,k] X[k,j]   (j < i),  X[i,i] = inv(L_ii)
+// grid = i + 1 column tiles.
+__global__ void __launch_bounds__(lbg::THREADS, 1)
+trtri_row_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ invD, double* __restrict__ X, int i)
+{
+    extern __shared__ __align__(16) double smem[];
+    constexpr int PB = lbg::BM + 4;
+    double* sT = smem + lbg::STAGES * lbg::STAGE_DOUBLES;
+    const int j = blockIdx.x;
+    double* Xij = X + (int64_t)i * LB_TILE + (int64_t)j * LB_TILE * ld;
+    const double* Di = invD + (int64_t)i * LB_TILE * LB_TILE;
+    if (j == i) {
+        for (int idx = threadIdx.x; idx < LB_TILE * LB_TILE; idx += lbg::THREADS) {
+            int r = idx & 127, c = idx >> 7;
+            Xij[r + (int64_t)c * ld] = Di[r + c * LB_TILE];
+        }
+        return;
+    }
+    lbg::Acc<128> acc;
+    acc.zero();
+    // A = L[i, j..i-1] (outer-contiguous), B = X[j..i-1, j] (k-contiguous)
+    lbg::mainloop<128, false, true>(acc, L + (int64_t)i * LB_TILE + (int64_t)j * LB_TILE * ld, ld,
+        X + (int64_t)j * LB_TILE + (int64_t)j * LB_TILE * ld, ld, (i - j) * LB_TILE, smem);
+    lbg::for_each_acc<128>(acc, [&](int r, int c, double v) { sT[c * PB + r] = -v; });
+    __syncthreads();
+    lbg::Acc<128> acc2;
+    acc2.zero();
+    lbg::mainloop_resB<128>(acc2, Di, LB_TILE, sT, smem);
+    lbg::for_each_acc<128>(acc2, [&](int r, int c, double v) { Xij[r + (int64_t)c * ld] = v; });
+}
+
+// Kinv[i,j] = sum_{k >= i} X[k,i]^T X[k,j]  for i >= j (lower tiles only)
+__global__ void __launch_bounds__(lbg::THREADS, 1)
+lauum_kernel(const double* __restrict__ X, int64_t ld, double* __restrict__ Kinv, int T)
+{
+    extern __shared__ __align__(16) double smem[];
+    // longest K ranges (small i) first: enumerate tiles so that i ascends
+    int t = blockIdx.x;
+    int r = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((int64_t)(r + 1) * (r + 2) / 2 <= t) ++r;
+    while ((int64_t)r * (r + 1) / 2 > t) --r;
+    const int i = r, j = t - r * (r + 1) / 2;
+    lbg::Acc<128> acc;
+    acc.zero();
+    const int64_t k0 = (int64_t)i * LB_TILE;
+    lbg::mainloop<128, true, true>(acc, X + k0 + (int64_t)i * LB_TILE * ld, ld, X + k0 + (int64_t)j * LB_TILE * ld, ld,
+        (T - i) * LB_TILE, smem);
+    double* C = Kinv + (int64_t)i * LB_TILE + (int64_t)j * LB_TILE * ld;
+    lbg::for_each_acc<128>(acc, [&](int rr, int cc, double v) { C[rr + (int64_t)cc * ld] = v; });
+}
+
+// mirror lower -> upper (export only)
+__global__ void symmetrize_kernel(double* __restrict__ A, int64_t n)
+{
+    __shared__ double tile[32][33];
+    int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    int64_t r = (int64_t)bi * 32 + threadIdx.x, c0 = (int64_t)bj * 32;
+    for (int cc = threadIdx.y; cc < 32; cc += 8) tile[cc][threadIdx.x] = A[r + (c0 + cc) * n];
+    __syncthreads();
+    // write A[c0+x, bi*32 + y] = tile[x][y]  (upper counterpart)
+    for (int cc = threadIdx.y; cc < 32; cc += 8) {
+        int64_t rr = c0 + threadIdx.x, col = (int64_t)bi * 32 + cc;
+        if (rr < col) A[rr + col * n] = tile[threadIdx.x][cc];
+    }
+}
+
+__device__ __forceinline__ void tile_from_index(int t, int& bi, int& bj)
+{
+    int r = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((int64_t)(r + 1) * (r + 2) / 2 <= t) ++r;
+    while ((int64_t)r * (r + 1) / 2 > t) --r;
+    bi = r;
+    bj = t - r * (r + 1) / 2;
+}
+
+// grad partials: part[tile][q], q < nh.
+//   sum_{i>=j} w_ij * dK_ij/dtheta_q * (1/2 if i==j)        gp.hpp:299-308
+//   w = alpha alpha^T - K^-1                                  gp.hpp:293-296
+__global__ void __launch_bounds__(256, 2)
+grad_kernel(const double* __restrict__ Xs, const double* __restrict__ Kinv, const double* __restrict__ alpha, int P,
+    int64_t N, int64_t Np, KernParams kp, int optimize_noise, int nh, double* __restrict__ part)
+{
+    __shared__ __align__(128) double sxi[DCH][LB_TILE];
+    __shared__ __align__(128) double sxj[DCH][LB_TILE];
+    __shared__ double sred[8][DCH + 4];
+    __shared__ double stot[LB_MAX_D + 2];
+    __shared__ __align__(8) uint64_t bar;
+    int bi, bj;
+    tile_from_index(blockIdx.x, bi, bj);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int li = lane & 7, lj = lane >> 3;
+    const int D = kp.D;
+    const int64_t i0 = (int64_t)bi * LB_TILE, j0 = (int64_t)bj * LB_TILE;
+    const int r0 = warp * 16 + 2 * li;
+    if (tid == 0) {
+        lb_mbar_init(&bar, 1);
+        lb_fence_barrier_init();
+    }
+    for (int q = tid; q < LB_MAX_D + 2; q += 256) stot[q] = 0.0;
+    __syncthreads();
+    uint32_t phase = 0;
+    const int npass = (D + DCH - 1) / DCH;
+    const bool ard = (kp.id == LB_K_SE_ARD);
+
+    auto stage = [&](int pass) {
+        const int d0 = pass * DCH;
+        const int dc = min(DCH, D - d0);
+        __syncthreads();
+        if (tid == 0) {
+            lb_fence_proxy_async();
+            lb_mbar_expect_tx(&bar, (uint32_t)(2 * dc * LB_TILE * sizeof(double)));
+            for (int d = 0; d < dc; ++d) {
+                lb_bulk_g2s(&sxi[d][0], Xs + (int64_t)(d0 + d) * Np + i0, LB_TILE * sizeof(double), &bar);
+                lb_bulk_g2s(&sxj[d][0], Xs + (int64_t)(d0 + d) * Np + j0, LB_TILE * sizeof(double), &bar);
+            }
+        }
+        lb_mbar_wait(&bar, phase);
+        phase ^= 1;
+        return dc;
+    };
+
+    double g_sf = 0.0, g_l = 0.0, g_noise = 0.0;
+    for (int h = 0; h < 2; ++h) {
+        double z[8][4];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) z[c][e] = 0.0;
+        for (int pass = 0; pass < npass; ++pass) {
+            int dc = D;
+            if (!(npass == 1 && h == 1)) dc = stage(pass);
+            else dc = min(DCH, D);
+            for (int d = 0; d < dc; ++d) {
+                const double2 xi = *reinterpret_cast<const double2*>(&sxi[d][r0]);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const double2 xj = *reinterpret_cast<const double2*>(&sxj[d][h * 64 + c * 8 + 2 * lj]);
+                    double q;
+                    q = xi.x - xj.x; z[c][0] = fma(q, q, z[c][0]);
+                    q = xi.y - xj.x; z[c][1] = fma(q, q, z[c][1]);
+                    q = xi.x - xj.y; z[c][2] = fma(q, q, z[c][2]);
+                    q = xi.y - xj.y; z[c][3] = fma(q, q, z[c][3]);
+                }
+            }
+        }
+        // weights w_ij * f_ij, and the parameter-independent factors
+        const int64_t gi = i0 + r0;
+        double wk[8][4]; // SE-ARD: w*f*k ; others unused
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int64_t gj = j0 + h * 64 + c * 8 + 2 * lj;
+            const double2 kv0 = *reinterpret_cast<const double2*>(&Kinv[gi + gj * Np]);
+            const double2 kv1 = *reinterpret_cast<const double2*>(&Kinv[gi + (gj + 1) * Np]);
+            const double kin[4] = {kv0.x, kv0.y, kv1.x, kv1.y};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t ii = gi + (e & 1), jj = gj + (e >> 1);
+                double w = -kin[e];
+                for (int p = 0; p < P; ++p) w = fma(alpha[ii + (int64_t)p * Np], alpha[jj + (int64_t)p * Np], w);
+                double f = (ii == jj) ? 0.5 : ((ii > jj) ? 1.0 : 0.0);
+                if (ii >= N || jj >= N) f = 0.0;
+                w *= f;
+                const double zz = z[c][e];
+                if (ard) { // squared_exp_ard.hpp:127-135
+                    double k = kp.sf2 * exp(-0.5 * zz);
+                    wk[c][e] = w * k;
+                    g_sf = fma(w, 2.0 * k, g_sf);
+                }
+                else {
+                    wk[c][e] = 0.0;
+                    double g0, g1;
+                    if (kp.id == LB_K_MATERN52) { // matern_five_halves.hpp:115-133
+                        double d = sqrt(zz), d_sq = d * d, l_sq = kp.l * kp.l;
+                        double term1 = sqrt(5.0) * d / kp.l;
+                        double term2 = 5. * d_sq / (3. * l_sq);
+                        double r = exp(-term1);
+                        g0 = kp.sf2 * (r * term1 * (1 + term1 + term2) + (-term1 - 2. * term2) * r);
+                        g1 = 2 * kp.sf2 * (1 + term1 + term2) * r;
+                    }
+                    else if (kp.id == LB_K_MATERN32) { // matern_three_halves.hpp:110-124
+                        double d = sqrt(zz);
+                        double term = sqrt(3.0) * d / kp.l;
+                        double r = exp(-term);
+                        g0 = kp.sf2 * (-term * r + (1 + term) * term * r);
+                        g1 = 2 * kp.sf2 * (1 + term) * r;
+                    }
+                    else { // exp.hpp:101-110
+                        double r = zz / (kp.l * kp.l);
+                        double k = kp.sf2 * exp(-0.5 * r);
+                        g0 = r * k;
+                        g1 = 2 * k;
+                    }
+                    g_l = fma(w, g0, g_l);
+                    g_sf = fma(w, g1, g_sf);
+                }
+                if (ii == jj) g_noise = fma(w, 2.0 * kp.noise, g_noise); // kernel.hpp:90-93
+            }
+        }
+        if (ard) {
+            // second sweep over the input dimensions: g_d += w k q_d^2
+            for (int pass = 0; pass < npass; ++pass) {
+                int dc;
+                if (npass > 1) dc = stage(pass);
+                else dc = D;
+                const int d0 = pass * DCH;
+                double gd[DCH];
+#pragma unroll
+                for (int d = 0; d < DCH; ++d) gd[d] = 0.0;
+#pragma unroll
+                for (int d = 0; d < DCH; ++d) {
+                    if (d < dc) {
+                        const double2 xi = *reinterpret_cast<const double2*>(&sxi[d][r0]);
+                        double s = 0.0;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const double2 xj = *reinterpret_cast<const double2*>(&sxj[d][h * 64 + c * 8 + 2 * lj]);
+                            double q;
+                            q = xi.x - xj.x; s = fma(wk[c][0], q * q, s);
+                            q = xi.y - xj.x; s = fma(wk[c][1], q * q, s);
+                            q = xi.x - xj.y; s = fma(wk[c][2], q * q, s);
+                            q = xi.y - xj.y; s = fma(wk[c][3], q * q, s);
+                        }
+                        gd[d] = s;
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < DCH; ++d) {
+                    double s = lb_warp_sum(gd[d]);
+                    if (lane == 0) sred[warp][d] = s;
+                }
+                __syncthreads();
+                if (tid < dc) {
+                    double s = 0.0;
+                    for (int w = 0; w < 8; ++w) s += sred[w][tid];
+                    stot[d0 + tid] += s;
+                }
+                __syncthreads();
+            }
+        }
+    }
+    // scalar parts
+    g_sf = lb_warp_sum(g_sf);
+    g_l = lb_warp_sum(g_l);
+    g_noise = lb_warp_sum(g_noise);
+    __syncthreads();
+    if (lane == 0) { sred[warp][0] = g_sf; sred[warp][1] = g_l; sred[warp][2] = g_noise; }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0, b = 0, c = 0;
+        for (int w = 0; w < 8; ++w) { a += sred[w][0]; b += sred[w][1]; c += sred[w][2]; }
+        double* out = part + (int64_t)blockIdx.x * nh;
+        if (ard) {
+            for (int d = 0; d < D; ++d) out[d] = stot[d];
+            out[D] = a;
+            if (optimize_noise) out[D + 1] = c;
+        }
+        else {
+            out[0] = b;
+            out[1] = a;
+            if (optimize_noise) out[2] = c;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+grad_reduce_kernel(const double* __restrict__ part, int ntiles, int nh, double* __restrict__ grad)
+{
+    __shared__ double red[8];
+    const int q = blockIdx.x;
+    double s = 0.0;
+    for (int t = threadIdx.x; t < ntiles; t += 256) s += part[(int64_t)t * nh + q];
+    s = lb_warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        grad[q] = t;
+    }
+}
+
+constexpr size_t TRTRI_SMEM = (size_t)lbg::STAGES * lbg::STAGE_DOUBLES * sizeof(double) + (size_t)128 * (lbg::BM + 4) * sizeof(double);
+
+bool g_attr_done = false;
+int set_attrs()
+{
+    if (g_attr_done) return LB_OK;
+    LB_CUDA(cudaFuncSetAttribute(trtri_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
+    LB_CUDA(cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::PIPE_BYTES));
+    g_attr_done = true;
+    return LB_OK;
+}
+
+} // namespace
+
+int lb_launch_loglik(lb_gp* h, double* dOut)
+{
+    loglik_kernel<<<1, 1024, 0, h->stream>>>(h->dL, h->Np, h->N, h->dY, h->dAlpha, h->P, dOut);
+    h->launches++;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+int lb_launch_linv(lb_gp* h)
+{
+    int rc = set_attrs();
+    if (rc) return rc;
+    const int T = (int)(h->Np / LB_TILE);
+    if (!h->dLinv) {
+        LB_CUDA(cudaMalloc(&h->dLinv, sizeof(double) * h->Np * h->Np));
+        LB_CUDA(cudaMemsetAsync(h->dLinv, 0, sizeof(double) * h->Np * h->Np, h->stream));
+    }
+    for (int i = 0; i < T; ++i) {
+        trtri_row_kernel<<<i + 1, lbg::THREADS, TRTRI_SMEM, h->stream>>>(h->dL, h->Np, h->dInvD, h->dLinv, i);
+        h->launches++;
+    }
+    LB_CUDA(cudaGetLastError());
+    h->linv_valid = true;
+    return LB_OK;
+}
+
+int lb_launch_kinv(lb_gp* h)
+{
+    int rc = set_attrs();
+    if (rc) return rc;
+    if (!h->linv_valid) {
+        rc = lb_launch_linv(h);
+        if (rc) return rc;
+    }
+    const int T = (int)(h->Np / LB_TILE);
+    if (!h->dKinv) LB_CUDA(cudaMalloc(&h->dKinv, sizeof(double) * h->Np * h->Np));
+    lauum_kernel<<<T * (T + 1) / 2, lbg::THREADS, lbg::PIPE_BYTES, h->stream>>>(h->dLinv, h->Np, h->dKinv, T);
+    h->launches++;
+    LB_CUDA(cudaGetLastError());
+    h->kinv_valid = true;
+    return LB_OK;
+}
+
+int lb_launch_symmetrize(lb_gp* h, double* dA)
+{
+    dim3 grid((unsigned)(h->Np / 32), (unsigned)(h->Np / 32));
+    symmetrize_kernel<<<grid, dim3(32, 8), 0, h->stream>>>(dA, h->Np);
+    h->launches++;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+int lb_launch_grad(lb_gp* h, int optimize_noise, double* dGrad)
+{
+    const int T = (int)(h->Np / LB_TILE);
+    const int ntiles = T * (T + 1) / 2;
+    const int nh = h->n_hparams + (optimize_noise ? 1 : 0);
+    int rc = lb_ensure_scratch(h, sizeof(double) * (size_t)ntiles * nh);
+    if (rc) return rc;
+    grad_kernel<<<ntiles, 256, 0, h->stream>>>(h->dXs, h->dKinv, h->dAlpha, h->P, h->N, h->Np, h->kp, optimize_noise, nh,
+        h->dScratch);
+    grad_reduce_kernel<<<nh, 256, 0, h->stream>>>(h->dScratch, ntiles, nh, dGrad);
+    h->launches += 2;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}

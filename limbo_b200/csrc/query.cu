@@ -1,0 +1,310 @@
+// limbo_b200/csrc/query.cu — batched GP prediction and acquisition.
+//
+// Replaces, for a batch of M candidates at once, the one-point-at-a-time
+//   GP::_compute_k (model/gp.hpp:626-632)   -> kstar_kernel      (K* = k(X, Xq), N x M)
+//   GP::_mu        (model/gp.hpp:613-616)   -> mu_kernel         (K*^T alpha)
+//   GP::_sigma     (model/gp.hpp:618-624)   -> query_step_kernel (V = L^-1 K*, blocked TRSM on DMMA)
+//                                              + colnorm_kernel  (k(v,v) - |V_m|^2, clamp, + noise gp.hpp:166)
+//   acqui::UCB / GP_UCB / EI (acqui/ucb.hpp:83-90, gp_ucb.hpp:96-103, ei.hpp:85-116)
+//                                           -> acq_kernel + argmax reduction
+#include "gemm.cuh"
+#include <cfloat>
+
+namespace {
+
+constexpr int DCH = 16;
+
+// K*[n, m] = k(x_n, q_m), no noise (kernel.hpp:81-84 with i=-1, j=-2).
+// grid: (Np/128, Mp/128); V is Np x Mp column-major (ld = Np).
+__global__ void __launch_bounds__(256, 2)
+kstar_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, const double* __restrict__ Qs, int64_t Mp,
+    int64_t M, double* __restrict__ V, KernParams kp)
+{
+    __shared__ __align__(128) double sxi[DCH][LB_TILE];
+    __shared__ __align__(128) double sxj[DCH][LB_TILE];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int li = lane & 7, lj = lane >> 3;
+    const int D = kp.D;
+    const int64_t i0 = (int64_t)blockIdx.x * LB_TILE, j0 = (int64_t)blockIdx.y * LB_TILE;
+    const int r0 = warp * 16 + 2 * li;
+    if (tid == 0) {
+        lb_mbar_init(&bar, 1);
+        lb_fence_barrier_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    const int npass = (D + DCH - 1) / DCH;
+    for (int h = 0; h < 2; ++h) {
+        double z[8][4];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) z[c][e] = 0.0;
+        for (int pass = 0; pass < npass; ++pass) {
+            const int d0 = pass * DCH;
+            const int dc = min(DCH, D - d0);
+            if (!(npass == 1 && h == 1)) {
+                __syncthreads();
+                if (tid == 0) {
+                    lb_fence_proxy_async();
+                    lb_mbar_expect_tx(&bar, (uint32_t)(2 * dc * LB_TILE * sizeof(double)));
+                    for (int d = 0; d < dc; ++d) {
+                        lb_bulk_g2s(&sxi[d][0], Xs + (int64_t)(d0 + d) * Np + i0, LB_TILE * sizeof(double), &bar);
+                        lb_bulk_g2s(&sxj[d][0], Qs + (int64_t)(d0 + d) * Mp + j0, LB_TILE * sizeof(double), &bar);
+                    }
+                }
+                lb_mbar_wait(&bar, phase);
+                phase ^= 1;
+            }
+            for (int d = 0; d < dc; ++d) {
+                const double2 xi = *reinterpret_cast<const double2*>(&sxi[d][r0]);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const double2 xj = *reinterpret_cast<const double2*>(&sxj[d][h * 64 + c * 8 + 2 * lj]);
+                    double q;
+                    q = xi.x - xj.x; z[c][0] = fma(q, q, z[c][0]);
+                    q = xi.y - xj.x; z[c][1] = fma(q, q, z[c][1]);
+                    q = xi.x - xj.y; z[c][2] = fma(q, q, z[c][2]);
+                    q = xi.y - xj.y; z[c][3] = fma(q, q, z[c][3]);
+                }
+            }
+        }
+        const int64_t gi = i0 + r0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int64_t gj = j0 + h * 64 + c * 8 + 2 * lj;
+            double v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t ii = gi + (e & 1), jj = gj + (e >> 1);
+                double k = lb_kernel_from_z(kp.id, z[c][e], kp.sf2, kp.l);
+                if (ii >= N || jj >= M) k = 0.0;
+                v[e] = k;
+            }
+            *reinterpret_cast<double2*>(&V[gi + gj * Np]) = make_double2(v[0], v[1]);
+            *reinterpret_cast<double2*>(&V[gi + (gj + 1) * Np]) = make_double2(v[2], v[3]);
+        }
+    }
+}
+
+// mu[m*P + p] = sum_n K*[n,m] alpha[n,p]   (one CTA per candidate, fixed order -> deterministic)
+__global__ void __launch_bounds__(256)
+mu_kernel(const double* __restrict__ V, int64_t Np, const double* __restrict__ alpha, int P, double* __restrict__ mu)
+{
+    __shared__ double red[8];
+    const int64_t m = blockIdx.x;
+    const double* col = V + m * Np;
+    for (int p = 0; p < P; ++p) {
+        const double* a = alpha + (int64_t)p * Np;
+        double s = 0.0;
+        for (int64_t n = threadIdx.x; n < Np; n += 256) s = fma(col[n], a[n], s);
+        s = lb_warp_sum(s);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += red[w];
+            mu[m * P + p] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// One block-row step of V <- L^-1 V:
+//   V_i <- inv(L_ii) * (V_i - L[i, 0:i] V[0:i])          grid = Mp / BN
+template <int BN>
+__global__ void __launch_bounds__(lbg::THREADS, 1)
+query_step_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ invD, double* __restrict__ V,
+    int i)
+{
+    extern __shared__ __align__(16) double smem[];
+    constexpr int PB = lbg::BM + 4;
+    double* sT = smem + lbg::STAGES * lbg::STAGE_DOUBLES; // overlays the B pipeline stages
+    const int64_t col0 = (int64_t)blockIdx.x * BN;
+    double* Vc = V + col0 * ld;
+    lbg::Acc<BN> acc;
+    acc.zero();
+    if (i > 0) lbg::mainloop<BN, false, true>(acc, L + (int64_t)i * LB_TILE, ld, Vc, ld, i * LB_TILE, smem);
+    // t = V_i - acc  -> smem [n][k]
+    double* Vi = Vc + (int64_t)i * LB_TILE;
+    lbg::for_each_acc<BN>(acc, [&](int r, int c, double v) { sT[c * PB + r] = Vi[r + (int64_t)c * ld] - v; });
+    __syncthreads();
+    lbg::Acc<BN> acc2;
+    acc2.zero();
+    lbg::mainloop_resB<BN>(acc2, invD + (int64_t)i * LB_TILE * LB_TILE, LB_TILE, sT, smem);
+    lbg::for_each_acc<BN>(acc2, [&](int r, int c, double v) { Vi[r + (int64_t)c * ld] = v; });
+}
+
+// sigma2[m] = k(v,v) - |V_m|^2, clamped (gp.hpp:623), + noise (gp.hpp:166)
+__global__ void __launch_bounds__(256)
+colnorm_kernel(const double* __restrict__ V, int64_t Np, double kvv, double noise, double* __restrict__ s2)
+{
+    __shared__ double red[8];
+    const int64_t m = blockIdx.x;
+    const double* col = V + m * Np;
+    double s = 0.0;
+    for (int64_t n = threadIdx.x; n < Np; n += 256) { double v = col[n]; s = fma(v, v, s); }
+    s = lb_warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        double res = kvv - t;
+        res = (res <= DBL_EPSILON) ? 0.0 : res;
+        s2[m] = res + noise;
+    }
+}
+
+// acquisition value per candidate (FirstElem aggregator, bo_base.hpp:99-105)
+//   acq_id 0: UCB / GP_UCB  mu + p0 * sqrt(s2)                 ucb.hpp:89, gp_ucb.hpp:102
+//   acq_id 1: EI  (p0 = f_max, p1 = jitter)                    ei.hpp:92-115
+__device__ __forceinline__ double acq_value(int acq_id, double mu, double s2, double p0, double p1)
+{
+    if (acq_id == 0) return mu + p0 * sqrt(s2);
+    double sigma = sqrt(s2);
+    if (sigma < 1e-10) return 0.0;
+    double X = mu - p0 - p1;
+    double Z = X / sigma;
+    double phi = exp(-0.5 * (Z * Z)) / sqrt(2.0 * M_PI);
+    double Phi = 0.5 * erfc(-Z / sqrt(2.0));
+    return X * Phi + sigma * phi;
+}
+
+__global__ void __launch_bounds__(256)
+acq_kernel(int acq_id, double p0, double p1, int64_t M, const double* __restrict__ mu0, int mu_stride,
+    const double* __restrict__ mean_at_q, double mean_const, const double* __restrict__ s2, double* __restrict__ acq,
+    double* __restrict__ blk_val, long long* __restrict__ blk_idx)
+{
+    __shared__ double sv[256];
+    __shared__ long long si[256];
+    int64_t m = blockIdx.x * (int64_t)256 + threadIdx.x;
+    double v = -DBL_MAX;
+    long long idx = LLONG_MAX;
+    if (m < M) {
+        double mu = mu0[m * mu_stride] + (mean_at_q ? mean_at_q[m] : mean_const);
+        v = acq_value(acq_id, mu, s2[m], p0, p1);
+        if (acq) acq[m] = v;
+        idx = m;
+        if (!(v == v)) { v = -DBL_MAX; } // NaN never wins
+    }
+    sv[threadIdx.x] = v;
+    si[threadIdx.x] = idx;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            double v2 = sv[threadIdx.x + o];
+            long long i2 = si[threadIdx.x + o];
+            if (v2 > sv[threadIdx.x] || (v2 == sv[threadIdx.x] && i2 < si[threadIdx.x])) {
+                sv[threadIdx.x] = v2;
+                si[threadIdx.x] = i2;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        blk_val[blockIdx.x] = sv[0];
+        blk_idx[blockIdx.x] = si[0];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+argmax_final_kernel(int nblk, const double* __restrict__ blk_val, const long long* __restrict__ blk_idx,
+    double* __restrict__ best_val, long long* __restrict__ best_idx)
+{
+    __shared__ double sv[256];
+    __shared__ long long si[256];
+    double v = -DBL_MAX;
+    long long idx = LLONG_MAX;
+    for (int b = threadIdx.x; b < nblk; b += 256) {
+        double v2 = blk_val[b];
+        long long i2 = blk_idx[b];
+        if (v2 > v || (v2 == v && i2 < idx)) { v = v2; idx = i2; }
+    }
+    sv[threadIdx.x] = v;
+    si[threadIdx.x] = idx;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            double v2 = sv[threadIdx.x + o];
+            long long i2 = si[threadIdx.x + o];
+            if (v2 > sv[threadIdx.x] || (v2 == sv[threadIdx.x] && i2 < si[threadIdx.x])) {
+                sv[threadIdx.x] = v2;
+                si[threadIdx.x] = i2;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        *best_val = sv[0];
+        *best_idx = si[0];
+    }
+}
+
+template <int BN>
+constexpr size_t step_smem()
+{
+    return (size_t)lbg::STAGES * lbg::STAGE_DOUBLES * sizeof(double)
+        + ((size_t)BN * (lbg::BM + 4) * sizeof(double) > (size_t)lbg::STAGES * lbg::STAGE_DOUBLES * sizeof(double)
+                  ? (size_t)BN * (lbg::BM + 4) * sizeof(double)
+                  : (size_t)lbg::STAGES * lbg::STAGE_DOUBLES * sizeof(double));
+}
+
+bool g_attr_done = false;
+int set_attrs()
+{
+    if (g_attr_done) return LB_OK;
+    LB_CUDA(cudaFuncSetAttribute(query_step_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<128>()));
+    LB_CUDA(cudaFuncSetAttribute(query_step_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<64>()));
+    g_attr_done = true;
+    return LB_OK;
+}
+
+} // namespace
+
+// Blocked V <- L^-1 V for a Np x Mp right-hand side (also used by K^-1).
+int lb_launch_trsm_lower(const lb_gp* h, cudaStream_t st, double* dV, int64_t Mp, int i_begin, long long* launches)
+{
+    int rc = set_attrs();
+    if (rc) return rc;
+    const int T = (int)(h->Np / LB_TILE);
+    const bool wide = (Mp / 128) >= 120;
+    for (int i = i_begin; i < T; ++i) {
+        if (wide)
+            query_step_kernel<128><<<(unsigned)(Mp / 128), lbg::THREADS, step_smem<128>(), st>>>(h->dL, h->Np, h->dInvD, dV, i);
+        else
+            query_step_kernel<64><<<(unsigned)(Mp / 64), lbg::THREADS, step_smem<64>(), st>>>(h->dL, h->Np, h->dInvD, dV, i);
+        if (launches) ++*launches;
+    }
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+int lb_launch_query(const lb_gp* h, cudaStream_t st, int64_t M, const double* dQs, int64_t Mp, double* dV, double* dMu,
+    double* dS2, long long* launches)
+{
+    dim3 grid((unsigned)(h->Np / LB_TILE), (unsigned)(Mp / LB_TILE));
+    kstar_kernel<<<grid, 256, 0, st>>>(h->dXs, h->Np, h->N, dQs, Mp, M, dV, h->kp);
+    mu_kernel<<<(unsigned)M, 256, 0, st>>>(dV, h->Np, h->dAlpha, h->P, dMu);
+    if (launches) *launches += 2;
+    int rc = lb_launch_trsm_lower(h, st, dV, Mp, 0, launches);
+    if (rc) return rc;
+    const double kvv = h->kp.sf2; // every kernel here has k(v,v) = sigma_f^2
+    colnorm_kernel<<<(unsigned)M, 256, 0, st>>>(dV, h->Np, kvv, h->kp.noise, dS2);
+    if (launches) ++*launches;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+int lb_launch_acq_full(cudaStream_t st, int acq_id, double p0, double p1, int64_t M, const double* dMu, int mu_stride,
+    const double* dMeanAtQ, double mean_const, const double* dS2, double* dAcq, double* dBlkVal, long long* dBlkIdx,
+    double* dBestVal, long long* dBestIdx, long long* launches)
+{
+    const int nblk = (int)((M + 255) / 256);
+    acq_kernel<<<nblk, 256, 0, st>>>(acq_id, p0, p1, M, dMu, mu_stride, dMeanAtQ, mean_const, dS2, dAcq, dBlkVal, dBlkIdx);
+    argmax_final_kernel<<<1, 256, 0, st>>>(nblk, dBlkVal, dBlkIdx, dBestVal, dBestIdx);
+    if (launches) *launches += 2;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}

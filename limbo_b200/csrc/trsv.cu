@@ -1,0 +1,231 @@
+// limbo_b200/csrc/trsv.cu — blocked triangular solves with few right-hand sides
+// (HBM-read bound: every byte of the lower triangle of L is read once per
+// direction).
+//
+// Replaces GP::_compute_alpha (model/gp.hpp:605-611):
+//     alpha = L^-1 obs_mean ; alpha = L^-T alpha
+// One persistent launch per direction: CTA i owns the 128-row block i,
+// accumulates  b_i - sum_j L[i,j] x_j  as the x_j become available (progress
+// flags in global memory, acquire/release through L2), then applies the
+// pre-inverted diagonal block.  Block ids are handed out by an atomic ticket so
+// a CTA only ever waits on CTAs that started before it (no deadlock, and the
+// spin is bounded: on timeout info[1] is set and LB_ERR_TIMEOUT returned).
+#include "common.cuh"
+
+namespace {
+
+constexpr int NR = 2; // right-hand sides per launch
+constexpr long long SPIN_LIMIT = 1LL << 24;
+
+__device__ __forceinline__ int ld_acquire(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ bool wait_flag(const int* flag, int* info)
+{
+    long long spins = 0;
+    while (ld_acquire(flag) == 0) {
+        __nanosleep(40);
+        if (++spins > SPIN_LIMIT) {
+            atomicExch(info + 1, 1);
+            return false;
+        }
+    }
+    return true;
+}
+
+// forward: solve L x = b in place (B: Np x nr, column-major, ld = ldb)
+__global__ void __launch_bounds__(256, 1)
+trsv_fwd_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ invD, double* __restrict__ B,
+    int64_t ldb, int nr, int T, int* __restrict__ flags, int* __restrict__ info)
+{
+    __shared__ double xs[NR][LB_TILE];
+    __shared__ double part[2][NR][LB_TILE];
+    __shared__ int s_i;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_i = atomicAdd(&flags[T], 1);
+    __syncthreads();
+    const int i = s_i;
+    const int r = tid & 127, q = tid >> 7;
+    double acc[NR];
+#pragma unroll
+    for (int p = 0; p < NR; ++p) acc[p] = 0.0;
+
+    for (int j = 0; j < i; ++j) {
+        // issue the loads of L[i,j] before waiting on x_j
+        const double* Lt = L + (int64_t)i * LB_TILE + r + ((int64_t)j * LB_TILE + q * 64) * ld;
+        double lv[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) lv[c] = __ldcs(Lt + (int64_t)c * ld);
+        if (tid == 0) wait_flag(&flags[j], info);
+        __syncthreads();
+        for (int idx = tid; idx < nr * LB_TILE; idx += 256) {
+            int p = idx >> 7, c = idx & 127;
+            xs[p][c] = __ldcg(B + (int64_t)j * LB_TILE + c + (int64_t)p * ldb);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < NR; ++p) {
+            if (p < nr) {
+                double s = acc[p];
+#pragma unroll
+                for (int c = 0; c < 64; ++c) s = fma(lv[c], xs[p][q * 64 + c], s);
+                acc[p] = s;
+            }
+        }
+        __syncthreads(); // xs reused next iteration
+    }
+#pragma unroll
+    for (int p = 0; p < NR; ++p) part[q][p][r] = acc[p];
+    __syncthreads();
+    // rhs block: b_i - sum
+    for (int idx = tid; idx < nr * LB_TILE; idx += 256) {
+        int p = idx >> 7, c = idx & 127;
+        xs[p][c] = B[(int64_t)i * LB_TILE + c + (int64_t)p * ldb] - (part[0][p][c] + part[1][p][c]);
+    }
+    __syncthreads();
+    // x_i = invD_i * rhs
+    const double* Di = invD + (int64_t)i * LB_TILE * LB_TILE + r + (int64_t)(q * 64) * LB_TILE;
+#pragma unroll
+    for (int p = 0; p < NR; ++p) acc[p] = 0.0;
+#pragma unroll 16
+    for (int c = 0; c < 64; ++c) {
+        double dv = Di[(int64_t)c * LB_TILE];
+#pragma unroll
+        for (int p = 0; p < NR; ++p)
+            if (p < nr) acc[p] = fma(dv, xs[p][q * 64 + c], acc[p]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < NR; ++p) part[q][p][r] = acc[p];
+    __syncthreads();
+    for (int idx = tid; idx < nr * LB_TILE; idx += 256) {
+        int p = idx >> 7, c = idx & 127;
+        B[(int64_t)i * LB_TILE + c + (int64_t)p * ldb] = part[0][p][c] + part[1][p][c];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release(&flags[i], 1);
+}
+
+// backward: solve L^T x = y in place
+__global__ void __launch_bounds__(256, 1)
+trsv_bwd_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ invD, double* __restrict__ B,
+    int64_t ldb, int nr, int T, int* __restrict__ flags, int* __restrict__ info)
+{
+    __shared__ double xs[NR][LB_TILE];
+    __shared__ double red[NR][LB_TILE];
+    __shared__ int s_i;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_i = T - 1 - atomicAdd(&flags[T], 1);
+    __syncthreads();
+    const int i = s_i;
+    // warp w owns columns c = w + 8*cc (cc = 0..15) of the block column i
+    double acc[NR][16];
+#pragma unroll
+    for (int p = 0; p < NR; ++p)
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) acc[p][cc] = 0.0;
+
+    for (int j = T - 1; j > i; --j) {
+        const double* Lt = L + (int64_t)j * LB_TILE + lane + ((int64_t)i * LB_TILE + warp) * ld;
+        double lv[16][4];
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) lv[cc][s] = __ldcs(Lt + 32 * s + (int64_t)(8 * cc) * ld);
+        if (tid == 0) wait_flag(&flags[j], info);
+        __syncthreads();
+        for (int idx = tid; idx < nr * LB_TILE; idx += 256) {
+            int p = idx >> 7, c = idx & 127;
+            xs[p][c] = __ldcg(B + (int64_t)j * LB_TILE + c + (int64_t)p * ldb);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < NR; ++p) {
+            if (p < nr) {
+                double xv[4];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) xv[s] = xs[p][lane + 32 * s];
+#pragma unroll
+                for (int cc = 0; cc < 16; ++cc)
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) acc[p][cc] = fma(lv[cc][s], xv[s], acc[p][cc]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int p = 0; p < NR; ++p)
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) {
+            double s = lb_warp_sum(acc[p][cc]);
+            if (lane == 0) red[p][warp + 8 * cc] = s;
+        }
+    __syncthreads();
+    for (int idx = tid; idx < nr * LB_TILE; idx += 256) {
+        int p = idx >> 7, c = idx & 127;
+        xs[p][c] = B[(int64_t)i * LB_TILE + c + (int64_t)p * ldb] - red[p][c];
+    }
+    __syncthreads();
+    // x_i = invD_i^T * rhs : column dot products
+    const double* Di = invD + (int64_t)i * LB_TILE * LB_TILE;
+#pragma unroll
+    for (int p = 0; p < NR; ++p) {
+        if (p < nr) {
+            for (int cc = 0; cc < 16; ++cc) {
+                const int c = warp + 8 * cc;
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s = fma(Di[lane + 32 * k + c * LB_TILE], xs[p][lane + 32 * k], s);
+                s = lb_warp_sum(s);
+                if (lane == 0) red[p][c] = s;
+            }
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nr * LB_TILE; idx += 256) {
+        int p = idx >> 7, c = idx & 127;
+        B[(int64_t)i * LB_TILE + c + (int64_t)p * ldb] = red[p][c];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release(&flags[i], 1);
+}
+
+} // namespace
+
+// Solve with the factor held by h, in place on dB (Np x nrhs, ld = Np).
+int lb_launch_trsv(lb_gp* h, double* dB, int nrhs, bool forward)
+{
+    const int T = (int)(h->Np / LB_TILE);
+    for (int p0 = 0; p0 < nrhs; p0 += NR) {
+        const int nr = (nrhs - p0 < NR) ? (nrhs - p0) : NR;
+        LB_CUDA(cudaMemsetAsync(h->dFlags, 0, (T + 1) * sizeof(int), h->stream));
+        if (forward)
+            trsv_fwd_kernel<<<T, 256, 0, h->stream>>>(h->dL, h->Np, h->dInvD, dB + (int64_t)p0 * h->Np, h->Np, nr, T,
+                h->dFlags, h->dInfo);
+        else
+            trsv_bwd_kernel<<<T, 256, 0, h->stream>>>(h->dL, h->Np, h->dInvD, dB + (int64_t)p0 * h->Np, h->Np, nr, T,
+                h->dFlags, h->dInfo);
+        h->launches++;
+    }
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+int lb_launch_solve_alpha(lb_gp* h)
+{
+    // alpha = obs_mean ; L^-1 ; L^-T      (gp.hpp:608-610)
+    LB_CUDA(cudaMemcpyAsync(h->dAlpha, h->dY, sizeof(double) * h->Np * h->P, cudaMemcpyDeviceToDevice, h->stream));
+    int rc = lb_launch_trsv(h, h->dAlpha, h->P, true);
+    if (rc) return rc;
+    return lb_launch_trsv(h, h->dAlpha, h->P, false);
+}

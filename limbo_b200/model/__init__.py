@@ -1,0 +1,2 @@
+from .gp import GP, GPBasic, GPOpt  # noqa: F401
+from .hp_opt import KernelLFOpt, NoLFOpt  # noqa: F401
