@@ -27,6 +27,38 @@ void lb_set_last_cuda_error(cudaError_t e, const char* file, int line)
     cudaGetLastError(); // clear sticky-less errors
 }
 
+#include <vector>
+struct Profiler {
+    struct Rec { cudaEvent_t a, b; int cls; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t cur[LB_PC_COUNT] = {};
+    double ms[LB_PC_COUNT] = {};
+    long long n[LB_PC_COUNT] = {};
+    std::mutex mu;
+    cudaEvent_t get()
+    {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+};
+void lb_prof_begin(const lb_gp* h, cudaStream_t st, int cls)
+{
+    Profiler* p = (Profiler*)h->prof;
+    std::lock_guard<std::mutex> lk(p->mu);
+    cudaEvent_t e = p->get();
+    cudaEventRecord(e, st);
+    p->cur[cls] = e;
+}
+void lb_prof_end(const lb_gp* h, cudaStream_t st, int cls)
+{
+    Profiler* p = (Profiler*)h->prof;
+    std::lock_guard<std::mutex> lk(p->mu);
+    cudaEvent_t e = p->get();
+    cudaEventRecord(e, st);
+    p->recs.push_back({p->cur[cls], e, cls});
+}
+
 namespace {
 
 struct QueryWs { // per-handle query workspace (guarded by qmutex)
@@ -225,6 +257,7 @@ int lb_ensure_scratch(lb_gp* h, size_t bytes)
 }
 
 extern "C" {
+int lb_profile_enable(lb_gp* h, int on);
 
 int lb_create(lb_gp** out, int device, int precision)
 {
@@ -260,6 +293,7 @@ int lb_destroy(lb_gp* hh)
     lb_gp_full* h = full(hh);
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    lb_profile_enable(h, 0);
     free_model(h);
     free_ws(h->ex.ws);
     cudaFree(h->dInfo);
@@ -719,6 +753,42 @@ int lb_clone(const lb_gp* src, lb_gp** out)
         if (cudaStreamSynchronize(st) != cudaSuccess) { lb_destroy(h); return LB_ERR_CUDA; }
     }
     *out = h;
+    return LB_OK;
+}
+
+// per-kernel-class event timing for bench.py's roofline (not part of the reference-facing header)
+int lb_profile_enable(lb_gp* h, int on)
+{
+    if (!h) return LB_ERR_ARG;
+    if (on && !h->prof) h->prof = new Profiler();
+    if (!on && h->prof) {
+        cudaStreamSynchronize(h->stream);
+        Profiler* p = (Profiler*)h->prof;
+        for (auto& r : p->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        for (auto e : p->pool) cudaEventDestroy(e);
+        delete p;
+        h->prof = nullptr;
+    }
+    return LB_OK;
+}
+// accumulates finished records; ms_out / count_out have LB_PC_COUNT entries; reset != 0 clears the totals
+int lb_profile_read(lb_gp* h, double* ms_out, long long* count_out, int reset)
+{
+    if (!h || !h->prof) return LB_ERR_STATE;
+    Profiler* p = (Profiler*)h->prof;
+    LB_CUDA(cudaStreamSynchronize(h->stream));
+    std::lock_guard<std::mutex> lk(p->mu);
+    for (auto& r : p->recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { p->ms[r.cls] += ms; p->n[r.cls]++; }
+        p->pool.push_back(r.a); p->pool.push_back(r.b);
+    }
+    p->recs.clear();
+    for (int c = 0; c < LB_PC_COUNT; ++c) {
+        if (ms_out) ms_out[c] = p->ms[c];
+        if (count_out) count_out[c] = p->n[c];
+        if (reset) { p->ms[c] = 0; p->n[c] = 0; }
+    }
     return LB_OK;
 }
 

@@ -195,6 +195,18 @@ struct lb_gp {
 
     // counters for bench.py ("gpu_launches")
     long long launches = 0;
+    void* prof = nullptr; // Profiler* when per-kernel-class event timing is enabled (abi.cu)
+};
+
+// per-kernel-class CUDA-event timing (bench.py roofline): no-ops unless enabled
+enum { LB_PC_KBUILD = 0, LB_PC_POTF2, LB_PC_TRSM_PANEL, LB_PC_SYRK, LB_PC_TRSV, LB_PC_KSTAR, LB_PC_QSTEP, LB_PC_QREDUCE,
+    LB_PC_ACQ, LB_PC_TRTRI, LB_PC_LAUUM, LB_PC_GRAD, LB_PC_OTHER, LB_PC_COUNT };
+void lb_prof_begin(const lb_gp* h, cudaStream_t st, int cls);
+void lb_prof_end(const lb_gp* h, cudaStream_t st, int cls);
+struct LbProfScope {
+    const lb_gp* h; cudaStream_t st; int cls;
+    LbProfScope(const lb_gp* h_, cudaStream_t st_, int c) : h(h_), st(st_), cls(c) { if (h->prof) lb_prof_begin(h, st, cls); }
+    ~LbProfScope() { if (h->prof) lb_prof_end(h, st, cls); }
 };
 
 // internal entry points (one per .cu)

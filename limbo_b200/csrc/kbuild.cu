@@ -137,6 +137,7 @@ int lb_launch_kbuild(lb_gp* h, double* dK)
 {
     const int64_t T = h->Np / LB_TILE;
     const int64_t tiles = T * (T + 1) / 2;
+    LbProfScope ps(h, h->stream, LB_PC_KBUILD);
     kbuild_kernel<<<(unsigned)tiles, 256, 0, h->stream>>>(h->dXs, dK, h->N, h->Np, h->kp);
     h->launches++;
     LB_CUDA(cudaGetLastError());

@@ -366,6 +366,7 @@ int lb_launch_linv(lb_gp* h)
         LB_CUDA(cudaMalloc(&h->dLinv, sizeof(double) * h->Np * h->Np));
         LB_CUDA(cudaMemsetAsync(h->dLinv, 0, sizeof(double) * h->Np * h->Np, h->stream));
     }
+    LbProfScope ps(h, h->stream, LB_PC_TRTRI);
     for (int i = 0; i < T; ++i) {
         trtri_row_kernel<<<i + 1, lbg::THREADS, TRTRI_SMEM, h->stream>>>(h->dL, h->Np, h->dInvD, h->dLinv, i);
         h->launches++;
@@ -385,6 +386,7 @@ int lb_launch_kinv(lb_gp* h)
     }
     const int T = (int)(h->Np / LB_TILE);
     if (!h->dKinv) LB_CUDA(cudaMalloc(&h->dKinv, sizeof(double) * h->Np * h->Np));
+    LbProfScope ps(h, h->stream, LB_PC_LAUUM);
     lauum_kernel<<<T * (T + 1) / 2, lbg::THREADS, lbg::PIPE_BYTES, h->stream>>>(h->dLinv, h->Np, h->dKinv, T);
     h->launches++;
     LB_CUDA(cudaGetLastError());
@@ -408,6 +410,7 @@ int lb_launch_grad(lb_gp* h, int optimize_noise, double* dGrad)
     const int nh = h->n_hparams + (optimize_noise ? 1 : 0);
     int rc = lb_ensure_scratch(h, sizeof(double) * (size_t)ntiles * nh);
     if (rc) return rc;
+    LbProfScope ps(h, h->stream, LB_PC_GRAD);
     grad_kernel<<<ntiles, 256, 0, h->stream>>>(h->dXs, h->dKinv, h->dAlpha, h->P, h->N, h->Np, h->kp, optimize_noise, nh,
         h->dScratch);
     grad_reduce_kernel<<<nh, 256, 0, h->stream>>>(h->dScratch, ntiles, nh, dGrad);

@@ -215,12 +215,21 @@ int lb_launch_potrf(lb_gp* h)
     const int T = (int)(h->Np / LB_TILE);
     LB_CUDA(cudaMemsetAsync(h->dInfo, 0, 2 * sizeof(int), h->stream));
     for (int k = 0; k < T; ++k) {
-        potf2_inv_kernel<<<1, 256, POTF2_SMEM, h->stream>>>(h->dL, h->Np, k, h->dInvD, h->dInfo, 1);
+        {
+            LbProfScope ps(h, h->stream, LB_PC_POTF2);
+            potf2_inv_kernel<<<1, 256, POTF2_SMEM, h->stream>>>(h->dL, h->Np, k, h->dInvD, h->dInfo, 1);
+        }
         h->launches++;
         const int n = T - k - 1;
         if (n > 0) {
-            trsm_panel_kernel<<<n, lbg::THREADS, lbg::PIPE_BYTES, h->stream>>>(h->dL, h->Np, k, h->dInvD);
-            syrk_kernel<<<n * (n + 1) / 2, lbg::THREADS, lbg::PIPE_BYTES, h->stream>>>(h->dL, h->Np, k);
+            {
+                LbProfScope ps(h, h->stream, LB_PC_TRSM_PANEL);
+                trsm_panel_kernel<<<n, lbg::THREADS, lbg::PIPE_BYTES, h->stream>>>(h->dL, h->Np, k, h->dInvD);
+            }
+            {
+                LbProfScope ps(h, h->stream, LB_PC_SYRK);
+                syrk_kernel<<<n * (n + 1) / 2, lbg::THREADS, lbg::PIPE_BYTES, h->stream>>>(h->dL, h->Np, k);
+            }
             h->launches += 2;
         }
     }

@@ -270,6 +270,7 @@ int lb_launch_trsm_lower(const lb_gp* h, cudaStream_t st, double* dV, int64_t Mp
     if (rc) return rc;
     const int T = (int)(h->Np / LB_TILE);
     const bool wide = (Mp / 128) >= 120;
+    LbProfScope ps(h, st, LB_PC_QSTEP);
     for (int i = i_begin; i < T; ++i) {
         if (wide)
             query_step_kernel<128><<<(unsigned)(Mp / 128), lbg::THREADS, step_smem<128>(), st>>>(h->dL, h->Np, h->dInvD, dV, i);
@@ -285,13 +286,22 @@ int lb_launch_query(const lb_gp* h, cudaStream_t st, int64_t M, const double* dQ
     double* dS2, long long* launches)
 {
     dim3 grid((unsigned)(h->Np / LB_TILE), (unsigned)(Mp / LB_TILE));
-    kstar_kernel<<<grid, 256, 0, st>>>(h->dXs, h->Np, h->N, dQs, Mp, M, dV, h->kp);
-    mu_kernel<<<(unsigned)M, 256, 0, st>>>(dV, h->Np, h->dAlpha, h->P, dMu);
+    {
+        LbProfScope ps(h, st, LB_PC_KSTAR);
+        kstar_kernel<<<grid, 256, 0, st>>>(h->dXs, h->Np, h->N, dQs, Mp, M, dV, h->kp);
+    }
+    {
+        LbProfScope ps(h, st, LB_PC_QREDUCE);
+        mu_kernel<<<(unsigned)M, 256, 0, st>>>(dV, h->Np, h->dAlpha, h->P, dMu);
+    }
     if (launches) *launches += 2;
     int rc = lb_launch_trsm_lower(h, st, dV, Mp, 0, launches);
     if (rc) return rc;
     const double kvv = h->kp.sf2; // every kernel here has k(v,v) = sigma_f^2
-    colnorm_kernel<<<(unsigned)M, 256, 0, st>>>(dV, h->Np, kvv, h->kp.noise, dS2);
+    {
+        LbProfScope ps(h, st, LB_PC_QREDUCE);
+        colnorm_kernel<<<(unsigned)M, 256, 0, st>>>(dV, h->Np, kvv, h->kp.noise, dS2);
+    }
     if (launches) ++*launches;
     LB_CUDA(cudaGetLastError());
     return LB_OK;

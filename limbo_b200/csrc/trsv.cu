@@ -209,6 +209,7 @@ int lb_launch_trsv(lb_gp* h, double* dB, int nrhs, bool forward)
     for (int p0 = 0; p0 < nrhs; p0 += NR) {
         const int nr = (nrhs - p0 < NR) ? (nrhs - p0) : NR;
         LB_CUDA(cudaMemsetAsync(h->dFlags, 0, (T + 1) * sizeof(int), h->stream));
+        LbProfScope ps(h, h->stream, LB_PC_TRSV);
         if (forward)
             trsv_fwd_kernel<<<T, 256, 0, h->stream>>>(h->dL, h->Np, h->dInvD, dB + (int64_t)p0 * h->Np, h->Np, nr, T,
                 h->dFlags, h->dInfo);

@@ -32,7 +32,7 @@ def eval_grad(f, x):  # optimizer.hpp:91-95
 
 
 def _signum(x: float) -> int:  # tools/math.hpp:71-91
-    return (0 < x) - (x < 0)
+    return int(0 < x) - int(x < 0)
 
 
 class Rprop:
