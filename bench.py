@@ -178,17 +178,18 @@ def run_reference(args) -> None:
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
-PC = ["kbuild", "potf2", "trsm_panel", "syrk", "trsv", "kstar", "qstep", "qreduce", "acq", "trtri", "lauum", "grad", "other"]
+PC = ["kbuild", "potf2", "trsm_panel", "syrk", "syrk_col", "trsv", "kstar", "qstep", "qreduce", "acq", "trtri", "lauum", "grad", "other"]
 
 
 def syrk_flops_per_fit(n: int) -> float:
-    """Algorithmic flops of all trailing updates of a right-looking factorisation with NB = 128:
-    sum over panels of m (m + 1) * NB with m the trailing order (lower triangle incl. diagonal)."""
+    """Algorithmic flops of the K=256 trailing updates (profile class "syrk") of one factorisation:
+    panels are taken in pairs (k, k+1); the update of the matrix right of the pair has order
+    m = (T - k - 2) * 128 and costs m (m + 1) * 256 flops (lower triangle incl. diagonal, 2 flops per MAC)."""
     nb, tot = 128, 0.0
     t = (n + nb - 1) // nb
-    for k in range(t):
-        m = (t - k - 1) * nb
-        tot += float(m) * (m + 1) * nb
+    for k in range(0, t, 2):
+        m = max(0, (t - k - 2)) * nb
+        tot += float(m) * (m + 1) * (2 * nb)
     return tot
 
 
@@ -245,7 +246,10 @@ def run_ours(args) -> None:
 
     gp = model.GP(d, 1, kernel=kernel.SquaredExpARD, mean=mean.Data, device=local_rank)
     h = gp._h
-    stream = torch.cuda.current_stream(dev)
+    # a real (non-default) stream: the library and the timing events must share it
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     gp.set_stream(stream.cuda_stream)
 
     # ---------------- device-resident leg ("value") ----------------

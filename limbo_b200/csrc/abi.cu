@@ -277,6 +277,12 @@ int lb_create(lb_gp** out, int device, int precision)
     }
     h->stream = h->ex.own;
     h->own_stream = true;
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi) != cudaSuccess) h->side = nullptr;
+        for (int i = 0; i < 6; ++i) cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming);
+    }
     if (cudaMalloc(&h->dInfo, 4 * sizeof(int)) != cudaSuccess || cudaMalloc(&h->ex.dMisc, 256 * sizeof(double)) != cudaSuccess) {
         delete h;
         return LB_ERR_ALLOC;
@@ -300,6 +306,8 @@ int lb_destroy(lb_gp* hh)
     cudaFree(h->dScratch);
     cudaFree(h->ex.dMisc);
     if (h->ex.own) cudaStreamDestroy(h->ex.own);
+    if (h->side) cudaStreamDestroy(h->side);
+    for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
     return LB_OK;
 }

@@ -168,6 +168,8 @@ struct lb_gp {
     int precision = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t side = nullptr;   // high-priority stream for the look-ahead panel factorisation
+    cudaEvent_t ev[6] = {};        // fork / panel / a-update / join events
 
     int64_t N = 0;   // live samples
     int64_t Np = 0;  // padded capacity (multiple of 128)
@@ -199,7 +201,7 @@ struct lb_gp {
 };
 
 // per-kernel-class CUDA-event timing (bench.py roofline): no-ops unless enabled
-enum { LB_PC_KBUILD = 0, LB_PC_POTF2, LB_PC_TRSM_PANEL, LB_PC_SYRK, LB_PC_TRSV, LB_PC_KSTAR, LB_PC_QSTEP, LB_PC_QREDUCE,
+enum { LB_PC_KBUILD = 0, LB_PC_POTF2, LB_PC_TRSM_PANEL, LB_PC_SYRK, LB_PC_SYRK_COL, LB_PC_TRSV, LB_PC_KSTAR, LB_PC_QSTEP, LB_PC_QREDUCE,
     LB_PC_ACQ, LB_PC_TRTRI, LB_PC_LAUUM, LB_PC_GRAD, LB_PC_OTHER, LB_PC_COUNT };
 void lb_prof_begin(const lb_gp* h, cudaStream_t st, int cls);
 void lb_prof_end(const lb_gp* h, cudaStream_t st, int cls);

@@ -1,6 +1,8 @@
 // limbo_b200/csrc/gemm.cuh — fp64 tensor-core (DMMA) tile GEMM building block.
 //
-// One CTA (256 threads = 8 warps, 4 along M x 2 along N) accumulates a
+// One CTA (512 threads = 16 warps, 4 along M x 4 along N; a single warp can only
+// drive the DMMA pipe of its SM sub-partition at half rate — measured,
+// profiles/r01_microbench.json — so every sub-partition gets 4 warps) accumulates a
 // 128 x BN tile  acc += A(128 x K) * B(K x BN)  with a 3-stage cp.async
 // pipeline (BK = 16).  Both operands can be "outer-contiguous" (the m / n index
 // is the unit-stride one, i.e. a column-major 128 x K block) or "K-contiguous"
@@ -18,7 +20,7 @@ namespace lbg {
 constexpr int BM = 128;
 constexpr int BK = 16;
 constexpr int STAGES = 3;
-constexpr int THREADS = 256;
+constexpr int THREADS = 512;
 constexpr int PITCH_OC = BM + 4; // outer-contiguous tile: [BK][128+4]
 constexpr int PITCH_KC = BK + 4; // k-contiguous tile:     [128][16+4]
 constexpr int STAGE_DOUBLES = BM * PITCH_KC; // 2560 >= BK*PITCH_OC (2112)
@@ -47,10 +49,10 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
 }
 
 // Accumulators of one warp: MT m16-tiles x NT n8-tiles.
-// Warp grid is 4 (M) x 2 (N): warp tile = 32 x (BN/2) -> MT = 2, NT = BN/16.
+// Warp grid is 4 (M) x 4 (N): warp tile = 32 x (BN/4) -> MT = 2, NT = BN/32.
 template <int BN>
 struct Acc {
-    static constexpr int NT = BN / 16;
+    static constexpr int NT = BN / 32;
     double v[2][NT][4];
     __device__ __forceinline__ void zero()
     {
@@ -63,14 +65,14 @@ struct Acc {
     }
 };
 
-template <int BN, bool A_KC, bool B_KC>
+template <int BN, bool A_KC, bool B_KC, bool NEG_A = false>
 __device__ __forceinline__ void compute_stage(Acc<BN>& acc, const double* sA, const double* sB)
 {
-    constexpr int NT = BN / 16;
+    constexpr int NT = BN / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;
-    const int m_base = wm * 32, n_base = wn * (BN / 2);
+    const int m_base = wm * 32, n_base = wn * (BN / 4);
 #pragma unroll
     for (int k0 = 0; k0 < BK; k0 += 8) {
         double a[2][4];
@@ -81,6 +83,7 @@ __device__ __forceinline__ void compute_stage(Acc<BN>& acc, const double* sA, co
                 int m = m_base + mt * 16 + g + 8 * (i & 1);
                 int k = k0 + t + 4 * (i >> 1);
                 a[mt][i] = A_KC ? sA[m * PITCH_KC + k] : sA[k * PITCH_OC + m];
+                if (NEG_A) a[mt][i] = -a[mt][i];
             }
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
@@ -97,12 +100,14 @@ __device__ __forceinline__ void compute_stage(Acc<BN>& acc, const double* sA, co
     }
 }
 
-// acc += A * B over K (multiple of 16).  gA/gB point at the (0,0) element of
+// acc += A * B (acc -= A * B with NEG_A, so a tile update C - A*B can preload C
+// into the accumulators and overlap those loads with the pipeline prologue
+// instead of paying a dependent load-subtract-store epilogue) over K (multiple of 16).  gA/gB point at the (0,0) element of
 // the operand tile for k = 0; stepping k by 16 advances an outer-contiguous
 // operand by 16*ld and a K-contiguous one by 16.  All threads must call.
 // smem: PIPE_BYTES.  On return all cp.async groups are drained and the CTA is
 // synchronised (smem may be reused).
-template <int BN, bool A_KC, bool B_KC>
+template <int BN, bool A_KC, bool B_KC, bool NEG_A = false>
 __device__ __forceinline__ void mainloop(Acc<BN>& acc, const double* __restrict__ gA, int64_t lda,
     const double* __restrict__ gB, int64_t ldb, int K, double* smem)
 {
@@ -130,7 +135,7 @@ __device__ __forceinline__ void mainloop(Acc<BN>& acc, const double* __restrict_
         }
         lb_cp_async_commit();
         int s = kt % STAGES;
-        compute_stage<BN, A_KC, B_KC>(acc, sA + s * STAGE_DOUBLES, sB + s * STAGE_DOUBLES);
+        compute_stage<BN, A_KC, B_KC, NEG_A>(acc, sA + s * STAGE_DOUBLES, sB + s * STAGE_DOUBLES);
     }
     lb_cp_async_wait<0>();
     __syncthreads();
@@ -141,7 +146,7 @@ __device__ __forceinline__ void mainloop(Acc<BN>& acc, const double* __restrict_
 template <int BN, typename F>
 __device__ __forceinline__ void for_each_acc(Acc<BN>& acc, F&& f)
 {
-    constexpr int NT = BN / 16;
+    constexpr int NT = BN / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;
@@ -152,9 +157,22 @@ __device__ __forceinline__ void for_each_acc(Acc<BN>& acc, F&& f)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 int row = wm * 32 + mt * 16 + g + 8 * (i >> 1);
-                int col = wn * (BN / 2) + nt * 8 + 2 * t + (i & 1);
+                int col = wn * (BN / 4) + nt * 8 + 2 * t + (i & 1);
                 f(row, col, acc.v[mt][nt][i]);
             }
+}
+
+// acc <- C tile (column-major, ld) : plain loads, no arithmetic, so they stay in
+// flight while the cp.async prologue is issued.
+template <int BN>
+__device__ __forceinline__ void load_acc(Acc<BN>& acc, const double* __restrict__ C, int64_t ld)
+{
+    for_each_acc<BN>(acc, [&](int r, int c, double& v) { v = __ldcs(C + r + (int64_t)c * ld); });
+}
+template <int BN>
+__device__ __forceinline__ void store_acc(Acc<BN>& acc, double* __restrict__ C, int64_t ld)
+{
+    for_each_acc<BN>(acc, [&](int r, int c, double& v) { C[r + (int64_t)c * ld] = v; });
 }
 
 // Second-phase product with a resident B operand: acc2 += A(128 x 128) * Bres
@@ -165,13 +183,13 @@ template <int BN>
 __device__ __forceinline__ void mainloop_resB(Acc<BN>& acc, const double* __restrict__ gA, int64_t lda,
     const double* sBres, double* smem_pipe)
 {
-    constexpr int NT = BN / 16;
+    constexpr int NT = BN / 32;
     constexpr int PB = BM + 4;
     const int nk = BM / BK;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;
-    const int m_base = wm * 32, n_base = wn * (BN / 2);
+    const int m_base = wm * 32, n_base = wn * (BN / 4);
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         load_tile<false>(smem_pipe + s * STAGE_DOUBLES, gA + (int64_t)s * BK * lda, lda, BM);

@@ -74,9 +74,9 @@ trtri_row_kernel(const double* __restrict__ L, int64_t ld, const double* __restr
     lbg::Acc<128> acc;
     acc.zero();
     // A = L[i, j..i-1] (outer-contiguous), B = X[j..i-1, j] (k-contiguous)
-    lbg::mainloop<128, false, true>(acc, L + (int64_t)i * LB_TILE + (int64_t)j * LB_TILE * ld, ld,
+    lbg::mainloop<128, false, true, true>(acc, L + (int64_t)i * LB_TILE + (int64_t)j * LB_TILE * ld, ld,
         X + (int64_t)j * LB_TILE + (int64_t)j * LB_TILE * ld, ld, (i - j) * LB_TILE, smem);
-    lbg::for_each_acc<128>(acc, [&](int r, int c, double v) { sT[c * PB + r] = -v; });
+    lbg::for_each_acc<128>(acc, [&](int r, int c, double v) { sT[c * PB + r] = v; });
     __syncthreads();
     lbg::Acc<128> acc2;
     acc2.zero();

@@ -163,26 +163,25 @@ trsm_panel_kernel(double* __restrict__ L, int64_t ld, int k, const double* __res
     lbg::for_each_acc<128>(acc, [&](int r, int c, double v) { A[r + (int64_t)c * ld] = v; });
 }
 
-// A[i,j] -= L[i,k] L[j,k]^T for k < j <= i < T
+// Trailing update with the panel block columns [kb, kb + kd):
+//   A[i,j] -= L[i, kb:kb+kd] L[j, kb:kb+kd]^T   for j in [j0, j0 + nc), j <= i < T
+// (kd = 1: one 128-column panel, K = 128; kd = 2: two panels at once, K = 256 —
+// half the C traffic and half the tile prologues per flop).  C is preloaded into
+// the accumulators so its latency overlaps the operand pipeline's prologue.
 __global__ void __launch_bounds__(lbg::THREADS, 1)
-syrk_kernel(double* __restrict__ L, int64_t ld, int k)
+syrk_kernel(double* __restrict__ L, int64_t ld, int kb, int kd, int j0, int nc, int T)
 {
     extern __shared__ __align__(16) double smem[];
-    int t = blockIdx.x;
-    int r = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((int64_t)(r + 1) * (r + 2) / 2 <= t) ++r;
-    while ((int64_t)r * (r + 1) / 2 > t) --r;
-    const int i = k + 1 + r, j = k + 1 + (t - r * (r + 1) / 2);
-    const double* A = L + (int64_t)i * LB_TILE + (int64_t)k * LB_TILE * ld;
-    const double* B = L + (int64_t)j * LB_TILE + (int64_t)k * LB_TILE * ld;
+    int idx = blockIdx.x, c = 0;
+    while (c < nc && idx >= T - j0 - c) { idx -= T - j0 - c; ++c; }
+    const int j = j0 + c, i = j + idx;
+    const double* A = L + (int64_t)i * LB_TILE + (int64_t)kb * LB_TILE * ld;
+    const double* B = L + (int64_t)j * LB_TILE + (int64_t)kb * LB_TILE * ld;
     double* C = L + (int64_t)i * LB_TILE + (int64_t)j * LB_TILE * ld;
     lbg::Acc<128> acc;
-    acc.zero();
-    lbg::mainloop<128, false, false>(acc, A, ld, B, ld, LB_TILE, smem);
-    lbg::for_each_acc<128>(acc, [&](int rr, int cc, double v) {
-        double* p = C + rr + (int64_t)cc * ld;
-        *p = *p - v;
-    });
+    lbg::load_acc<128>(acc, C, ld);
+    lbg::mainloop<128, false, false, true>(acc, A, ld, B, ld, kd * LB_TILE, smem);
+    lbg::store_acc<128>(acc, C, ld);
 }
 
 bool g_attr_done = false;
@@ -208,30 +207,87 @@ int lb_launch_potf2_block(lb_gp* h, int k, int do_factor)
     return LB_OK;
 }
 
+static inline int syrk_tiles(int T, int j0, int nc)
+{
+    int n = 0;
+    for (int c = 0; c < nc; ++c) n += T - j0 - c;
+    return n;
+}
+
+// Right-looking factorisation in pairs of 128-column panels with look-ahead:
+//   side stream : panel(p)  = potf2(k) trsm(k) syrk[k -> col k+1] potf2(k+1) trsm(k+1)
+//   main stream : a(p)      = K=256 update of the next pair's two block columns (k+2, k+3)
+//                 b(p)      = K=256 update of everything right of them
+// panel(p+1) only needs a(p), so the latency-bound panel work runs under b(p).
 int lb_launch_potrf(lb_gp* h)
 {
     int rc = set_attrs();
     if (rc) return rc;
     const int T = (int)(h->Np / LB_TILE);
-    LB_CUDA(cudaMemsetAsync(h->dInfo, 0, 2 * sizeof(int), h->stream));
-    for (int k = 0; k < T; ++k) {
+    const int64_t ld = h->Np;
+    cudaStream_t main = h->stream, side = h->side ? h->side : h->stream;
+    LB_CUDA(cudaMemsetAsync(h->dInfo, 0, 2 * sizeof(int), main));
+    if (side != main) {
+        LB_CUDA(cudaEventRecord(h->ev[0], main)); // inputs (K) ready
+        LB_CUDA(cudaStreamWaitEvent(side, h->ev[0], 0));
+    }
+    int p = 0;
+    for (int k = 0; k < T; k += 2, ++p) {
+        const bool pair = (k + 1 < T);
+        // ---- panel(p) on the side stream ----
         {
-            LbProfScope ps(h, h->stream, LB_PC_POTF2);
-            potf2_inv_kernel<<<1, 256, POTF2_SMEM, h->stream>>>(h->dL, h->Np, k, h->dInvD, h->dInfo, 1);
+            LbProfScope ps(h, side, LB_PC_POTF2);
+            potf2_inv_kernel<<<1, 256, POTF2_SMEM, side>>>(h->dL, ld, k, h->dInvD, h->dInfo, 1);
         }
         h->launches++;
-        const int n = T - k - 1;
-        if (n > 0) {
+        if (pair) {
             {
-                LbProfScope ps(h, h->stream, LB_PC_TRSM_PANEL);
-                trsm_panel_kernel<<<n, lbg::THREADS, lbg::PIPE_BYTES, h->stream>>>(h->dL, h->Np, k, h->dInvD);
+                LbProfScope ps(h, side, LB_PC_TRSM_PANEL);
+                trsm_panel_kernel<<<T - k - 1, lbg::THREADS, lbg::PIPE_BYTES, side>>>(h->dL, ld, k, h->dInvD);
             }
             {
-                LbProfScope ps(h, h->stream, LB_PC_SYRK);
-                syrk_kernel<<<n * (n + 1) / 2, lbg::THREADS, lbg::PIPE_BYTES, h->stream>>>(h->dL, h->Np, k);
+                LbProfScope ps(h, side, LB_PC_SYRK_COL);
+                syrk_kernel<<<T - k - 1, lbg::THREADS, lbg::PIPE_BYTES, side>>>(h->dL, ld, k, 1, k + 1, 1, T);
             }
-            h->launches += 2;
+            {
+                LbProfScope ps(h, side, LB_PC_POTF2);
+                potf2_inv_kernel<<<1, 256, POTF2_SMEM, side>>>(h->dL, ld, k + 1, h->dInvD, h->dInfo, 1);
+            }
+            h->launches += 3;
+            if (k + 2 < T) {
+                LbProfScope ps(h, side, LB_PC_TRSM_PANEL);
+                trsm_panel_kernel<<<T - k - 2, lbg::THREADS, lbg::PIPE_BYTES, side>>>(h->dL, ld, k + 1, h->dInvD);
+                h->launches++;
+            }
         }
+        if (k + 2 >= T) break;
+        if (side != main) {
+            LB_CUDA(cudaEventRecord(h->ev[1 + (p & 1)], side));
+            LB_CUDA(cudaStreamWaitEvent(main, h->ev[1 + (p & 1)], 0));
+        }
+        // ---- a(p): the next pair's block columns ----
+        const int j0 = k + 2;
+        const int nca = (T - j0 < 2) ? (T - j0) : 2;
+        {
+            LbProfScope ps(h, main, LB_PC_SYRK);
+            syrk_kernel<<<syrk_tiles(T, j0, nca), lbg::THREADS, lbg::PIPE_BYTES, main>>>(h->dL, ld, k, 2, j0, nca, T);
+        }
+        h->launches++;
+        if (side != main) {
+            LB_CUDA(cudaEventRecord(h->ev[3 + (p & 1)], main));
+            LB_CUDA(cudaStreamWaitEvent(side, h->ev[3 + (p & 1)], 0));
+        }
+        // ---- b(p): the rest of the trailing matrix ----
+        const int ncb = T - j0 - nca;
+        if (ncb > 0) {
+            LbProfScope ps(h, main, LB_PC_SYRK);
+            syrk_kernel<<<syrk_tiles(T, j0 + nca, ncb), lbg::THREADS, lbg::PIPE_BYTES, main>>>(h->dL, ld, k, 2, j0 + nca, ncb, T);
+            h->launches++;
+        }
+    }
+    if (side != main) { // join
+        LB_CUDA(cudaEventRecord(h->ev[5], side));
+        LB_CUDA(cudaStreamWaitEvent(main, h->ev[5], 0));
     }
     LB_CUDA(cudaGetLastError());
     return LB_OK;

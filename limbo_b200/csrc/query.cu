@@ -124,11 +124,11 @@ query_step_kernel(const double* __restrict__ L, int64_t ld, const double* __rest
     const int64_t col0 = (int64_t)blockIdx.x * BN;
     double* Vc = V + col0 * ld;
     lbg::Acc<BN> acc;
-    acc.zero();
-    if (i > 0) lbg::mainloop<BN, false, true>(acc, L + (int64_t)i * LB_TILE, ld, Vc, ld, i * LB_TILE, smem);
-    // t = V_i - acc  -> smem [n][k]
     double* Vi = Vc + (int64_t)i * LB_TILE;
-    lbg::for_each_acc<BN>(acc, [&](int r, int c, double v) { sT[c * PB + r] = Vi[r + (int64_t)c * ld] - v; });
+    lbg::load_acc<BN>(acc, Vi, ld); // acc = V_i, then acc -= L[i,0:i] V[0:i]
+    if (i > 0) lbg::mainloop<BN, false, true, true>(acc, L + (int64_t)i * LB_TILE, ld, Vc, ld, i * LB_TILE, smem);
+    // t -> smem [n][k]
+    lbg::for_each_acc<BN>(acc, [&](int r, int c, double v) { sT[c * PB + r] = v; });
     __syncthreads();
     lbg::Acc<BN> acc2;
     acc2.zero();
