@@ -14,6 +14,10 @@
 int lb_launch_potf2_block(lb_gp* h, int k, int do_factor);
 int lb_launch_linv(lb_gp* h);
 int lb_launch_symmetrize(lb_gp* h, double* dA);
+int lb_query_fused_supported(const lb_gp* h);
+size_t lb_query_fused_scratch_doubles(const lb_gp* h, int grid);
+int lb_launch_query_fused(const lb_gp* h, cudaStream_t st, int64_t M, const double* dQs, int64_t Mp, double* dVscratch,
+    int grid, double* dMu, double* dS2, long long* launches);
 int lb_launch_acq_full(cudaStream_t st, int acq_id, double p0, double p1, int64_t M, const double* dMu, int mu_stride,
     const double* dMeanAtQ, double mean_const, const double* dS2, double* dAcq, double* dBlkVal, long long* dBlkIdx,
     double* dBestVal, long long* dBestIdx, long long* launches);
@@ -427,6 +431,8 @@ int lb_fit_async(lb_gp* h) // same as lb_fit without the final host sync / info 
 }
 
 int lb_check_info(lb_gp* h) { return h ? check_info(h) : LB_ERR_ARG; }
+// testing hook: force the multi-launch (unfused) query path
+int lb_debug_force_unfused_query(lb_gp* h, int on) { if (!h) return LB_ERR_ARG; h->force_unfused = on != 0; return LB_OK; }
 
 // stage timers for bench.py: run only one stage (inputs must already be in place)
 int lb_stage_kbuild(lb_gp* h)
@@ -559,6 +565,20 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
             LB_CUDA(cudaMemcpyAsync(w.dQraw, Xq, sizeof(double) * M * D, cudaMemcpyHostToDevice, st));
             dQraw = w.dQraw;
         }
+        if (lb_query_fused_supported(h) && !h->force_unfused) {
+            // fused persistent path: one CTA per candidate slab, private V scratch per CTA
+            int sms = 0;
+            LB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+            const int64_t ntiles = (M + 7) / 8;
+            const int grid = (int)std::min<int64_t>(sms, ntiles);
+            if ((rc = ensure(&w.dQs, &w.qs_bytes, sizeof(double) * D * Mp))) return rc;
+            if ((rc = ensure(&w.dV, &w.v_bytes, sizeof(double) * lb_query_fused_scratch_doubles(h, grid)))) return rc;
+            dim3 g1((unsigned)((Mp + 255) / 256), (unsigned)D);
+            pack_soa_kernel<<<g1, 256, 0, st>>>(dQraw, M, D, w.dQs, Mp, h->kp, 1);
+            h->launches++;
+            if ((rc = lb_launch_query_fused(h, st, M, w.dQs, Mp, w.dV, grid, w.dMu, w.dS2, &h->launches))) return rc;
+        }
+        else {
         // candidate chunks bounded so that V (Np x Mc) stays <= ~4 GiB
         int64_t Mc = Mp;
         const int64_t maxcols = std::max<int64_t>(LB_TILE, ((int64_t)4 << 30) / (8 * h->Np) / LB_TILE * LB_TILE);
@@ -572,6 +592,7 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
             pack_soa_kernel<<<g1, 256, 0, st>>>(dQraw + m0 * D, mc, D, w.dQs, mcp, h->kp, 1);
             h->launches++;
             if ((rc = lb_launch_query(h, st, mc, w.dQs, mcp, w.dV, w.dMu + m0 * P, w.dS2 + m0, &h->launches))) return rc;
+        }
         }
     }
     if (with_acq) {

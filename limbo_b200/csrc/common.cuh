@@ -194,6 +194,7 @@ struct lb_gp {
     bool fitted = false;
     bool linv_valid = false;
     bool kinv_valid = false;
+    bool force_unfused = false; // tests: use the multi-launch query path
 
     // counters for bench.py ("gpu_launches")
     long long launches = 0;

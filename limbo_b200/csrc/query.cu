@@ -318,3 +318,349 @@ int lb_launch_acq_full(cudaStream_t st, int acq_id, double p0, double p1, int64_
     LB_CUDA(cudaGetLastError());
     return LB_OK;
 }
+
+// ===========================================================================
+// Fused, persistent batched query (the production path for D <= 16, P <= 4).
+//
+// One CTA per candidate slab of up to 72 candidates; the slab walks all T row
+// blocks of the factor by itself, so there is no inter-CTA dependency, no
+// per-step launch and no wave quantisation (slabs are sized so that all 148 SMs
+// get 8 or 9 n8-tiles).  For row block i:
+//   acc  = K*[i, slab]  (generated on chip from X_i and the slab's candidates;
+//                        mu += K*^T alpha on the way)
+//   acc -= L[i, 0:i] V[0:i, slab]      (DMMA, A = L via L2, B = the CTA's private V)
+//   V_i  = inv(L_ii) acc               (DMMA), |V_i|^2 accumulated per candidate
+// The 16 warps are 8 row-warps x 2 K-groups: group g takes the g-th k8 step of
+// every 16-deep pipeline stage and the two partial tiles are combined through
+// shared memory once per row block, which keeps 4 DMMA-issuing warps on every
+// SM sub-partition.
+// ===========================================================================
+namespace slab {
+
+constexpr int NTMAX = 9;
+constexpr int SLAB = NTMAX * 8;  // 72
+constexpr int THREADS = 512;
+constexpr int BK = 16;
+constexpr int STAGES = 3;
+constexpr int PA = 132;  // A stage [16][132]
+constexpr int PBK = 20;  // B stage [SLAB][20]
+constexpr int PT = 132;  // resident tile [SLAB][132]
+constexpr int DMAXF = 16;
+constexpr int PMAXF = 4;
+constexpr int A_STAGE = BK * PA;     // 2112
+constexpr int B_STAGE = SLAB * PBK;  // 1440
+constexpr int OFF_A = 0;
+constexpr int OFF_B = OFF_A + STAGES * A_STAGE;
+constexpr int OFF_T = OFF_B + STAGES * B_STAGE;
+constexpr int OFF_X = OFF_T + SLAB * PT;
+constexpr int OFF_Q = OFF_X + DMAXF * LB_TILE;
+constexpr int OFF_AL = OFF_Q + DMAXF * SLAB;
+constexpr int OFF_RED = OFF_AL + PMAXF * LB_TILE;
+constexpr int OFF_MU = OFF_RED + 8 * SLAB;
+constexpr int OFF_NRM = OFF_MU + PMAXF * SLAB;
+constexpr int SMEM_DOUBLES = OFF_NRM + SLAB;
+constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * sizeof(double);
+
+__device__ __forceinline__ void load_A_stage(double* s, const double* __restrict__ g, int64_t ld)
+{
+    // 16 k-columns x 128 rows (outer-contiguous): 1024 chunks of 16 B, 2 per thread
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        int c = threadIdx.x + q * THREADS;
+        int k = c >> 6, oc = c & 63;
+        lb_cp_async16(s + k * PA + 2 * oc, g + (int64_t)k * ld + 2 * oc);
+    }
+}
+__device__ __forceinline__ void load_B_stage(double* s, const double* __restrict__ g, int64_t ld, int ncols)
+{
+    // ncols candidates x 16 k (k-contiguous): ncols * 8 chunks
+    int c = threadIdx.x;
+    if (c < ncols * 8) {
+        int n = c >> 3, kc = c & 7;
+        lb_cp_async16(s + n * PBK + 2 * kc, g + (int64_t)n * ld + 2 * kc);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+query_slab_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ invD, const double* __restrict__ Xs,
+    int64_t N, const double* __restrict__ Qs, int64_t Mp, int64_t M, const double* __restrict__ alpha, int P, KernParams kp,
+    double* __restrict__ Vscratch, int nslabs, int64_t ntiles_total, double* __restrict__ mu_out, double* __restrict__ s2_out)
+{
+    extern __shared__ __align__(16) double sm[];
+    double* sA = sm + OFF_A;
+    double* sB = sm + OFF_B;
+    double* sT = sm + OFF_T;
+    double* sX = sm + OFF_X;
+    double* sQ = sm + OFF_Q;
+    double* sAl = sm + OFF_AL;
+    double* sRed = sm + OFF_RED;
+    double* sMu = sm + OFF_MU;
+    double* sNrm = sm + OFF_NRM;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int grp = warp >> 3, wr = warp & 7;
+    const int T = (int)(ld / LB_TILE);
+    const int D = kp.D;
+    double* V = Vscratch + (int64_t)blockIdx.x * ld * SLAB; // private [c][n], ld per candidate
+    const int r_lo = 16 * wr + g; // rows r_lo, r_lo + 8 of the current row block
+
+    for (int s = blockIdx.x; s < nslabs; s += gridDim.x) {
+        // balanced partition of the n8-tiles over the slabs
+        const int64_t t0 = ntiles_total * s / nslabs, t1 = ntiles_total * (s + 1) / nslabs;
+        const int ntc = (int)(t1 - t0);
+        const int ncols = ntc * 8;
+        const int64_t c0 = t0 * 8; // first candidate of the slab
+        __syncthreads();
+        for (int idx = tid; idx < D * ncols; idx += THREADS) {
+            int d = idx / ncols, c = idx - d * ncols;
+            sQ[d * SLAB + c] = Qs[(int64_t)d * Mp + c0 + c];
+        }
+        for (int idx = tid; idx < PMAXF * SLAB; idx += THREADS) sMu[idx] = 0.0;
+        if (tid < SLAB) sNrm[tid] = 0.0;
+        __syncthreads();
+
+        for (int i = 0; i < T; ++i) {
+            const int64_t row0 = (int64_t)i * LB_TILE;
+            // ---- stage X_i and alpha_i ----
+            for (int idx = tid; idx < D * LB_TILE; idx += THREADS) {
+                int d = idx >> 7, r = idx & 127;
+                sX[d * LB_TILE + r] = Xs[(int64_t)d * ld + row0 + r];
+            }
+            for (int idx = tid; idx < P * LB_TILE; idx += THREADS) {
+                int p = idx >> 7, r = idx & 127;
+                sAl[p * LB_TILE + r] = alpha[(int64_t)p * ld + row0 + r];
+            }
+            // prefetch the first pipeline stages of phase 1 while K* is generated
+            const int nk = i * (LB_TILE / BK);
+            const double* gA = L + row0;          // L[i-block rows, k = 0..]
+            const double* gB = V;                 // V[k = 0.., slab]
+#pragma unroll
+            for (int st = 0; st < STAGES - 1; ++st) {
+                if (st < nk) {
+                    load_A_stage(sA + st * A_STAGE, gA + (int64_t)st * BK * ld, ld);
+                    load_B_stage(sB + st * B_STAGE, gB + st * BK, ld, ncols);
+                }
+                lb_cp_async_commit();
+            }
+            __syncthreads();
+            // ---- phase 0: acc = K*[i, slab] (group 0), mu partials ----
+            double acc[NTMAX][4];
+#pragma unroll
+            for (int nt = 0; nt < NTMAX; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[nt][e] = 0.0;
+            if (grp == 0) {
+#pragma unroll
+                for (int nt = 0; nt < NTMAX; ++nt) {
+                    if (nt < ntc) {
+                        double z[4] = {0.0, 0.0, 0.0, 0.0};
+                        const int cl = 8 * nt + 2 * t;
+                        for (int d = 0; d < D; ++d) {
+                            const double x0 = sX[d * LB_TILE + r_lo], x1 = sX[d * LB_TILE + r_lo + 8];
+                            const double q0 = sQ[d * SLAB + cl], q1 = sQ[d * SLAB + cl + 1];
+                            double u;
+                            u = x0 - q0; z[0] = fma(u, u, z[0]);
+                            u = x0 - q1; z[1] = fma(u, u, z[1]);
+                            u = x1 - q0; z[2] = fma(u, u, z[2]);
+                            u = x1 - q1; z[3] = fma(u, u, z[3]);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int64_t gr = row0 + r_lo + 8 * (e >> 1), gc = c0 + cl + (e & 1);
+                            double k = lb_kernel_from_z(kp.id, z[e], kp.sf2, kp.l);
+                            if (gr >= N || gc >= M) k = 0.0;
+                            acc[nt][e] = k;
+                        }
+                    }
+                }
+            }
+            // mu += K*^T alpha (deterministic: shuffle over the 8 row lanes, then a fixed-order sum over warps)
+            for (int p = 0; p < P; ++p) {
+                if (grp == 0) {
+                    const double a0 = sAl[p * LB_TILE + r_lo], a1 = sAl[p * LB_TILE + r_lo + 8];
+#pragma unroll
+                    for (int nt = 0; nt < NTMAX; ++nt) {
+                        if (nt < ntc) {
+                            double s0 = fma(acc[nt][0], a0, acc[nt][2] * a1);
+                            double s1 = fma(acc[nt][1], a0, acc[nt][3] * a1);
+#pragma unroll
+                            for (int o = 4; o < 32; o <<= 1) {
+                                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                            }
+                            if (g == 0) {
+                                sRed[wr * SLAB + 8 * nt + 2 * t] = s0;
+                                sRed[wr * SLAB + 8 * nt + 2 * t + 1] = s1;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                if (tid < ncols) {
+                    double sum = 0.0;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) sum += sRed[w * SLAB + tid];
+                    sMu[p * SLAB + tid] += sum;
+                }
+                __syncthreads();
+            }
+            // ---- phase 1: acc -= L[i, 0:i] V[0:i] ----
+            for (int kt = 0; kt < nk; ++kt) {
+                lb_cp_async_wait<STAGES - 2>();
+                __syncthreads();
+                const int nx = kt + STAGES - 1;
+                if (nx < nk) {
+                    load_A_stage(sA + (nx % STAGES) * A_STAGE, gA + (int64_t)nx * BK * ld, ld);
+                    load_B_stage(sB + (nx % STAGES) * B_STAGE, gB + nx * BK, ld, ncols);
+                }
+                lb_cp_async_commit();
+                const double* a_s = sA + (kt % STAGES) * A_STAGE;
+                const double* b_s = sB + (kt % STAGES) * B_STAGE;
+                const int k0 = 8 * grp;
+                double a[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a[e] = -a_s[(k0 + t + 4 * (e >> 1)) * PA + r_lo + 8 * (e & 1)];
+#pragma unroll
+                for (int nt = 0; nt < NTMAX; ++nt) {
+                    if (nt < ntc) {
+                        double b[2];
+                        b[0] = b_s[(8 * nt + g) * PBK + k0 + t];
+                        b[1] = b_s[(8 * nt + g) * PBK + k0 + t + 4];
+                        lb_dmma_16x8x8(acc[nt], a, b);
+                    }
+                }
+            }
+            lb_cp_async_wait<0>();
+            __syncthreads();
+            // ---- combine the two K-groups: t = acc0 + acc1 -> sT[n][k] ----
+            if (grp == 1) {
+#pragma unroll
+                for (int nt = 0; nt < NTMAX; ++nt)
+                    if (nt < ntc)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) sT[(8 * nt + 2 * t + (e & 1)) * PT + r_lo + 8 * (e >> 1)] = acc[nt][e];
+            }
+            // start streaming inv(L_ii) (phase 2 operand A) meanwhile
+            const double* gD = invD + (int64_t)i * LB_TILE * LB_TILE;
+#pragma unroll
+            for (int st = 0; st < STAGES - 1; ++st) {
+                load_A_stage(sA + st * A_STAGE, gD + (int64_t)st * BK * LB_TILE, LB_TILE);
+                lb_cp_async_commit();
+            }
+            __syncthreads();
+            if (grp == 0) {
+#pragma unroll
+                for (int nt = 0; nt < NTMAX; ++nt)
+                    if (nt < ntc)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            double* p = &sT[(8 * nt + 2 * t + (e & 1)) * PT + r_lo + 8 * (e >> 1)];
+                            *p = acc[nt][e] + *p;
+                        }
+            }
+#pragma unroll
+            for (int nt = 0; nt < NTMAX; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[nt][e] = 0.0;
+            // ---- phase 2: acc = inv(L_ii) * t ----
+            for (int kt = 0; kt < LB_TILE / BK; ++kt) {
+                lb_cp_async_wait<STAGES - 2>();
+                __syncthreads(); // also publishes group 0's sT writes on the first iteration
+                const int nx = kt + STAGES - 1;
+                if (nx < LB_TILE / BK) load_A_stage(sA + (nx % STAGES) * A_STAGE, gD + (int64_t)nx * BK * LB_TILE, LB_TILE);
+                lb_cp_async_commit();
+                const double* a_s = sA + (kt % STAGES) * A_STAGE;
+                const int k0 = 8 * grp;
+                double a[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a[e] = a_s[(k0 + t + 4 * (e >> 1)) * PA + r_lo + 8 * (e & 1)];
+#pragma unroll
+                for (int nt = 0; nt < NTMAX; ++nt) {
+                    if (nt < ntc) {
+                        double b[2];
+                        b[0] = sT[(8 * nt + g) * PT + kt * BK + k0 + t];
+                        b[1] = sT[(8 * nt + g) * PT + kt * BK + k0 + t + 4];
+                        lb_dmma_16x8x8(acc[nt], a, b);
+                    }
+                }
+            }
+            lb_cp_async_wait<0>();
+            __syncthreads();
+            if (grp == 1) {
+#pragma unroll
+                for (int nt = 0; nt < NTMAX; ++nt)
+                    if (nt < ntc)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) sT[(8 * nt + 2 * t + (e & 1)) * PT + r_lo + 8 * (e >> 1)] = acc[nt][e];
+            }
+            __syncthreads();
+            if (grp == 0) {
+#pragma unroll
+                for (int nt = 0; nt < NTMAX; ++nt) {
+                    if (nt < ntc) {
+                        double v[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int c = 8 * nt + 2 * t + (e & 1), r = r_lo + 8 * (e >> 1);
+                            v[e] = acc[nt][e] + sT[c * PT + r];
+                            V[(int64_t)c * ld + row0 + r] = v[e];
+                        }
+                        double s0 = fma(v[0], v[0], v[2] * v[2]);
+                        double s1 = fma(v[1], v[1], v[3] * v[3]);
+#pragma unroll
+                        for (int o = 4; o < 32; o <<= 1) {
+                            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                        }
+                        if (g == 0) {
+                            sRed[wr * SLAB + 8 * nt + 2 * t] = s0;
+                            sRed[wr * SLAB + 8 * nt + 2 * t + 1] = s1;
+                        }
+                    }
+                }
+            }
+            __syncthreads(); // V_i visible to the whole CTA (later cp.async reads), sRed complete
+            if (tid < ncols) {
+                double sum = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) sum += sRed[w * SLAB + tid];
+                sNrm[tid] += sum;
+            }
+        }
+        __syncthreads();
+        if (tid < ncols && c0 + tid < M) {
+            double res = kp.sf2 - sNrm[tid]; // k(v,v) - z.z            gp.hpp:621
+            res = (res <= DBL_EPSILON) ? 0.0 : res; //                   gp.hpp:623
+            s2_out[c0 + tid] = res + kp.noise; //                        gp.hpp:166
+            for (int p = 0; p < P; ++p) mu_out[(c0 + tid) * P + p] = sMu[p * SLAB + tid];
+        }
+    }
+}
+
+bool g_attr = false;
+
+} // namespace slab
+
+int lb_query_fused_supported(const lb_gp* h) { return h->D <= slab::DMAXF && h->P <= slab::PMAXF; }
+size_t lb_query_fused_scratch_doubles(const lb_gp* h, int grid) { return (size_t)grid * h->Np * slab::SLAB; }
+
+int lb_launch_query_fused(const lb_gp* h, cudaStream_t st, int64_t M, const double* dQs, int64_t Mp, double* dVscratch,
+    int grid, double* dMu, double* dS2, long long* launches)
+{
+    if (!slab::g_attr) {
+        LB_CUDA(cudaFuncSetAttribute(slab::query_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab::SMEM_BYTES));
+        slab::g_attr = true;
+    }
+    const int64_t ntiles = (M + 7) / 8;
+    // slabs of <= 9 n8-tiles, a multiple of the grid so every CTA gets the same number of slabs
+    int64_t nslabs = (ntiles + slab::NTMAX - 1) / slab::NTMAX;
+    nslabs = (nslabs + grid - 1) / grid * grid;
+    if (nslabs > ntiles) nslabs = ntiles;
+    LbProfScope ps(h, st, LB_PC_QSTEP);
+    slab::query_slab_kernel<<<grid, slab::THREADS, slab::SMEM_BYTES, st>>>(h->dL, h->Np, h->dInvD, h->dXs, h->N, dQs, Mp, M,
+        h->dAlpha, h->P, h->kp, dVscratch, (int)nslabs, ntiles, dMu, dS2);
+    if (launches) ++*launches;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}

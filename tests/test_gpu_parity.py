@@ -298,3 +298,27 @@ def test_concurrent_const_queries(oracle_mod):
     [t.start() for t in th]
     [t.join() for t in th]
     assert not errs
+
+
+def test_fused_and_multilaunch_query_paths_agree(oracle_mod, lib):
+    """The fused persistent slab kernel (D <= 16, P <= 4) and the multi-launch blocked TRSM path
+    (any D / P) both match the oracle; large D / P route to the latter automatically."""
+    import ctypes as C
+    from limbo_b200 import synth
+    lib.lb_debug_force_unfused_query.argtypes = [C.c_void_p, C.c_int]
+    gp, og, X, Y = _make("SquaredExpARD", 700, 6)
+    Xq = synth.points(5, 1111, 6)
+    mu_f, s2_f = gp.query_batch(Xq)
+    lib.lb_debug_force_unfused_query(gp._h, 1)
+    mu_u, s2_u = gp.query_batch(Xq)
+    lib.lb_debug_force_unfused_query(gp._h, 0)
+    mu_o, s2_o = og.query(Xq)
+    mu_o = mu_o + Y.mean(axis=0)
+    for mu, s2 in ((mu_f, s2_f), (mu_u, s2_u)):
+        assert np.abs(mu - mu_o).max() <= TOL_ABS and np.abs(s2 - s2_o).max() <= TOL_ABS
+    # D = 20 (> 16) and P = 5 (> 4) take the multi-launch path
+    gp, og, X, Y = _make("MaternFiveHalves", 260, 20, P=5)
+    Xq = synth.points(6, 333, 20)
+    mu, s2 = gp.query_batch(Xq)
+    mu_o, s2_o = og.query(Xq)
+    assert np.abs(mu - (mu_o + Y.mean(axis=0))).max() <= TOL_ABS and np.abs(s2 - s2_o).max() <= TOL_ABS
