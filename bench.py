@@ -233,6 +233,7 @@ def run_ours(args) -> None:
     if world > 1:
         dist.barrier()
     from limbo_b200 import _lib, acqui, kernel, mean, model, synth
+    from limbo_b200 import dist as lbdist
 
     lib = _lib.load()
     lib.lb_profile_enable.argtypes = [C.c_void_p, C.c_int]
@@ -327,9 +328,8 @@ def run_ours(args) -> None:
     def step_e2e():
         gp2.compute(Xl, yl)                     # host samples/observations in, H2D inside
         best, idx = ucb.argmax_batch(Xqp.numpy())  # host candidates in, (value, index) out
-        if world > 1:
-            rec = torch.tensor([best, float(idx + rank * m)], dtype=torch.float64, device=dev)
-            dist.all_gather(gather_buf, rec)
+        if world > 1:  # the one collective: (value, global index) records -> global argmax on every rank
+            best, idx = lbdist.allgather_argmax(best, idx + rank * m, device=dev)
         return best, idx
 
     e2e_steps = max(2, min(steps, 5))

@@ -1,0 +1,160 @@
+// oracle/ref_shim/ref_driver.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// Runs the REFERENCE'S OWN hot-path code (headers included from
+// /root/reference/src where they lie: limbo/model/gp.hpp, kernel/*.hpp,
+// mean/data.hpp, acqui/ucb.hpp, acqui/ei.hpp, model/gp/kernel_lf_opt.hpp,
+// opt/rprop.hpp) with the dense linear algebra supplied by the stand-in in
+// ./Eigen.  Used to pin oracle/limbo_oracle.hpp (tests/test_oracle_vs_ref.py)
+// and to generate tests/golden/*.npz (tests/golden/make_golden.py).
+// No reference source is copied: this file only instantiates its templates.
+#define protected public // same trick as src/tests/test_gp.cpp:48 to read _kernel
+#include <limbo/acqui/ei.hpp>
+#include <limbo/acqui/ucb.hpp>
+#include <limbo/kernel/exp.hpp>
+#include <limbo/kernel/matern_five_halves.hpp>
+#include <limbo/kernel/matern_three_halves.hpp>
+#include <limbo/kernel/squared_exp_ard.hpp>
+#include <limbo/mean/data.hpp>
+#include <limbo/model/gp.hpp>
+#include <limbo/model/gp/kernel_lf_opt.hpp>
+#include <limbo/opt/rprop.hpp>
+#undef protected
+#include <cstring>
+
+using namespace limbo;
+
+struct Params {
+    struct kernel {
+        BO_DYN_PARAM(double, noise);
+        BO_PARAM(bool, optimize_noise, false);
+    };
+    struct kernel_squared_exp_ard : public defaults::kernel_squared_exp_ard {};
+    struct kernel_maternfivehalves : public defaults::kernel_maternfivehalves {};
+    struct kernel_maternthreehalves : public defaults::kernel_maternthreehalves {};
+    struct kernel_exp : public defaults::kernel_exp {};
+    struct opt_rprop {
+        BO_DYN_PARAM(int, iterations);
+        BO_PARAM(double, eps_stop, 0.0);
+    };
+    struct acqui_ucb : public defaults::acqui_ucb {};
+    struct acqui_ei : public defaults::acqui_ei {};
+};
+BO_DECLARE_DYN_PARAM(double, Params::kernel, noise);
+BO_DECLARE_DYN_PARAM(int, Params::opt_rprop, iterations);
+
+struct ParamsNoise : Params {
+    struct kernel {
+        BO_DYN_PARAM(double, noise);
+        BO_PARAM(bool, optimize_noise, true);
+    };
+};
+BO_DECLARE_DYN_PARAM(double, ParamsNoise::kernel, noise);
+
+// bayes_opt/bo_base.hpp:99-105 (FirstElem) restated: bo_base.hpp itself needs Boost.Parameter/Fusion
+struct FirstElem {
+    double operator()(const Eigen::VectorXd& x) const { return x(0); }
+};
+
+namespace {
+
+std::vector<Eigen::VectorXd> rows_of(const double* a, long n, int d)
+{
+    std::vector<Eigen::VectorXd> v;
+    for (long i = 0; i < n; ++i) {
+        Eigen::VectorXd x((Eigen::Index)d);
+        for (int k = 0; k < d; ++k) x(k) = a[i * d + k];
+        v.push_back(x);
+    }
+    return v;
+}
+
+void put(const Eigen::MatrixXd& m, double* dst)
+{
+    if (dst) std::memcpy(dst, m.data(), sizeof(double) * (size_t)m.size());
+}
+
+template <typename P, typename Kernel>
+int run(long N, int D, int Pout, const double* X, const double* Y, double noise, const double* hp, int nh, long N0, long M,
+    const double* Xq, int rprop_iters, double* K, double* L, double* alpha, double* mu, double* s2, double* loglik, double* grad,
+    double* ucb, double* ei, double* hp_out)
+{
+    P::kernel::set_noise(noise);
+    using GP_t = model::GP<P, Kernel, mean::Data<P>, model::gp::KernelLFOpt<P, opt::Rprop<P>>>;
+    auto samples = rows_of(X, N, D);
+    auto obs = rows_of(Y, N, Pout);
+    GP_t gp(D, Pout);
+    if (hp) {
+        Eigen::VectorXd h((Eigen::Index)nh);
+        for (int i = 0; i < nh; ++i) h(i) = hp[i];
+        gp.kernel_function().set_h_params(h);
+    }
+    if (N0 > 0 && N0 < N) { // gp.hpp:126-152 incremental path for the last N - N0 samples
+        std::vector<Eigen::VectorXd> s0(samples.begin(), samples.begin() + N0), o0(obs.begin(), obs.begin() + N0);
+        gp.compute(s0, o0);
+        for (long i = N0; i < N; ++i) gp.add_sample(samples[i], obs[i]);
+    }
+    else
+        gp.compute(samples, obs);
+    if (rprop_iters > 0) {
+        Params::opt_rprop::set_iterations(rprop_iters);
+        gp.optimize_hyperparams();
+    }
+    if (hp_out) {
+        Eigen::VectorXd h = gp.kernel_function().h_params();
+        for (Eigen::Index i = 0; i < h.size(); ++i) hp_out[i] = h(i);
+    }
+    put(gp._kernel, K);
+    put(gp.matrixL(), L);
+    put(gp.alpha(), alpha);
+    if (loglik) *loglik = gp.compute_log_lik();
+    if (grad) {
+        Eigen::VectorXd g = gp.compute_kernel_grad_log_lik();
+        for (Eigen::Index i = 0; i < g.size(); ++i) grad[i] = g(i);
+    }
+    acqui::UCB<P, GP_t> a_ucb(gp);
+    acqui::EI<P, GP_t> a_ei(gp);
+    FirstElem afun;
+    for (long q = 0; q < M; ++q) {
+        Eigen::VectorXd v((Eigen::Index)D);
+        for (int k = 0; k < D; ++k) v(k) = Xq[q * D + k];
+        Eigen::VectorXd m;
+        double s;
+        std::tie(m, s) = gp.query(v);
+        for (int p = 0; p < Pout; ++p) mu[q * Pout + p] = m(p);
+        s2[q] = s;
+        // the reference's own consistency property (test_gp.cpp:506-507)
+        if (!(gp.sigma(v) == s)) return 2;
+        if (ucb) ucb[q] = opt::fun(a_ucb(v, afun, false));
+        if (ei) ei[q] = opt::fun(a_ei(v, afun, false));
+    }
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+// kernel_id: 0 SquaredExpARD, 1 MaternFiveHalves, 2 MaternThreeHalves, 3 Exp.  Y is N x P row-major observations
+// (NOT mean-subtracted: mean::Data is the reference's own).  optimize_noise selects ParamsNoise (grad gets +1 entry).
+int ref_gp_run(int kernel_id, int optimize_noise, long N, int D, int P, const double* X, const double* Y, double noise,
+    const double* hp, int nh, long N0, long M, const double* Xq, int rprop_iters, double* K, double* L, double* alpha, double* mu,
+    double* s2, double* loglik, double* grad, double* ucb, double* ei, double* hp_out)
+{
+#define RUN(PP, KK) return run<PP, kernel::KK<PP>>(N, D, P, X, Y, noise, hp, nh, N0, M, Xq, rprop_iters, K, L, alpha, mu, s2, loglik, grad, ucb, ei, hp_out)
+    if (optimize_noise) {
+        switch (kernel_id) {
+        case 0: RUN(ParamsNoise, SquaredExpARD);
+        case 1: RUN(ParamsNoise, MaternFiveHalves);
+        case 2: RUN(ParamsNoise, MaternThreeHalves);
+        default: RUN(ParamsNoise, Exp);
+        }
+    }
+    switch (kernel_id) {
+    case 0: RUN(Params, SquaredExpARD);
+    case 1: RUN(Params, MaternFiveHalves);
+    case 2: RUN(Params, MaternThreeHalves);
+    default: RUN(Params, Exp);
+    }
+#undef RUN
+}
+}
