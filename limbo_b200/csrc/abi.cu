@@ -12,6 +12,7 @@
 #include <string>
 
 int lb_launch_potf2_block(lb_gp* h, int k, int do_factor);
+int lb_debug_potf2_clocks(lb_gp* h, int k, long long* out_host, int n);
 int lb_launch_linv(lb_gp* h);
 int lb_launch_symmetrize(lb_gp* h, double* dA);
 int lb_query_fused_supported(const lb_gp* h);
@@ -232,6 +233,7 @@ int alloc_model(lb_gp* h, int64_t Np, int D, int P)
     LB_CUDA(cudaMalloc(&h->dAlpha, sizeof(double) * P * Np));
     LB_CUDA(cudaMalloc(&h->dL, sizeof(double) * Np * Np));
     LB_CUDA(cudaMalloc(&h->dInvD, sizeof(double) * T * LB_TILE * LB_TILE));
+    LB_CUDA(cudaMemset(h->dInvD, 0, sizeof(double) * T * LB_TILE * LB_TILE)); // upper triangles stay zero
     LB_CUDA(cudaMalloc(&h->dFlags, sizeof(int) * (T + 8)));
     h->Np = Np;
     return LB_OK;
@@ -431,6 +433,7 @@ int lb_fit_async(lb_gp* h) // same as lb_fit without the final host sync / info 
 }
 
 int lb_check_info(lb_gp* h) { return h ? check_info(h) : LB_ERR_ARG; }
+int lb_debug_potf2(lb_gp* h, int k, long long* out, int n) { return h ? lb_debug_potf2_clocks(h, k, out, n) : LB_ERR_ARG; }
 // testing hook: force the multi-launch (unfused) query path
 int lb_debug_force_unfused_query(lb_gp* h, int on) { if (!h) return LB_ERR_ARG; h->force_unfused = on != 0; return LB_OK; }
 

@@ -15,138 +15,220 @@
 
 namespace {
 
-constexpr int PS = LB_TILE + 1;   // pitch of the diagonal block in smem
-constexpr int XB = 32 * 33;       // one 32x32 inverse block, pitch 33
+constexpr int PS = LB_TILE + 4;   // pitch of the diagonal block in smem (== 4 mod 16: conflict-free DMMA fragment loads)
+constexpr int XP = 36;            // pitch of a 32x32 inverse block
+constexpr int XB = 32 * XP;
 constexpr size_t POTF2_SMEM = (size_t)(LB_TILE * PS + 10 * XB + LB_TILE) * sizeof(double);
 
 __device__ __forceinline__ int blk(int ib, int jb) { return ib * (ib + 1) / 2 + jb; }
 
-__global__ void __launch_bounds__(256, 1)
-potf2_inv_kernel(double* __restrict__ L, int64_t ld, int k, double* __restrict__ invD, int* __restrict__ info, int do_factor)
+// One warp: c(16x8) += sum_k A(m,k) B(k,n), K a multiple of 8; fa(m,k), fb(k,n) read shared memory.
+template <typename FA, typename FB>
+__device__ __forceinline__ void warp_mma(double (&c)[4], int K, FA fa, FB fb)
 {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        double a[4], b[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = fa(g + 8 * (i & 1), k0 + t + 4 * (i >> 1));
+#pragma unroll
+        for (int i = 0; i < 2; ++i) b[i] = fb(k0 + t + 4 * i, g);
+        lb_dmma_16x8x8(c, a, b);
+    }
+}
+
+__device__ __forceinline__ double rsqrt_nr(double x)
+{
+    // branch-free reciprocal square root: MUFU.RSQ64H seed + two Newton steps (<= 1 ulp for normal x)
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double h = 0.5 * x;
+    r = fma(r, fma(-h * r, r, 0.5), r);
+    r = fma(r, fma(-h * r, r, 0.5), r);
+    return r;
+}
+
+// Factor the 128x128 diagonal block k of L in place and form its inverse (invD[k]).
+// Panel work is latency bound (a chain of 128 dependent pivots), so everything that is
+// not on that chain runs on the tensor cores from shared memory (block kept COLUMN-major,
+// S[c*PS + r], so global <-> shared copies are 16-byte vectors and every DMMA fragment
+// load is bank-conflict free):
+//   per 32-column sub-block jb:
+//     warp 0   : 32x32 Cholesky in registers (row per lane, warp shuffles, branch-free
+//                rsqrt) and its inverse by column-oriented substitution;
+//     all warps: rows below  X = A * inv(Ld)^T      (DMMA, in place)
+//                trailing    A22 -= X X^T           (DMMA, lower tiles)
+//   then the off-diagonal blocks of inv(L_kk) block row by block row (DMMA).
+__global__ void __launch_bounds__(256, 1)
+potf2_inv_kernel(double* __restrict__ L, int64_t ld, int k, double* __restrict__ invD, int* __restrict__ info, int do_factor,
+    long long* __restrict__ clk = nullptr)
+{
+    int clk_n = 0;
+#define LB_TICK() do { if (clk && threadIdx.x == 0) clk[clk_n++] = clock64(); } while (0)
+    LB_TICK();
     extern __shared__ __align__(16) double smem[];
-    double* S = smem;                         // [128][PS]
-    double* Xb = smem + LB_TILE * PS;         // 10 blocks [32][33]
+    double* S = smem;                         // [128 cols][PS]   S[c*PS + r]
+    double* Xb = smem + LB_TILE * PS;         // 10 blocks [32 cols][XP]  X[c*XP + r]
     double* sInv = Xb + 10 * XB;              // [128] reciprocal diagonal
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
     const int64_t k0 = (int64_t)k * LB_TILE;
     double* Lkk = L + k0 + k0 * ld;
 
-    for (int idx = tid; idx < LB_TILE * LB_TILE; idx += 256) {
-        int r = idx & 127, c = idx >> 7;
-        S[r * PS + c] = (c <= r) ? Lkk[r + (int64_t)c * ld] : 0.0;
+    for (int idx = tid; idx < LB_TILE * (LB_TILE / 2); idx += 256) { // 16-byte chunks, coalesced along rows
+        const int c = idx >> 6, r = (idx & 63) * 2;
+        lb_cp_async16(&S[c * PS + r], Lkk + r + (int64_t)c * ld);
     }
+    lb_cp_async_commit();
+    lb_cp_async_wait<0>();
     __syncthreads();
-    if (!do_factor) { // block already factored (incremental update): only (re)build its inverse
-        if (tid < LB_TILE) sInv[tid] = 1.0 / S[tid * PS + tid];
-        __syncthreads();
-    }
+    LB_TICK();
+    int bad = 0;
 
-    for (int jb = 0; jb < (do_factor ? 4 : 0); ++jb) {
+    for (int jb = 0; jb < 4; ++jb) {
         const int c0 = 32 * jb;
-        // (1) 32x32 diagonal sub-block, one row per lane, right-looking
         if (warp == 0) {
             double a[32];
+            if (do_factor) {
+                // ---- 32x32 Cholesky, one row per lane, right-looking ----
 #pragma unroll
-            for (int c = 0; c < 32; ++c) a[c] = S[(c0 + lane) * PS + c0 + c];
+                for (int c = 0; c < 32; ++c) a[c] = S[(c0 + c) * PS + c0 + lane];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                double ajj = __shfl_sync(0xffffffffu, a[j], j);
-                if (!(ajj > 0.0) && lane == 0) atomicCAS(info, 0, (int)(k0 + c0 + j + 1));
-                double d = sqrt(ajj);
-                double inv = 1.0 / d;
-                double lij = (lane > j) ? a[j] * inv : ((lane == j) ? d : 0.0);
-                a[j] = lij;
-                if (lane == j) sInv[c0 + j] = inv;
+                for (int j = 0; j < 32; ++j) {
+                    const double ajj = __shfl_sync(0xffffffffu, a[j], j);
+                    if (!(ajj > 0.0) && bad == 0) bad = c0 + j + 1;
+                    const double inv = rsqrt_nr(ajj);
+                    const double d = ajj * inv;
+                    const double lij = (lane > j) ? a[j] * inv : ((lane == j) ? d : 0.0);
+                    a[j] = lij;
+                    if (lane == j) sInv[c0 + j] = inv;
 #pragma unroll
-                for (int kk = j + 1; kk < 32; ++kk) {
-                    double lkj = __shfl_sync(0xffffffffu, lij, kk);
-                    a[kk] = fma(-lij, lkj, a[kk]);
+                    for (int kk = j + 1; kk < 32; ++kk) {
+                        const double lkj = __shfl_sync(0xffffffffu, lij, kk);
+                        a[kk] = fma(-lij, lkj, a[kk]);
+                    }
                 }
-            }
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-                if (c <= lane) S[(c0 + lane) * PS + c0 + c] = a[c];
-        }
-        __syncthreads();
-        const int nrem = LB_TILE - c0 - 32;
-        // (2) rows below: x = a * Ld^-T (forward substitution along the row)
-        if (tid < nrem) {
-            const int r = c0 + 32 + tid;
+                for (int c = 0; c < 32; ++c) S[(c0 + c) * PS + c0 + lane] = (c <= lane) ? a[c] : 0.0;
+            }
+            else {
+                sInv[c0 + lane] = 1.0 / S[(c0 + lane) * PS + c0 + lane];
+            }
+            __syncwarp();
+            if (jb == 0) LB_TICK();
+            // ---- inverse of the 32x32 diagonal sub-block: lane = column of X, column-oriented ----
             double x[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) x[c] = S[r * PS + c0 + c];
+            for (int i = 0; i < 32; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                double s = x[c];
+            for (int kk = 0; kk < 32; ++kk) {
+                const double xk = x[kk] * sInv[c0 + kk];
+                x[kk] = xk;
 #pragma unroll
-                for (int kk = 0; kk < c; ++kk) s = fma(-x[kk], S[(c0 + c) * PS + c0 + kk], s);
-                x[c] = s * sInv[c0 + c];
+                for (int i = kk + 1; i < 32; ++i) x[i] = fma(-S[(c0 + kk) * PS + c0 + i], xk, x[i]);
             }
+            double* X = Xb + blk(jb, jb) * XB;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) S[r * PS + c0 + c] = x[c];
+            for (int i = 0; i < 32; ++i) X[lane * XP + i] = (i >= lane) ? x[i] : 0.0;
         }
         __syncthreads();
-        // (3) trailing update inside the block (lower part)
-        for (int idx = tid; idx < nrem * nrem; idx += 256) {
-            const int r = c0 + 32 + idx % nrem, c = c0 + 32 + idx / nrem;
-            if (c <= r) {
-                double s = S[r * PS + c];
-#pragma unroll 8
-                for (int kk = 0; kk < 32; ++kk) s = fma(-S[r * PS + c0 + kk], S[c * PS + c0 + kk], s);
-                S[r * PS + c] = s;
+        if (jb == 0) LB_TICK();
+        if (!do_factor) continue;
+        const int nrem = LB_TILE - c0 - 32;
+        const int r0 = c0 + 32;
+        // ---- rows below: X = A * inv(Ld)^T, in place; one m16 row tile (all 4 n8 tiles) per warp ----
+        const double* Wd = Xb + blk(jb, jb) * XB;
+        for (int mt = warp; mt < nrem / 16; mt += 8) {
+            const int rb = r0 + 16 * mt;
+            double acc[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[nt][e] = 0.0;
+                warp_mma(acc[nt], 32, [&](int m, int kk) { return S[(c0 + kk) * PS + rb + m]; },
+                    [&](int kk, int n) { return Wd[kk * XP + 8 * nt + n]; }); // (Wd^T)(kk, n) = Wd[n][kk]
             }
+            __syncwarp();
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) S[(c0 + 8 * nt + 2 * t + (e & 1)) * PS + rb + g + 8 * (e >> 1)] = acc[nt][e];
+        }
+        __syncthreads();
+        if (jb == 0) LB_TICK();
+        // ---- trailing update of the block: A22 -= X X^T (tiles touching the lower triangle) ----
+        {
+            const int mts = nrem / 16, nts = nrem / 8;
+            int w = 0;
+            for (int mt = 0; mt < mts; ++mt)
+                for (int nt = 0; nt < nts && nt <= 2 * mt + 1; ++nt, ++w) {
+                    if ((w & 7) != warp) continue;
+                    const int rb = r0 + 16 * mt, cb = r0 + 8 * nt;
+                    double c[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) c[e] = 0.0;
+                    warp_mma(c, 32, [&](int m, int kk) { return S[(c0 + kk) * PS + rb + m]; },
+                        [&](int kk, int n) { return S[(c0 + kk) * PS + cb + n]; });
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) S[(cb + 2 * t + (e & 1)) * PS + rb + g + 8 * (e >> 1)] -= c[e];
+                }
         }
         __syncthreads();
     }
+    if (bad && tid == 0) atomicCAS(info, 0, (int)(k0 + bad));
 
-    // (4) inverses of the four 32x32 diagonal sub-blocks, one column per lane
-    if (warp < 4) {
-        const int c0 = 32 * warp;
-        double x[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            double s = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-            for (int kk = 0; kk < i; ++kk) s = fma(-S[(c0 + i) * PS + c0 + kk], x[kk], s);
-            x[i] = s * sInv[c0 + i];
-        }
-        double* X = Xb + blk(warp, warp) * XB;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) X[i * 33 + lane] = (i >= lane) ? x[i] : 0.0;
-    }
-    __syncthreads();
-    // (5) off-diagonal inverse blocks, block row by block row:
-    //     X[ib,jb] = -X[ib,ib] * sum_{kb=jb}^{ib-1} L[ib,kb] X[kb,jb]
+    LB_TICK();
+    // ---- off-diagonal blocks of the inverse, block row by block row:
+    //      X[ib,jb] = -X[ib,ib] * sum_{kb=jb}^{ib-1} L[ib,kb] X[kb,jb]
     for (int ib = 1; ib < 4; ++ib) {
-        for (int o = tid; o < 1024 * ib; o += 256) {
-            const int r = o & 31, c = (o >> 5) & 31, jb = o >> 10;
-            double s = 0.0;
+        // T[jb] (32x32) -> free upper block (rows of jb, cols of ib) of S; 8 mma tiles per jb
+        for (int w = warp; w < 8 * ib; w += 8) {
+            const int jb = w >> 3, mt = (w >> 2) & 1, nt = w & 3;
+            double c[4] = {0.0, 0.0, 0.0, 0.0};
             for (int kb = jb; kb < ib; ++kb) {
                 const double* Xk = Xb + blk(kb, jb) * XB;
-#pragma unroll 8
-                for (int kk = 0; kk < 32; ++kk) s = fma(S[(32 * ib + r) * PS + 32 * kb + kk], Xk[kk * 33 + c], s);
+                warp_mma(c, 32, [&](int m, int kk) { return S[(32 * kb + kk) * PS + 32 * ib + 16 * mt + m]; },
+                    [&](int kk, int n) { return Xk[(8 * nt + n) * XP + kk]; });
             }
-            S[(32 * jb + r) * PS + 32 * ib + c] = s; // temp T in the free upper block (jb, ib)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) S[(32 * ib + 8 * nt + 2 * t + (e & 1)) * PS + 32 * jb + 16 * mt + g + 8 * (e >> 1)] = c[e];
         }
         __syncthreads();
-        for (int o = tid; o < 1024 * ib; o += 256) {
-            const int r = o & 31, c = (o >> 5) & 31, jb = o >> 10;
-            const double* Xd = Xb + blk(ib, ib) * XB;
-            double s = 0.0;
-#pragma unroll 8
-            for (int kk = 0; kk < 32; ++kk) s = fma(Xd[r * 33 + kk], S[(32 * jb + kk) * PS + 32 * ib + c], s);
-            Xb[blk(ib, jb) * XB + r * 33 + c] = -s;
+        const double* Xd = Xb + blk(ib, ib) * XB;
+        for (int w = warp; w < 8 * ib; w += 8) {
+            const int jb = w >> 3, mt = (w >> 2) & 1, nt = w & 3;
+            double c[4] = {0.0, 0.0, 0.0, 0.0};
+            warp_mma(c, 32, [&](int m, int kk) { return Xd[kk * XP + 16 * mt + m]; },
+                [&](int kk, int n) { return S[(32 * ib + 8 * nt + n) * PS + 32 * jb + kk]; });
+            double* Xo = Xb + blk(ib, jb) * XB;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) Xo[(8 * nt + 2 * t + (e & 1)) * XP + 16 * mt + g + 8 * (e >> 1)] = -c[e];
         }
         __syncthreads();
     }
-    // (6) write back L[k,k] (clean lower) and inv(L[k,k])
+    LB_TICK();
+    // ---- write back L[k,k] (clean lower) and inv(L[k,k]): two consecutive rows per 16-byte store ----
     double* inv_out = invD + (int64_t)k * LB_TILE * LB_TILE;
-    for (int idx = tid; idx < LB_TILE * LB_TILE; idx += 256) {
-        int r = idx & 127, c = idx >> 7;
-        Lkk[r + (int64_t)c * ld] = (c <= r) ? S[r * PS + c] : 0.0;
-        inv_out[r + c * LB_TILE] = (c <= r) ? Xb[blk(r >> 5, c >> 5) * XB + (r & 31) * 33 + (c & 31)] : 0.0;
+    for (int idx = tid; idx < LB_TILE * (LB_TILE / 2); idx += 256) {
+        const int c = idx >> 6, r = (idx & 63) * 2;
+        if (c > r + 1) continue; // strictly upper part: never read by any consumer (invD is zero-initialised)
+        if (do_factor) {
+            double2 v = *reinterpret_cast<const double2*>(&S[c * PS + r]);
+            if (c > r) v.x = 0.0;
+            if (c > r + 1) v.y = 0.0;
+            *reinterpret_cast<double2*>(Lkk + r + (int64_t)c * ld) = v;
+        }
+        double2 x = make_double2(0.0, 0.0);
+        if (c <= r + 1) {
+            const double* Xs_ = Xb + blk(r >> 5, c >> 5) * XB + (c & 31) * XP + (r & 31);
+            x = *reinterpret_cast<const double2*>(Xs_);
+            if (c > r) x.x = 0.0;
+        }
+        *reinterpret_cast<double2*>(inv_out + r + c * LB_TILE) = x;
     }
+    __syncthreads();
+    LB_TICK();
+#undef LB_TICK
 }
 
 // L[i,k] <- A[i,k] * inv(L[k,k])^T for i = k+1 .. T-1
@@ -196,6 +278,22 @@ int set_attrs()
 }
 
 } // namespace
+
+// debug: cycle stamps of the phases of one panel factorisation (thread 0): start, loaded, [jb=0: factored,
+// inverted, panel solved], all sub-blocks done, inverse assembled, written back
+int lb_debug_potf2_clocks(lb_gp* h, int k, long long* out_host, int n)
+{
+    int rc = set_attrs();
+    if (rc) return rc;
+    long long* d = nullptr;
+    LB_CUDA(cudaMalloc(&d, sizeof(long long) * 16));
+    LB_CUDA(cudaMemset(d, 0, sizeof(long long) * 16));
+    potf2_inv_kernel<<<1, 256, POTF2_SMEM, h->stream>>>(h->dL, h->Np, k, h->dInvD, h->dInfo, 1, d);
+    LB_CUDA(cudaStreamSynchronize(h->stream));
+    LB_CUDA(cudaMemcpy(out_host, d, sizeof(long long) * (n < 16 ? n : 16), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return LB_OK;
+}
 
 int lb_launch_potf2_block(lb_gp* h, int k, int do_factor)
 {
