@@ -1,0 +1,109 @@
+// tests/cpp/dropin_test.cpp — the drop-in claim, compiled: the reference's OWN policy templates
+// (acqui::UCB, acqui::EI, model::gp::KernelLFOpt<Params, opt::Rprop>, kernel::*, mean::Data from
+// /root/reference/src/limbo) instantiated over limbo_b200::model::GP and, side by side, over the
+// reference's limbo::model::GP; results must agree to the fp64 bar.  Needs a GPU to run.
+// (Eigen is the stand-in from oracle/ref_shim because the image has no Eigen.)
+#include <cstdio>
+#include <limbo/acqui/ei.hpp>
+#include <limbo/acqui/ucb.hpp>
+#include <limbo/kernel/matern_five_halves.hpp>
+#include <limbo/kernel/squared_exp_ard.hpp>
+#include <limbo/mean/data.hpp>
+#include <limbo/model/gp.hpp>
+#include <limbo/model/gp/kernel_lf_opt.hpp>
+#include <limbo/opt/rprop.hpp>
+
+#include <limbo_b200/model/gp.hpp>
+
+using namespace limbo;
+
+struct Params {
+    struct kernel : public defaults::kernel {};
+    struct kernel_squared_exp_ard : public defaults::kernel_squared_exp_ard {};
+    struct kernel_maternfivehalves : public defaults::kernel_maternfivehalves {};
+    struct opt_rprop {
+        BO_PARAM(int, iterations, 6);
+        BO_PARAM(double, eps_stop, 0.0);
+    };
+    struct acqui_ucb : public defaults::acqui_ucb {};
+    struct acqui_ei : public defaults::acqui_ei {};
+};
+
+struct FirstElem {
+    double operator()(const Eigen::VectorXd& x) const { return x(0); }
+};
+
+static double u01(unsigned long long& s)
+{ // splitmix64, as limbo_b200/synth.py
+    s += 0x9E3779B97F4A7C15ULL;
+    unsigned long long z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+template <typename Kernel>
+int run_case(const char* name, int N, int D)
+{
+    using HP = model::gp::KernelLFOpt<Params, opt::Rprop<Params>>;
+    using RefGP = model::GP<Params, Kernel, mean::Data<Params>, HP>;
+    using NewGP = limbo_b200::model::GP<Params, Kernel, mean::Data<Params>, HP>;
+    unsigned long long seed = 42;
+    std::vector<Eigen::VectorXd> X, Y, Q;
+    for (int i = 0; i < N + 3; ++i) {
+        Eigen::VectorXd x((Eigen::Index)D), y((Eigen::Index)1);
+        double s = 0;
+        for (int d = 0; d < D; ++d) { x(d) = u01(seed); s += std::cos(3.0 * x(d)); }
+        y(0) = s;
+        X.push_back(x);
+        Y.push_back(y);
+    }
+    for (int i = 0; i < 64; ++i) {
+        Eigen::VectorXd q((Eigen::Index)D);
+        for (int d = 0; d < D; ++d) q(d) = u01(seed);
+        Q.push_back(q);
+    }
+    std::vector<Eigen::VectorXd> X0(X.begin(), X.begin() + N), Y0(Y.begin(), Y.begin() + N);
+    RefGP ref(D, 1);
+    NewGP gpu(D, 1);
+    ref.compute(X0, Y0);
+    gpu.compute(X0, Y0);
+    for (int i = N; i < N + 3; ++i) { ref.add_sample(X[i], Y[i]); gpu.add_sample(X[i], Y[i]); } // gp.hpp:126-152
+    ref.optimize_hyperparams(); // the reference's KernelLFOpt<Rprop> driving each model
+    gpu.optimize_hyperparams();
+    double dh = (ref.kernel_function().h_params() - gpu.kernel_function().h_params()).norm();
+    double dll = std::fabs(ref.get_log_lik() - gpu.get_log_lik()) / std::fabs(ref.get_log_lik());
+    acqui::UCB<Params, RefGP> ucb_r(ref);
+    acqui::UCB<Params, NewGP> ucb_n(gpu);
+    acqui::EI<Params, RefGP> ei_r(ref);
+    acqui::EI<Params, NewGP> ei_n(gpu);
+    FirstElem afun;
+    double dmu = 0, ds = 0, ducb = 0, dei = 0;
+    for (auto& q : Q) {
+        Eigen::VectorXd m1, m2;
+        double s1, s2;
+        std::tie(m1, s1) = ref.query(q);
+        std::tie(m2, s2) = gpu.query(q);
+        dmu = std::max(dmu, std::fabs(m1(0) - m2(0)));
+        ds = std::max(ds, std::fabs(s1 - s2));
+        ducb = std::max(ducb, std::fabs(opt::fun(ucb_r(q, afun, false)) - opt::fun(ucb_n(q, afun, false))));
+        dei = std::max(dei, std::fabs(opt::fun(ei_r(q, afun, false)) - opt::fun(ei_n(q, afun, false))));
+    }
+    double dL = (ref.matrixL() - gpu.matrixL()).norm();
+    NewGP copy(gpu); // value semantics (kernel_lf_opt.hpp:79)
+    double dcopy = std::fabs(copy.sigma(Q[0]) - gpu.sigma(Q[0]));
+    std::printf("%s N=%d D=%d |dh|=%.3e dll_rel=%.3e dmu=%.3e dsigma2=%.3e ducb=%.3e dei=%.3e |dL|=%.3e dcopy=%.3e\n", name, N + 3, D, dh,
+        dll, dmu, ds, ducb, dei, dL, dcopy);
+    bool ok = dh < 1e-8 && dll < 1e-10 && dmu < 1e-9 && ds < 1e-10 && ducb < 1e-9 && dei < 1e-9 && dL < 1e-8 && dcopy == 0.0;
+    return ok ? 0 : 1;
+}
+
+int main()
+{
+    int bad = 0;
+    bad += run_case<kernel::SquaredExpARD<Params>>("SquaredExpARD", 60, 3);
+    bad += run_case<kernel::MaternFiveHalves<Params>>("MaternFiveHalves", 150, 2);
+    std::printf(bad ? "DROPIN FAIL\n" : "DROPIN OK\n");
+    return bad;
+}
