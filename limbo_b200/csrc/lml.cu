@@ -84,6 +84,59 @@ trtri_row_kernel(const double* __restrict__ L, int64_t ld, const double* __restr
     lbg::for_each_acc<128>(acc2, [&](int r, int c, double v) { Xij[r + (int64_t)c * ld] = v; });
 }
 
+// ---- recursive (divide and conquer) triangular inverse ----------------------------------
+// inv [[A,0],[B,C]] = [[A^-1, 0], [-C^-1 B A^-1, C^-1]].  Level with half-size sb (in 128-blocks): the matrix is cut
+// into problems of 2*sb block rows; problem q has A = X[a0:a0+sb, a0:a0+sb] and C = X[c0:c0+sb, c0:c0+sb] already
+// inverted by the previous level (a0 = 2*q*sb, c0 = a0 + sb) and B = L[c0:c0+sb, a0:a0+sb].
+//   step 1:  W = B * A^-1            W[i,j] = sum_{k >= j} B[i,k] Ainv[k,j]
+//   step 2:  X[C rows, A cols] = -C^-1 * W   [i,j] = -sum_{k <= i} Cinv[i,k] W[k,j]
+// All tiles of a level are independent (one launch per step), unlike the block-row recurrence whose j = 0
+// tile serialises T^2/2 K-chunks on one SM.
+__global__ void __launch_bounds__(lbg::THREADS, 1)
+trtri_level_kernel(const double* __restrict__ L, double* __restrict__ X, double* __restrict__ W, int64_t ld, int sb, int step,
+    int T)
+{
+    extern __shared__ __align__(16) double smem[];
+    const int per = sb * sb;
+    const int q = blockIdx.x / per;
+    int rem = blockIdx.x - q * per;
+    const int a0 = 2 * q * sb, c0 = a0 + sb;
+    int nC = sb;                       // block rows available in the C part (last problem may be short)
+    if (c0 >= T) return;
+    if (c0 + nC > T) nC = T - c0;
+    lbg::Acc<128> acc;
+    acc.zero();
+    if (step == 1) {
+        const int j = rem / sb, i = rem - j * sb; // heavy tiles (small j) first
+        if (i >= nC) return;
+        // A = B[i, j..sb-1] = L[(c0+i), (a0+j)...] (outer-contiguous); Bop(k,n) = Ainv[(a0+j)+k, (a0+j)*128+n] (k-contiguous)
+        lbg::mainloop<128, false, true>(acc, L + (int64_t)(c0 + i) * LB_TILE + (int64_t)(a0 + j) * LB_TILE * ld, ld,
+            X + (int64_t)(a0 + j) * LB_TILE + (int64_t)(a0 + j) * LB_TILE * ld, ld, (sb - j) * LB_TILE, smem);
+        lbg::store_acc<128>(acc, W + (int64_t)(c0 + i) * LB_TILE + (int64_t)(a0 + j) * LB_TILE * ld, ld);
+    }
+    else {
+        const int ii = rem / sb, j = rem - ii * sb;
+        const int i = sb - 1 - ii; // heavy tiles (large i) first
+        if (i >= nC) return;
+        // A = Cinv[i, 0..i] = X[(c0+i), c0...] (outer-contiguous); Bop(k,n) = W[c0*128 + k, (a0+j)*128 + n] (k-contiguous)
+        lbg::mainloop<128, false, true, true>(acc, X + (int64_t)(c0 + i) * LB_TILE + (int64_t)c0 * LB_TILE * ld, ld,
+            W + (int64_t)c0 * LB_TILE + (int64_t)(a0 + j) * LB_TILE * ld, ld, (i + 1) * LB_TILE, smem);
+        lbg::store_acc<128>(acc, X + (int64_t)(c0 + i) * LB_TILE + (int64_t)(a0 + j) * LB_TILE * ld, ld);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+trtri_diag_copy_kernel(const double* __restrict__ invD, double* __restrict__ X, int64_t ld)
+{
+    const int d = blockIdx.x;
+    const double* src = invD + (int64_t)d * LB_TILE * LB_TILE;
+    double* dst = X + (int64_t)d * LB_TILE + (int64_t)d * LB_TILE * ld;
+    for (int idx = threadIdx.x; idx < LB_TILE * LB_TILE; idx += 256) {
+        int r = idx & 127, c = idx >> 7;
+        dst[r + (int64_t)c * ld] = src[idx];
+    }
+}
+
 // Kinv[i,j] = sum_{k >= i} X[k,i]^T X[k,j]  for i >= j (lower tiles only)
 __global__ void __launch_bounds__(lbg::THREADS, 1)
 lauum_kernel(const double* __restrict__ X, int64_t ld, double* __restrict__ Kinv, int T)
@@ -343,6 +396,7 @@ int set_attrs()
     if (g_attr_done) return LB_OK;
     LB_CUDA(cudaFuncSetAttribute(trtri_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
     LB_CUDA(cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::PIPE_BYTES));
+    LB_CUDA(cudaFuncSetAttribute(trtri_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::PIPE_BYTES));
     g_attr_done = true;
     return LB_OK;
 }
@@ -362,14 +416,22 @@ int lb_launch_linv(lb_gp* h)
     int rc = set_attrs();
     if (rc) return rc;
     const int T = (int)(h->Np / LB_TILE);
+    const size_t bytes = sizeof(double) * h->Np * h->Np;
     if (!h->dLinv) {
-        LB_CUDA(cudaMalloc(&h->dLinv, sizeof(double) * h->Np * h->Np));
-        LB_CUDA(cudaMemsetAsync(h->dLinv, 0, sizeof(double) * h->Np * h->Np, h->stream));
+        LB_CUDA(cudaMalloc(&h->dLinv, bytes));
+        LB_CUDA(cudaMemsetAsync(h->dLinv, 0, bytes, h->stream)); // strict upper part stays zero
     }
+    if (!h->dKinv) LB_CUDA(cudaMalloc(&h->dKinv, bytes)); // doubles as the W workspace of the recursion
     LbProfScope ps(h, h->stream, LB_PC_TRTRI);
-    for (int i = 0; i < T; ++i) {
-        trtri_row_kernel<<<i + 1, lbg::THREADS, TRTRI_SMEM, h->stream>>>(h->dL, h->Np, h->dInvD, h->dLinv, i);
-        h->launches++;
+    trtri_diag_copy_kernel<<<T, 256, 0, h->stream>>>(h->dInvD, h->dLinv, h->Np);
+    h->launches++;
+    for (int sb = 1; sb < T; sb *= 2) {
+        const int nprob = (T + 2 * sb - 1) / (2 * sb);
+        for (int step = 1; step <= 2; ++step) {
+            trtri_level_kernel<<<nprob * sb * sb, lbg::THREADS, lbg::PIPE_BYTES, h->stream>>>(h->dL, h->dLinv, h->dKinv, h->Np, sb,
+                step, T);
+            h->launches++;
+        }
     }
     LB_CUDA(cudaGetLastError());
     h->linv_valid = true;
