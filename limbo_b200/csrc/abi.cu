@@ -182,7 +182,7 @@ __global__ void krow_kernel(const double* __restrict__ Xs, int64_t np, int64_t n
         double q = Xs[(int64_t)d * np + i] - Xs[(int64_t)d * np + inew];
         z = fma(q, q, z);
     }
-    out[i] = (i < n) ? lb_kernel_from_z(kp.id, z, kp.sf2, kp.l) : 0.0;
+    out[i] = (i < n) ? lb_kernel_from_z(kp.id, z, kp) : 0.0;
 }
 
 // finish the incremental row (gp.hpp:591-597): L[n, 0:n] = l^T ; L[n,n] = sqrt(k_nn - l.l)
@@ -399,6 +399,10 @@ int lb_set_kernel(lb_gp* h, int kernel_id, const double* p, int n_hparams, doubl
         kp.l = std::exp(p[0]);
         kp.sf2 = std::exp(2.0 * p[1]);
     }
+    kp.c1 = kp.c2 = 0.0;
+    if (kernel_id == LB_K_MATERN52) { kp.c1 = std::sqrt(5.0) / kp.l; kp.c2 = 5.0 / (3.0 * (kp.l * kp.l)); }
+    else if (kernel_id == LB_K_MATERN32) kp.c1 = std::sqrt(3.0) / kp.l;
+    else if (kernel_id == LB_K_EXP) kp.c1 = 1.0 / (kp.l * kp.l);
     h->n_hparams = n_hparams;
     h->kernel_set = true;
     h->fitted = false; h->linv_valid = false; h->kinv_valid = false;

@@ -50,6 +50,8 @@ struct KernParams {
     double l;        // isotropic length scale            matern_five_halves.hpp:100
     double noise;    // kernel/kernel.hpp:76-79
     double inv_ell[LB_MAX_D]; // SE-ARD: 1/exp(p_d)
+    double c1;       // Matern: sqrt(5)/l resp. sqrt(3)/l ; Exp: 1/l^2   (host-precomputed, saves a divide per pair)
+    double c2;       // Matern-5/2: 5/(3 l^2)
 };
 
 // ---------------------------------------------------------------------------
@@ -81,6 +83,38 @@ __device__ __forceinline__ double lb_kernel_from_z(int id, double z, double sf2,
         double r = z / (l * l);
         return sf2 * exp(-0.5 * r);
     }
+    }
+}
+
+// Same functors with the per-pair divisions and the square root replaced by host-precomputed reciprocals and a
+// branch-free rsqrt (<= a few ulp from the reference's operation order; K stays within 1e-15 of the Eigen path).
+__device__ __forceinline__ double lb_rsqrt_nr(double x)
+{
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double h = 0.5 * x;
+    r = fma(r, fma(-h * r, r, 0.5), r);
+    r = fma(r, fma(-h * r, r, 0.5), r);
+    return r;
+}
+__device__ __forceinline__ double lb_kernel_from_z(int id, double z, const KernParams& kp)
+{
+    switch (id) {
+    case LB_K_SE_ARD:
+        return kp.sf2 * exp(-0.5 * z);
+    case LB_K_MATERN52: {
+        const double d = (z > 0.0) ? z * lb_rsqrt_nr(z) : 0.0;
+        const double term1 = kp.c1 * d;
+        const double term2 = kp.c2 * (d * d);
+        return kp.sf2 * (1 + term1 + term2) * exp(-term1);
+    }
+    case LB_K_MATERN32: {
+        const double d = (z > 0.0) ? z * lb_rsqrt_nr(z) : 0.0;
+        const double term = kp.c1 * d;
+        return kp.sf2 * (1 + term) * exp(-term);
+    }
+    default:
+        return kp.sf2 * exp(-0.5 * (z * kp.c1));
     }
 }
 

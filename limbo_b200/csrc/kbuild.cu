@@ -37,15 +37,13 @@ __device__ __forceinline__ void tile_from_index(int t, int& bi, int& bj)
     bj = t - r * (r + 1) / 2;
 }
 
-__global__ void __launch_bounds__(256, 2)
-kbuild_kernel(const double* __restrict__ Xs, double* __restrict__ K, int64_t N, int64_t Np, KernParams kp)
+// KID: kernel id (compile time, so only one functor is inlined); EDGE: the tile touches the diagonal or the identity
+// padding (noise / padding predicates); interior tiles (the vast majority) skip every per-element test.
+template <int KID, bool EDGE>
+__device__ __forceinline__ void kbuild_tile(const double* __restrict__ Xs, double* __restrict__ K, int64_t N, int64_t Np,
+    const KernParams& kp, int bi, int bj, double (*sxi)[LB_TILE], double (*sxj)[LB_TILE], uint64_t* barp)
 {
-    __shared__ __align__(128) double sxi[DCH][LB_TILE];
-    __shared__ __align__(128) double sxj[DCH][LB_TILE];
-    __shared__ __align__(8) uint64_t bar;
-
-    int bi, bj;
-    tile_from_index(blockIdx.x, bi, bj);
+    uint64_t& bar = *barp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int li = lane & 7, lj = lane >> 3;
     const int D = kp.D;
@@ -105,10 +103,12 @@ kbuild_kernel(const double* __restrict__ Xs, double* __restrict__ K, int64_t N, 
             double v[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int64_t ii = gi + (e & 1), jj = gj + (e >> 1);
-                double k = lb_kernel_from_z(kp.id, z[c][e], kp.sf2, kp.l);
-                if (ii == jj) k += kp.noise + 1e-8; // kernel.hpp:83
-                if (ii >= N || jj >= N) k = (ii == jj) ? 1.0 : 0.0; // identity padding
+                double k = lb_kernel_from_z(KID, z[c][e], kp);
+                if (EDGE) {
+                    const int64_t ii = gi + (e & 1), jj = gj + (e >> 1);
+                    if (ii == jj) k += kp.noise + 1e-8; // kernel.hpp:83
+                    if (ii >= N || jj >= N) k = (ii == jj) ? 1.0 : 0.0; // identity padding
+                }
                 v[e] = k;
             }
             // tile (rows gi.., col gj / gj+1): two consecutive rows per store
@@ -120,6 +120,20 @@ kbuild_kernel(const double* __restrict__ Xs, double* __restrict__ K, int64_t N, 
             }
         }
     }
+}
+
+template <int KID>
+__global__ void __launch_bounds__(256, 2)
+kbuild_kernel(const double* __restrict__ Xs, double* __restrict__ K, int64_t N, int64_t Np, KernParams kp)
+{
+    __shared__ __align__(128) double sxi[DCH][LB_TILE];
+    __shared__ __align__(128) double sxj[DCH][LB_TILE];
+    __shared__ __align__(8) uint64_t bar;
+    int bi, bj;
+    tile_from_index(blockIdx.x, bi, bj);
+    const bool edge = (bi == bj) || ((int64_t)(bi + 1) * LB_TILE > N);
+    if (edge) kbuild_tile<KID, true>(Xs, K, N, Np, kp, bi, bj, sxi, sxj, &bar);
+    else kbuild_tile<KID, false>(Xs, K, N, Np, kp, bi, bj, sxi, sxj, &bar);
 }
 
 } // namespace
@@ -138,7 +152,12 @@ int lb_launch_kbuild(lb_gp* h, double* dK)
     const int64_t T = h->Np / LB_TILE;
     const int64_t tiles = T * (T + 1) / 2;
     LbProfScope ps(h, h->stream, LB_PC_KBUILD);
-    kbuild_kernel<<<(unsigned)tiles, 256, 0, h->stream>>>(h->dXs, dK, h->N, h->Np, h->kp);
+    switch (h->kp.id) {
+    case LB_K_SE_ARD: kbuild_kernel<LB_K_SE_ARD><<<(unsigned)tiles, 256, 0, h->stream>>>(h->dXs, dK, h->N, h->Np, h->kp); break;
+    case LB_K_MATERN52: kbuild_kernel<LB_K_MATERN52><<<(unsigned)tiles, 256, 0, h->stream>>>(h->dXs, dK, h->N, h->Np, h->kp); break;
+    case LB_K_MATERN32: kbuild_kernel<LB_K_MATERN32><<<(unsigned)tiles, 256, 0, h->stream>>>(h->dXs, dK, h->N, h->Np, h->kp); break;
+    default: kbuild_kernel<LB_K_EXP><<<(unsigned)tiles, 256, 0, h->stream>>>(h->dXs, dK, h->N, h->Np, h->kp); break;
+    }
     h->launches++;
     LB_CUDA(cudaGetLastError());
     return LB_OK;

@@ -78,7 +78,7 @@ kstar_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, const double*
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int64_t ii = gi + (e & 1), jj = gj + (e >> 1);
-                double k = lb_kernel_from_z(kp.id, z[c][e], kp.sf2, kp.l);
+                double k = lb_kernel_from_z(kp.id, z[c][e], kp);
                 if (ii >= N || jj >= M) k = 0.0;
                 v[e] = k;
             }
@@ -468,7 +468,7 @@ query_slab_kernel(const double* __restrict__ L, int64_t ld, const double* __rest
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int64_t gr = row0 + r_lo + 8 * (e >> 1), gc = c0 + cl + (e & 1);
-                            double k = lb_kernel_from_z(kp.id, z[e], kp.sf2, kp.l);
+                            double k = lb_kernel_from_z(kp.id, z[e], kp);
                             if (gr >= N || gc >= M) k = 0.0;
                             acc[nt][e] = k;
                         }
