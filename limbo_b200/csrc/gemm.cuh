@@ -4,7 +4,7 @@
 // drive the DMMA pipe of its SM sub-partition at half rate — measured,
 // profiles/r01_microbench.json — so every sub-partition gets 4 warps) accumulates a
 // 128 x BN tile  acc += A(128 x K) * B(K x BN)  with a 3-stage cp.async
-// pipeline (BK = 16).  Both operands can be "outer-contiguous" (the m / n index
+// pipeline (BK = 32: one CTA barrier per 32 k).  Both operands can be "outer-contiguous" (the m / n index
 // is the unit-stride one, i.e. a column-major 128 x K block) or "K-contiguous"
 // (the k index is unit-stride).  Shared-memory tiles are padded (+4 doubles)
 // so every 64-bit fragment load is bank-conflict free.
@@ -18,7 +18,7 @@
 namespace lbg {
 
 constexpr int BM = 128;
-constexpr int BK = 16;
+constexpr int BK = 32;
 constexpr int STAGES = 3;
 constexpr int THREADS = 512;
 constexpr int PITCH_OC = BM + 4; // outer-contiguous tile: [BK][128+4]
@@ -32,9 +32,10 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
 {
     const int tid = threadIdx.x;
     if (KC) {
-        // element (o, k) at g[k + o*ld]; smem [o][k], 8 chunks of 16 B per row
-        for (int c = tid; c < nouter * 8; c += THREADS) {
-            int o = c >> 3, kc = c & 7;
+        // element (o, k) at g[k + o*ld]; smem [o][k], BK/2 chunks of 16 B per row
+        constexpr int CPR = BK / 2;
+        for (int c = tid; c < nouter * CPR; c += THREADS) {
+            int o = c / CPR, kc = c - o * CPR;
             lb_cp_async16(s + o * PITCH_KC + 2 * kc, g + (int64_t)o * ld + 2 * kc);
         }
     }

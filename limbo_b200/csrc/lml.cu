@@ -52,38 +52,6 @@ __global__ void set_identity_kernel(double* __restrict__ A, int64_t n)
     }
 }
 
-// Block row i of X = L^-1 (X lower triangular, stored full Np x Np, zero above):
-//   X[i,j] = -inv(L_ii) * sum_{k=j}^{i-1} L[i,k] X[k,j]   (j < i),  X[i,i] = inv(L_ii)
-// grid = i + 1 column tiles.
-__global__ void __launch_bounds__(lbg::THREADS, 1)
-trtri_row_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ invD, double* __restrict__ X, int i)
-{
-    extern __shared__ __align__(16) double smem[];
-    constexpr int PB = lbg::BM + 4;
-    double* sT = smem + lbg::STAGES * lbg::STAGE_DOUBLES;
-    const int j = blockIdx.x;
-    double* Xij = X + (int64_t)i * LB_TILE + (int64_t)j * LB_TILE * ld;
-    const double* Di = invD + (int64_t)i * LB_TILE * LB_TILE;
-    if (j == i) {
-        for (int idx = threadIdx.x; idx < LB_TILE * LB_TILE; idx += lbg::THREADS) {
-            int r = idx & 127, c = idx >> 7;
-            Xij[r + (int64_t)c * ld] = Di[r + c * LB_TILE];
-        }
-        return;
-    }
-    lbg::Acc<128> acc;
-    acc.zero();
-    // A = L[i, j..i-1] (outer-contiguous), B = X[j..i-1, j] (k-contiguous)
-    lbg::mainloop<128, false, true, true>(acc, L + (int64_t)i * LB_TILE + (int64_t)j * LB_TILE * ld, ld,
-        X + (int64_t)j * LB_TILE + (int64_t)j * LB_TILE * ld, ld, (i - j) * LB_TILE, smem);
-    lbg::for_each_acc<128>(acc, [&](int r, int c, double v) { sT[c * PB + r] = v; });
-    __syncthreads();
-    lbg::Acc<128> acc2;
-    acc2.zero();
-    lbg::mainloop_resB<128>(acc2, Di, LB_TILE, sT, smem);
-    lbg::for_each_acc<128>(acc2, [&](int r, int c, double v) { Xij[r + (int64_t)c * ld] = v; });
-}
-
 // ---- recursive (divide and conquer) triangular inverse ----------------------------------
 // inv [[A,0],[B,C]] = [[A^-1, 0], [-C^-1 B A^-1, C^-1]].  Level with half-size sb (in 128-blocks): the matrix is cut
 // into problems of 2*sb block rows; problem q has A = X[a0:a0+sb, a0:a0+sb] and C = X[c0:c0+sb, c0:c0+sb] already
@@ -388,13 +356,11 @@ grad_reduce_kernel(const double* __restrict__ part, int ntiles, int nh, double* 
     }
 }
 
-constexpr size_t TRTRI_SMEM = (size_t)lbg::STAGES * lbg::STAGE_DOUBLES * sizeof(double) + (size_t)128 * (lbg::BM + 4) * sizeof(double);
 
 bool g_attr_done = false;
 int set_attrs()
 {
     if (g_attr_done) return LB_OK;
-    LB_CUDA(cudaFuncSetAttribute(trtri_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRTRI_SMEM));
     LB_CUDA(cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::PIPE_BYTES));
     LB_CUDA(cudaFuncSetAttribute(trtri_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::PIPE_BYTES));
     g_attr_done = true;

@@ -255,7 +255,6 @@ bool g_attr_done = false;
 int set_attrs()
 {
     if (g_attr_done) return LB_OK;
-    LB_CUDA(cudaFuncSetAttribute(query_step_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<128>()));
     LB_CUDA(cudaFuncSetAttribute(query_step_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<64>()));
     g_attr_done = true;
     return LB_OK;
@@ -269,13 +268,9 @@ int lb_launch_trsm_lower(const lb_gp* h, cudaStream_t st, double* dV, int64_t Mp
     int rc = set_attrs();
     if (rc) return rc;
     const int T = (int)(h->Np / LB_TILE);
-    const bool wide = (Mp / 128) >= 120;
     LbProfScope ps(h, st, LB_PC_QSTEP);
     for (int i = i_begin; i < T; ++i) {
-        if (wide)
-            query_step_kernel<128><<<(unsigned)(Mp / 128), lbg::THREADS, step_smem<128>(), st>>>(h->dL, h->Np, h->dInvD, dV, i);
-        else
-            query_step_kernel<64><<<(unsigned)(Mp / 64), lbg::THREADS, step_smem<64>(), st>>>(h->dL, h->Np, h->dInvD, dV, i);
+        query_step_kernel<64><<<(unsigned)(Mp / 64), lbg::THREADS, step_smem<64>(), st>>>(h->dL, h->Np, h->dInvD, dV, i);
         if (launches) ++*launches;
     }
     LB_CUDA(cudaGetLastError());
