@@ -60,7 +60,7 @@ __global__ void set_identity_kernel(double* __restrict__ A, int64_t n)
 //   step 2:  X[C rows, A cols] = -C^-1 * W   [i,j] = -sum_{k <= i} Cinv[i,k] W[k,j]
 // All tiles of a level are independent (one launch per step), unlike the block-row recurrence whose j = 0
 // tile serialises T^2/2 K-chunks on one SM.
-__global__ void __launch_bounds__(lbg::THREADS, 1)
+__global__ void __launch_bounds__(lbg::CfgWide::THREADS, 1)
 trtri_level_kernel(const double* __restrict__ L, double* __restrict__ X, double* __restrict__ W, int64_t ld, int sb, int step,
     int T)
 {
@@ -72,24 +72,24 @@ trtri_level_kernel(const double* __restrict__ L, double* __restrict__ X, double*
     int nC = sb;                       // block rows available in the C part (last problem may be short)
     if (c0 >= T) return;
     if (c0 + nC > T) nC = T - c0;
-    lbg::Acc<128> acc;
+    lbg::Acc<lbg::CfgWide> acc;
     acc.zero();
     if (step == 1) {
         const int j = rem / sb, i = rem - j * sb; // heavy tiles (small j) first
         if (i >= nC) return;
         // A = B[i, j..sb-1] = L[(c0+i), (a0+j)...] (outer-contiguous); Bop(k,n) = Ainv[(a0+j)+k, (a0+j)*128+n] (k-contiguous)
-        lbg::mainloop<128, false, true>(acc, L + (int64_t)(c0 + i) * LB_TILE + (int64_t)(a0 + j) * LB_TILE * ld, ld,
+        lbg::mainloop<lbg::CfgWide, false, true>(acc, L + (int64_t)(c0 + i) * LB_TILE + (int64_t)(a0 + j) * LB_TILE * ld, ld,
             X + (int64_t)(a0 + j) * LB_TILE + (int64_t)(a0 + j) * LB_TILE * ld, ld, (sb - j) * LB_TILE, smem);
-        lbg::store_acc<128>(acc, W + (int64_t)(c0 + i) * LB_TILE + (int64_t)(a0 + j) * LB_TILE * ld, ld);
+        lbg::store_acc<lbg::CfgWide>(acc, W + (int64_t)(c0 + i) * LB_TILE + (int64_t)(a0 + j) * LB_TILE * ld, ld);
     }
     else {
         const int ii = rem / sb, j = rem - ii * sb;
         const int i = sb - 1 - ii; // heavy tiles (large i) first
         if (i >= nC) return;
         // A = Cinv[i, 0..i] = X[(c0+i), c0...] (outer-contiguous); Bop(k,n) = W[c0*128 + k, (a0+j)*128 + n] (k-contiguous)
-        lbg::mainloop<128, false, true, true>(acc, X + (int64_t)(c0 + i) * LB_TILE + (int64_t)c0 * LB_TILE * ld, ld,
+        lbg::mainloop<lbg::CfgWide, false, true, true>(acc, X + (int64_t)(c0 + i) * LB_TILE + (int64_t)c0 * LB_TILE * ld, ld,
             W + (int64_t)c0 * LB_TILE + (int64_t)(a0 + j) * LB_TILE * ld, ld, (i + 1) * LB_TILE, smem);
-        lbg::store_acc<128>(acc, X + (int64_t)(c0 + i) * LB_TILE + (int64_t)(a0 + j) * LB_TILE * ld, ld);
+        lbg::store_acc<lbg::CfgWide>(acc, X + (int64_t)(c0 + i) * LB_TILE + (int64_t)(a0 + j) * LB_TILE * ld, ld);
     }
 }
 
@@ -106,7 +106,7 @@ trtri_diag_copy_kernel(const double* __restrict__ invD, double* __restrict__ X, 
 }
 
 // Kinv[i,j] = sum_{k >= i} X[k,i]^T X[k,j]  for i >= j (lower tiles only)
-__global__ void __launch_bounds__(lbg::THREADS, 1)
+__global__ void __launch_bounds__(lbg::CfgWide::THREADS, 1)
 lauum_kernel(const double* __restrict__ X, int64_t ld, double* __restrict__ Kinv, int T)
 {
     extern __shared__ __align__(16) double smem[];
@@ -116,13 +116,13 @@ lauum_kernel(const double* __restrict__ X, int64_t ld, double* __restrict__ Kinv
     while ((int64_t)(r + 1) * (r + 2) / 2 <= t) ++r;
     while ((int64_t)r * (r + 1) / 2 > t) --r;
     const int i = r, j = t - r * (r + 1) / 2;
-    lbg::Acc<128> acc;
+    lbg::Acc<lbg::CfgWide> acc;
     acc.zero();
     const int64_t k0 = (int64_t)i * LB_TILE;
-    lbg::mainloop<128, true, true>(acc, X + k0 + (int64_t)i * LB_TILE * ld, ld, X + k0 + (int64_t)j * LB_TILE * ld, ld,
+    lbg::mainloop<lbg::CfgWide, true, true>(acc, X + k0 + (int64_t)i * LB_TILE * ld, ld, X + k0 + (int64_t)j * LB_TILE * ld, ld,
         (T - i) * LB_TILE, smem);
     double* C = Kinv + (int64_t)i * LB_TILE + (int64_t)j * LB_TILE * ld;
-    lbg::for_each_acc<128>(acc, [&](int rr, int cc, double v) { C[rr + (int64_t)cc * ld] = v; });
+    lbg::store_acc<lbg::CfgWide>(acc, C, ld);
 }
 
 // mirror lower -> upper (export only)
@@ -361,8 +361,8 @@ bool g_attr_done = false;
 int set_attrs()
 {
     if (g_attr_done) return LB_OK;
-    LB_CUDA(cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::PIPE_BYTES));
-    LB_CUDA(cudaFuncSetAttribute(trtri_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::PIPE_BYTES));
+    LB_CUDA(cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::CfgWide::PIPE_BYTES));
+    LB_CUDA(cudaFuncSetAttribute(trtri_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::CfgWide::PIPE_BYTES));
     g_attr_done = true;
     return LB_OK;
 }
@@ -394,7 +394,7 @@ int lb_launch_linv(lb_gp* h)
     for (int sb = 1; sb < T; sb *= 2) {
         const int nprob = (T + 2 * sb - 1) / (2 * sb);
         for (int step = 1; step <= 2; ++step) {
-            trtri_level_kernel<<<nprob * sb * sb, lbg::THREADS, lbg::PIPE_BYTES, h->stream>>>(h->dL, h->dLinv, h->dKinv, h->Np, sb,
+            trtri_level_kernel<<<nprob * sb * sb, lbg::CfgWide::THREADS, lbg::CfgWide::PIPE_BYTES, h->stream>>>(h->dL, h->dLinv, h->dKinv, h->Np, sb,
                 step, T);
             h->launches++;
         }
@@ -415,7 +415,7 @@ int lb_launch_kinv(lb_gp* h)
     const int T = (int)(h->Np / LB_TILE);
     if (!h->dKinv) LB_CUDA(cudaMalloc(&h->dKinv, sizeof(double) * h->Np * h->Np));
     LbProfScope ps(h, h->stream, LB_PC_LAUUM);
-    lauum_kernel<<<T * (T + 1) / 2, lbg::THREADS, lbg::PIPE_BYTES, h->stream>>>(h->dLinv, h->Np, h->dKinv, T);
+    lauum_kernel<<<T * (T + 1) / 2, lbg::CfgWide::THREADS, lbg::CfgWide::PIPE_BYTES, h->stream>>>(h->dLinv, h->Np, h->dKinv, T);
     h->launches++;
     LB_CUDA(cudaGetLastError());
     h->kinv_valid = true;

@@ -232,17 +232,18 @@ potf2_inv_kernel(double* __restrict__ L, int64_t ld, int k, double* __restrict__
 }
 
 // L[i,k] <- A[i,k] * inv(L[k,k])^T for i = k+1 .. T-1
-__global__ void __launch_bounds__(lbg::THREADS, 1)
+__global__ void __launch_bounds__(lbg::CfgWide::THREADS, 1)
 trsm_panel_kernel(double* __restrict__ L, int64_t ld, int k, const double* __restrict__ invD)
 {
+    using C = lbg::CfgWide;
     extern __shared__ __align__(16) double smem[];
     const int i = k + 1 + blockIdx.x;
     double* A = L + (int64_t)i * LB_TILE + (int64_t)k * LB_TILE * ld;
     const double* B = invD + (int64_t)k * LB_TILE * LB_TILE; // B(kk,n) = inv[n + kk*128]
-    lbg::Acc<128> acc;
+    lbg::Acc<C> acc;
     acc.zero();
-    lbg::mainloop<128, false, false>(acc, A, ld, B, LB_TILE, LB_TILE, smem);
-    lbg::for_each_acc<128>(acc, [&](int r, int c, double v) { A[r + (int64_t)c * ld] = v; });
+    lbg::mainloop<C, false, false>(acc, A, ld, B, LB_TILE, LB_TILE, smem);
+    lbg::store_acc<C>(acc, A, ld);
 }
 
 // Trailing update with the panel block columns [kb, kb + kd):
@@ -250,29 +251,37 @@ trsm_panel_kernel(double* __restrict__ L, int64_t ld, int k, const double* __res
 // (kd = 1: one 128-column panel, K = 128; kd = 2: two panels at once, K = 256 —
 // half the C traffic and half the tile prologues per flop).  C is preloaded into
 // the accumulators so its latency overlaps the operand pipeline's prologue.
-__global__ void __launch_bounds__(lbg::THREADS, 1)
+// Cfg = CfgDual: 128 x 64 tiles, 256 threads, two CTAs per SM (one CTA's C-tile prologue / store epilogue
+// hides under the other's DMMA stream).
+template <typename C>
+__global__ void __launch_bounds__(C::THREADS, (C::THREADS == 256) ? 2 : 1)
 syrk_kernel(double* __restrict__ L, int64_t ld, int kb, int kd, int j0, int nc, int T)
 {
     extern __shared__ __align__(16) double smem[];
-    int idx = blockIdx.x, c = 0;
+    constexpr int SPLIT = LB_TILE / C::BN; // column sub-tiles per 128-block
+    int idx = blockIdx.x / SPLIT, c = 0;
+    const int h = blockIdx.x - idx * SPLIT;
     while (c < nc && idx >= T - j0 - c) { idx -= T - j0 - c; ++c; }
     const int j = j0 + c, i = j + idx;
     const double* A = L + (int64_t)i * LB_TILE + (int64_t)kb * LB_TILE * ld;
-    const double* B = L + (int64_t)j * LB_TILE + (int64_t)kb * LB_TILE * ld;
-    double* C = L + (int64_t)i * LB_TILE + (int64_t)j * LB_TILE * ld;
-    lbg::Acc<128> acc;
-    lbg::load_acc<128>(acc, C, ld);
-    lbg::mainloop<128, false, false, true>(acc, A, ld, B, ld, kd * LB_TILE, smem);
-    lbg::store_acc<128>(acc, C, ld);
+    const double* B = L + (int64_t)j * LB_TILE + h * C::BN + (int64_t)kb * LB_TILE * ld;
+    double* Cg = L + (int64_t)i * LB_TILE + ((int64_t)j * LB_TILE + h * C::BN) * ld;
+    lbg::Acc<C> acc;
+    lbg::load_acc<C>(acc, Cg, ld);
+    lbg::mainloop<C, false, false, true>(acc, A, ld, B, ld, kd * LB_TILE, smem);
+    lbg::store_acc<C>(acc, Cg, ld);
 }
+
+using SyrkCfg = lbg::CfgDual;
+constexpr int SYRK_SPLIT = LB_TILE / SyrkCfg::BN;
 
 bool g_attr_done = false;
 int set_attrs()
 {
     if (g_attr_done) return LB_OK;
     LB_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTF2_SMEM));
-    LB_CUDA(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::PIPE_BYTES));
-    LB_CUDA(cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::PIPE_BYTES));
+    LB_CUDA(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::CfgWide::PIPE_BYTES));
+    LB_CUDA(cudaFuncSetAttribute(syrk_kernel<SyrkCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg::PIPE_BYTES));
     g_attr_done = true;
     return LB_OK;
 }
@@ -341,11 +350,11 @@ int lb_launch_potrf(lb_gp* h)
         if (pair) {
             {
                 LbProfScope ps(h, side, LB_PC_TRSM_PANEL);
-                trsm_panel_kernel<<<T - k - 1, lbg::THREADS, lbg::PIPE_BYTES, side>>>(h->dL, ld, k, h->dInvD);
+                trsm_panel_kernel<<<T - k - 1, lbg::CfgWide::THREADS, lbg::CfgWide::PIPE_BYTES, side>>>(h->dL, ld, k, h->dInvD);
             }
             {
                 LbProfScope ps(h, side, LB_PC_SYRK_COL);
-                syrk_kernel<<<T - k - 1, lbg::THREADS, lbg::PIPE_BYTES, side>>>(h->dL, ld, k, 1, k + 1, 1, T);
+                syrk_kernel<SyrkCfg><<<(T - k - 1) * SYRK_SPLIT, SyrkCfg::THREADS, SyrkCfg::PIPE_BYTES, side>>>(h->dL, ld, k, 1, k + 1, 1, T);
             }
             {
                 LbProfScope ps(h, side, LB_PC_POTF2);
@@ -354,7 +363,7 @@ int lb_launch_potrf(lb_gp* h)
             h->launches += 3;
             if (k + 2 < T) {
                 LbProfScope ps(h, side, LB_PC_TRSM_PANEL);
-                trsm_panel_kernel<<<T - k - 2, lbg::THREADS, lbg::PIPE_BYTES, side>>>(h->dL, ld, k + 1, h->dInvD);
+                trsm_panel_kernel<<<T - k - 2, lbg::CfgWide::THREADS, lbg::CfgWide::PIPE_BYTES, side>>>(h->dL, ld, k + 1, h->dInvD);
                 h->launches++;
             }
         }
@@ -368,7 +377,7 @@ int lb_launch_potrf(lb_gp* h)
         const int nca = (T - j0 < 2) ? (T - j0) : 2;
         {
             LbProfScope ps(h, main, LB_PC_SYRK);
-            syrk_kernel<<<syrk_tiles(T, j0, nca), lbg::THREADS, lbg::PIPE_BYTES, main>>>(h->dL, ld, k, 2, j0, nca, T);
+            syrk_kernel<SyrkCfg><<<syrk_tiles(T, j0, nca) * SYRK_SPLIT, SyrkCfg::THREADS, SyrkCfg::PIPE_BYTES, main>>>(h->dL, ld, k, 2, j0, nca, T);
         }
         h->launches++;
         if (side != main) {
@@ -379,7 +388,7 @@ int lb_launch_potrf(lb_gp* h)
         const int ncb = T - j0 - nca;
         if (ncb > 0) {
             LbProfScope ps(h, main, LB_PC_SYRK);
-            syrk_kernel<<<syrk_tiles(T, j0 + nca, ncb), lbg::THREADS, lbg::PIPE_BYTES, main>>>(h->dL, ld, k, 2, j0 + nca, ncb, T);
+            syrk_kernel<SyrkCfg><<<syrk_tiles(T, j0 + nca, ncb) * SYRK_SPLIT, SyrkCfg::THREADS, SyrkCfg::PIPE_BYTES, main>>>(h->dL, ld, k, 2, j0 + nca, ncb, T);
             h->launches++;
         }
     }

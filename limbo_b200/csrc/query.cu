@@ -113,27 +113,27 @@ mu_kernel(const double* __restrict__ V, int64_t Np, const double* __restrict__ a
 
 // One block-row step of V <- L^-1 V:
 //   V_i <- inv(L_ii) * (V_i - L[i, 0:i] V[0:i])          grid = Mp / BN
-template <int BN>
-__global__ void __launch_bounds__(lbg::THREADS, 1)
+template <typename C>
+__global__ void __launch_bounds__(C::THREADS, 1)
 query_step_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ invD, double* __restrict__ V,
     int i)
 {
     extern __shared__ __align__(16) double smem[];
     constexpr int PB = lbg::BM + 4;
-    double* sT = smem + lbg::STAGES * lbg::STAGE_DOUBLES; // overlays the B pipeline stages
-    const int64_t col0 = (int64_t)blockIdx.x * BN;
+    double* sT = smem + C::A_PIPE_DOUBLES; // overlays the B pipeline stages
+    const int64_t col0 = (int64_t)blockIdx.x * C::BN;
     double* Vc = V + col0 * ld;
-    lbg::Acc<BN> acc;
+    lbg::Acc<C> acc;
     double* Vi = Vc + (int64_t)i * LB_TILE;
-    lbg::load_acc<BN>(acc, Vi, ld); // acc = V_i, then acc -= L[i,0:i] V[0:i]
-    if (i > 0) lbg::mainloop<BN, false, true, true>(acc, L + (int64_t)i * LB_TILE, ld, Vc, ld, i * LB_TILE, smem);
+    lbg::load_acc<C>(acc, Vi, ld); // acc = V_i, then acc -= L[i,0:i] V[0:i]
+    if (i > 0) lbg::mainloop<C, false, true, true>(acc, L + (int64_t)i * LB_TILE, ld, Vc, ld, i * LB_TILE, smem);
     // t -> smem [n][k]
-    lbg::for_each_acc<BN>(acc, [&](int r, int c, double v) { sT[c * PB + r] = v; });
+    lbg::for_each_acc<C>(acc, [&](int r, int c, double& v) { sT[c * PB + r] = v; });
     __syncthreads();
-    lbg::Acc<BN> acc2;
+    lbg::Acc<C> acc2;
     acc2.zero();
-    lbg::mainloop_resB<BN>(acc2, invD + (int64_t)i * LB_TILE * LB_TILE, LB_TILE, sT, smem);
-    lbg::for_each_acc<BN>(acc2, [&](int r, int c, double v) { Vi[r + (int64_t)c * ld] = v; });
+    lbg::mainloop_resB<C>(acc2, invD + (int64_t)i * LB_TILE * LB_TILE, LB_TILE, sT, smem);
+    lbg::store_acc<C>(acc2, Vi, ld);
 }
 
 // sigma2[m] = k(v,v) - |V_m|^2, clamped (gp.hpp:623), + noise (gp.hpp:166)
@@ -242,20 +242,20 @@ argmax_final_kernel(int nblk, const double* __restrict__ blk_val, const long lon
     }
 }
 
-template <int BN>
+using StepCfg = lbg::CfgStep;
 constexpr size_t step_smem()
 {
-    return (size_t)lbg::STAGES * lbg::STAGE_DOUBLES * sizeof(double)
-        + ((size_t)BN * (lbg::BM + 4) * sizeof(double) > (size_t)lbg::STAGES * lbg::STAGE_DOUBLES * sizeof(double)
-                  ? (size_t)BN * (lbg::BM + 4) * sizeof(double)
-                  : (size_t)lbg::STAGES * lbg::STAGE_DOUBLES * sizeof(double));
+    constexpr size_t a = (size_t)StepCfg::A_PIPE_DOUBLES * sizeof(double);
+    constexpr size_t b = (size_t)lbg::STAGES * StepCfg::B_STAGE * sizeof(double);
+    constexpr size_t t = (size_t)StepCfg::BN * (lbg::BM + 4) * sizeof(double);
+    return a + (t > b ? t : b);
 }
 
 bool g_attr_done = false;
 int set_attrs()
 {
     if (g_attr_done) return LB_OK;
-    LB_CUDA(cudaFuncSetAttribute(query_step_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<64>()));
+    LB_CUDA(cudaFuncSetAttribute(query_step_kernel<StepCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem()));
     g_attr_done = true;
     return LB_OK;
 }
@@ -270,7 +270,7 @@ int lb_launch_trsm_lower(const lb_gp* h, cudaStream_t st, double* dV, int64_t Mp
     const int T = (int)(h->Np / LB_TILE);
     LbProfScope ps(h, st, LB_PC_QSTEP);
     for (int i = i_begin; i < T; ++i) {
-        query_step_kernel<64><<<(unsigned)(Mp / 64), lbg::THREADS, step_smem<64>(), st>>>(h->dL, h->Np, h->dInvD, dV, i);
+        query_step_kernel<StepCfg><<<(unsigned)(Mp / StepCfg::BN), StepCfg::THREADS, step_smem(), st>>>(h->dL, h->Np, h->dInvD, dV, i);
         if (launches) ++*launches;
     }
     LB_CUDA(cudaGetLastError());
