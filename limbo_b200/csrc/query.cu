@@ -369,8 +369,7 @@ __device__ __forceinline__ void load_A_stage(double* s, const double* __restrict
 __device__ __forceinline__ void load_B_stage(double* s, const double* __restrict__ g, int64_t ld, int ncols)
 {
     // ncols candidates x 16 k (k-contiguous): ncols * 8 chunks
-    int c = threadIdx.x;
-    if (c < ncols * 8) {
+    for (int c = threadIdx.x; c < ncols * 8; c += THREADS) { // up to 576 chunks: more than one per thread
         int n = c >> 3, kc = c & 7;
         lb_cp_async16(s + n * PBK + 2 * kc, g + (int64_t)n * ld + 2 * kc);
     }

@@ -1,0 +1,122 @@
+"""BASELINE.json's configurations at full size.
+ * config 2 (N=4096, D=6, MaternFiveHalves, 10k UCB queries) is small enough to check DIRECTLY against the
+   oracle (3 s fit on one host core).
+ * config 3 (N=16384, D=6, SquaredExpARD, log-lik + gradient) is checked through size-independent properties:
+   K alpha = y residual with an independently formed K, interpolation bounds (test_gp.cpp:467-500), analytic
+   gradient vs central finite differences of the device log-lik (test_gp.cpp:131-193 style), batched == single
+   query, acquisition argmax == argmax of the returned values, add_sample == fresh compute (test_gp.cpp:568-635)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config2_matern_n4096_vs_oracle(oracle_mod):
+    from limbo_b200 import acqui, kernel, mean, model, synth
+    O = oracle_mod
+    N, D, M = 4096, 6, 10000
+    X = synth.points(1234, N, D)
+    y = synth.targets(X)
+    Xq = synth.points(1235, M, D)
+    gp = model.GP(D, 1, kernel=kernel.MaternFiveHalves, mean=mean.Data)
+    gp.compute(list(X), list(y[:, None]))
+    assert gp.chol_info() == 0
+    og = O.OracleGP()
+    og.set_data(X, (y - y.mean())[:, None])
+    og.set_kernel(O.K_MATERN52, np.zeros(2), 0.01)
+    assert og.fit() == -1
+    A, Ao = gp.alpha(), og.get(2)
+    assert np.abs(A - Ao).max() <= 1e-9 * np.abs(Ao).max()
+    best, idx, vals = acqui.UCB(gp).argmax_batch(Xq, return_values=True)
+    mu, s2 = gp.query_batch(Xq)
+    sub = np.arange(0, M, 5)  # 2000 oracle queries, fanned over the host threads
+    mu_o, s2_o = og.query(Xq[sub], nthreads=16)
+    assert np.abs(mu[sub, 0] - (mu_o[:, 0] + y.mean())).max() <= 1e-10
+    assert np.abs(s2[sub] - s2_o).max() <= 1e-10
+    ucb_o = O.ucb(mu_o[:, 0] + y.mean(), s2_o, 0.5)
+    assert np.abs(vals[sub] - ucb_o).max() <= 1e-10
+    assert idx == int(np.argmax(vals)) and best == vals[idx]
+    ll, llo = gp.compute_log_lik(), og.log_lik()
+    assert abs(ll - llo) <= 1e-10 * abs(llo)
+
+
+@pytest.fixture(scope="module")
+def gp16k():
+    from limbo_b200 import kernel, mean, model, synth
+    N, D = 16384, 6
+    X = synth.points(1234, N, D)
+    y = synth.targets(X)
+    gp = model.GP(D, 1, kernel=kernel.SquaredExpARD, mean=mean.Data)
+    gp.compute(list(X), list(y[:, None]))
+    return gp, X, y
+
+
+def test_config3_factor_residual_and_interpolation(gp16k):
+    gp, X, y = gp16k
+    assert gp.chol_info() == 0
+    N = len(y)
+    a = gp.alpha()[:, 0]
+    # independent K (numpy, row blocks) times alpha must give back obs_mean
+    om = y - y.mean()
+    res = 0.0
+    for lo in range(0, N, 2048):
+        d2 = ((X[lo:lo + 2048, None, :] - X[None, :, :]) ** 2).sum(-1)
+        Kb = np.exp(-0.5 * d2)
+        Kb[np.arange(Kb.shape[0]), np.arange(lo, lo + Kb.shape[0])] += 0.01 + 1e-8
+        res = max(res, np.abs(Kb @ a - om[lo:lo + 2048]).max())
+    assert res <= 1e-9 * max(1.0, np.abs(a).max()), res
+    # query path vs fit path at the training points: K alpha = y - m  =>  mu(x_i) = y_i - (noise + 1e-8) alpha_i exactly,
+    # and noise <= sigma^2(x_i) = 2 noise + 1e-8 - (noise + 1e-8)^2 (K^-1)_ii <= 2 (noise + 1e-8)   (test_gp.cpp:467-500 bounds)
+    mu, s2 = gp.query_batch(X[:3000])
+    assert np.abs(mu[:, 0] - (y[:3000] - (0.01 + 1e-8) * a[:3000])).max() <= 1e-9
+    assert np.all(s2 <= 2 * (0.01 + 1e-8) + 1e-12) and np.all(s2 >= 0.01 - 1e-12)
+
+
+def test_config3_loglik_gradient_vs_fd(gp16k):
+    gp, X, y = gp16k
+    k = gp.kernel_function()
+    hp0 = np.array([0.1, -0.05, 0.2, 0.0, 0.15, -0.1, 0.05])
+    k.set_h_params(hp0)
+    gp.recompute(False)
+    ll0 = gp.compute_log_lik()
+    g = gp.compute_kernel_grad_log_lik()
+    eps = 1e-4
+    for i in (0, 3, 6):
+        hp = hp0.copy(); hp[i] += eps
+        k.set_h_params(hp); gp.recompute(False); lp = gp.compute_log_lik()
+        hp = hp0.copy(); hp[i] -= eps
+        k.set_h_params(hp); gp.recompute(False); lm = gp.compute_log_lik()
+        fd = (lp - lm) / (2 * eps)
+        assert abs(fd - g[i]) <= 2e-5 * max(1.0, abs(g[i])), (i, fd, g[i])
+    k.set_h_params(np.zeros(7))
+    gp.recompute(False)
+    assert np.isfinite(ll0)
+
+
+def test_config3_batched_equals_single_and_argmax(gp16k):
+    from limbo_b200 import acqui, synth
+    gp, X, y = gp16k
+    Xq = synth.points(1235, 3000, 6)
+    mu, s2 = gp.query_batch(Xq)
+    for i in (0, 1234, 2999):
+        m1, s1 = gp.query(Xq[i])
+        assert m1[0] == mu[i, 0] and s1 == s2[i]
+    best, idx, vals = acqui.EI(gp).argmax_batch(Xq, return_values=True)
+    assert idx == int(np.argmax(vals)) and best == vals[idx]
+    assert np.all(vals >= 0.0)
+
+
+def test_config3_add_sample_equals_fresh_compute():
+    from limbo_b200 import kernel, mean, model, synth
+    N, D = 16384, 6  # the appended sample crosses the 128-padding boundary (capacity grows by one tile)
+    X = synth.points(1234, N + 1, D)
+    y = synth.targets(X)
+    gp = model.GP(D, 1, kernel=kernel.SquaredExpARD, mean=mean.Data)
+    gp.compute(list(X[:N]), list(y[:N, None]))
+    gp.add_sample(X[N], y[N:N + 1])
+    gp2 = model.GP(D, 1, kernel=kernel.SquaredExpARD, mean=mean.Data)
+    gp2.compute(list(X), list(y[:, None]))
+    Xq = synth.points(99, 500, D)
+    (m1, s1), (m2, s2) = gp.query_batch(Xq), gp2.query_batch(Xq)
+    assert np.abs(m1 - m2).max() <= 1e-9 and np.abs(s1 - s2).max() <= 1e-10
+    assert abs(gp.compute_log_lik() - gp2.compute_log_lik()) <= 1e-9 * abs(gp2.compute_log_lik())

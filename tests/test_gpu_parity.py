@@ -322,3 +322,15 @@ def test_fused_and_multilaunch_query_paths_agree(oracle_mod, lib):
     mu, s2 = gp.query_batch(Xq)
     mu_o, s2_o = og.query(Xq)
     assert np.abs(mu - (mu_o + Y.mean(axis=0))).max() <= TOL_ABS and np.abs(s2 - s2_o).max() <= TOL_ABS
+
+
+def test_query_slab_nine_tiles(oracle_mod):
+    """M = 10000 candidates -> slabs of 8 and 9 n8-tiles per CTA (the benchmark shape).  Regression for the B-stage
+    loader that skipped the 9th tile (caught by tests/test_gpu_fullsize.py)."""
+    from limbo_b200 import synth
+    gp, og, X, Y = _make("SquaredExpARD", 300, 6)
+    Xq = synth.points(4321, 10000, 6)
+    mu, s2 = gp.query_batch(Xq)
+    mu_o, s2_o = og.query(Xq, nthreads=8)
+    assert np.abs(mu - (mu_o + Y.mean(axis=0))).max() <= TOL_ABS
+    assert np.abs(s2 - s2_o).max() <= TOL_ABS
