@@ -140,6 +140,17 @@ __device__ __forceinline__ void lb_dmma_16x8x8(double (&c)[4], const double (&a)
         : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
 }
 
+// The native SASS shape.  ptxas lowers one m16n8k8 into FOUR chained DMMA.8x8x4 (k0-3 -> temp -> k4-7 per row
+// half), i.e. no instruction-level parallelism inside a warp; issuing m8n8k4 ourselves, one independent tile after
+// the other, keeps dependent DMMAs a whole tile-sweep apart.
+//   a: A[row g][k t]   b: B[k t][n g]   c0,c1: C[row g][cols 2t, 2t+1]
+__device__ __forceinline__ void lb_dmma_8x8x4(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
 __device__ __forceinline__ void lb_cp_async16(void* smem_dst, const void* gmem_src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(lb_smem_u32(smem_dst)), "l"(gmem_src));

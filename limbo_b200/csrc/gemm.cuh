@@ -45,30 +45,42 @@ using CfgWide = Cfg<128, 4, 32>;  // 512 threads, 1 CTA / SM
 using CfgDual = Cfg<64, 2, 16>;   // 256 threads, 2 CTAs / SM
 using CfgStep = Cfg<64, 4, 32>;   // 512 threads, 64-wide right-hand sides (multi-launch TRSM path)
 
-// Load one BK-slab of an operand tile (NOUTER "outer" x BK k) into shared memory.
+// Per-thread copy plan for one operand: which 16-byte chunks of a (NOUTER x BK) slab this thread moves.  The
+// chunk -> (global offset, shared offset) mapping is the same for every k-slab, so it is computed once; per
+// pipeline stage only a base pointer advances (the per-stage index arithmetic used to sit between the CTA
+// barrier and the first DMMA of every stage).
 template <typename C, bool KC, int NOUTER, int PITCH_OC>
-__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, int64_t ld)
-{
-    const int tid = threadIdx.x;
-    if (KC) {
-        // element (o, k) at g[k + o*ld]; smem [o][k], BK/2 chunks of 16 B per row
-        constexpr int CPR = C::BK / 2;
+struct TilePlan {
+    static constexpr int CHUNKS = NOUTER * C::BK / 2;
+    static constexpr int PER_THREAD = (CHUNKS + C::THREADS - 1) / C::THREADS;
+    int64_t goff[PER_THREAD];
+    int soff[PER_THREAD];
+    __device__ __forceinline__ void init(int64_t ld)
+    {
 #pragma unroll
-        for (int c = tid; c < NOUTER * CPR; c += C::THREADS) {
-            int o = c / CPR, kc = c - o * CPR;
-            lb_cp_async16(s + o * C::PITCH_KC + 2 * kc, g + (int64_t)o * ld + 2 * kc);
+        for (int q = 0; q < PER_THREAD; ++q) {
+            const int c = threadIdx.x + q * C::THREADS;
+            if (KC) { // element (o, k) at g[k + o*ld]; smem [o][k]
+                constexpr int CPR = C::BK / 2;
+                const int o = c / CPR, kc = c - o * CPR;
+                goff[q] = (int64_t)o * ld + 2 * kc;
+                soff[q] = o * C::PITCH_KC + 2 * kc;
+            }
+            else { // element (o, k) at g[o + k*ld]; smem [k][o]
+                constexpr int CPR = NOUTER / 2;
+                const int k = c / CPR, oc = c - k * CPR;
+                goff[q] = (int64_t)k * ld + 2 * oc;
+                soff[q] = k * PITCH_OC + 2 * oc;
+            }
         }
     }
-    else {
-        // element (o, k) at g[o + k*ld]; smem [k][o]
-        constexpr int CPR = NOUTER / 2; // 16 B chunks per k-row
+    __device__ __forceinline__ void issue(double* s, const double* __restrict__ g) const
+    {
 #pragma unroll
-        for (int c = tid; c < C::BK * CPR; c += C::THREADS) {
-            int k = c / CPR, oc = c - k * CPR;
-            lb_cp_async16(s + k * PITCH_OC + 2 * oc, g + (int64_t)k * ld + 2 * oc);
-        }
+        for (int q = 0; q < PER_THREAD; ++q)
+            if (CHUNKS % C::THREADS == 0 || (int)threadIdx.x + q * C::THREADS < CHUNKS) lb_cp_async16(s + soff[q], g + goff[q]);
     }
-}
+};
 
 // Accumulators of one warp: 2 m16-tiles x NT n8-tiles.
 template <typename C>
@@ -93,29 +105,31 @@ __device__ __forceinline__ void compute_stage(Acc<C>& acc, const double* sA, con
     const int wm = warp & 3, wn = warp >> 2;
     const int m_base = wm * 32, n_base = wn * (C::BN / C::WN);
 #pragma unroll
-    for (int k0 = 0; k0 < C::BK; k0 += 8) {
-        double a[2][4];
+    for (int k0 = 0; k0 < C::BK; k0 += 4) {
+        // one k4 step: 4 A values (rows g, g+8 of both m16 tiles), NT B values, then 4*NT independent DMMA.8x8x4
+        double a[2][2], b[C::NT];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                int m = m_base + mt * 16 + g + 8 * (i & 1);
-                int k = k0 + t + 4 * (i >> 1);
+            for (int i = 0; i < 2; ++i) {
+                int m = m_base + mt * 16 + g + 8 * i;
+                int k = k0 + t;
                 a[mt][i] = A_KC ? sA[m * C::PITCH_KC + k] : sA[k * C::PITCH_A_OC + m];
                 if (NEG_A) a[mt][i] = -a[mt][i];
             }
 #pragma unroll
         for (int nt = 0; nt < C::NT; ++nt) {
-            double b[2];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                int n = n_base + nt * 8 + g;
-                int k = k0 + t + 4 * i;
-                b[i] = B_KC ? sB[n * C::PITCH_KC + k] : sB[k * C::PITCH_B_OC + n];
-            }
-            lb_dmma_16x8x8(acc.v[0][nt], a[0], b);
-            lb_dmma_16x8x8(acc.v[1][nt], a[1], b);
+            int n = n_base + nt * 8 + g;
+            int k = k0 + t;
+            b[nt] = B_KC ? sB[n * C::PITCH_KC + k] : sB[k * C::PITCH_B_OC + n];
         }
+#pragma unroll
+        for (int nt = 0; nt < C::NT; ++nt)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                lb_dmma_8x8x4(acc.v[mt][nt][0], acc.v[mt][nt][1], a[mt][0], b[nt]);
+                lb_dmma_8x8x4(acc.v[mt][nt][2], acc.v[mt][nt][3], a[mt][1], b[nt]);
+            }
     }
 }
 
@@ -132,26 +146,32 @@ __device__ __forceinline__ void mainloop(Acc<C>& acc, const double* __restrict__
     const int nk = K / C::BK;
     const int64_t stepA = A_KC ? C::BK : (int64_t)C::BK * lda;
     const int64_t stepB = B_KC ? C::BK : (int64_t)C::BK * ldb;
+    TilePlan<C, A_KC, BM, C::PITCH_A_OC> pa;
+    TilePlan<C, B_KC, C::BN, C::PITCH_B_OC> pb;
+    pa.init(lda);
+    pb.init(ldb);
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < nk) {
-            load_tile<C, A_KC, BM, C::PITCH_A_OC>(sA + s * C::A_STAGE, gA + s * stepA, lda);
-            load_tile<C, B_KC, C::BN, C::PITCH_B_OC>(sB + s * C::B_STAGE, gB + s * stepB, ldb);
+            pa.issue(sA + s * C::A_STAGE, gA + s * stepA);
+            pb.issue(sB + s * C::B_STAGE, gB + s * stepB);
         }
         lb_cp_async_commit();
     }
     for (int kt = 0; kt < nk; ++kt) {
         lb_cp_async_wait<STAGES - 2>();
         __syncthreads();
-        int nx = kt + STAGES - 1;
+        // compute first: the DMMA stream restarts right after the barrier; the prefetch of slab kt+2 (whose slot
+        // was last read in iteration kt-1, i.e. before this barrier) is issued behind it
+        const int s = kt % STAGES;
+        compute_stage<C, A_KC, B_KC, NEG_A>(acc, sA + s * C::A_STAGE, sB + s * C::B_STAGE);
+        const int nx = kt + STAGES - 1;
         if (nx < nk) {
-            int s = nx % STAGES;
-            load_tile<C, A_KC, BM, C::PITCH_A_OC>(sA + s * C::A_STAGE, gA + nx * stepA, lda);
-            load_tile<C, B_KC, C::BN, C::PITCH_B_OC>(sB + s * C::B_STAGE, gB + nx * stepB, ldb);
+            const int sn = nx % STAGES;
+            pa.issue(sA + sn * C::A_STAGE, gA + nx * stepA);
+            pb.issue(sB + sn * C::B_STAGE, gB + nx * stepB);
         }
         lb_cp_async_commit();
-        int s = kt % STAGES;
-        compute_stage<C, A_KC, B_KC, NEG_A>(acc, sA + s * C::A_STAGE, sB + s * C::B_STAGE);
     }
     lb_cp_async_wait<0>();
     __syncthreads();
@@ -202,41 +222,36 @@ __device__ __forceinline__ void mainloop_resB(Acc<C>& acc, const double* __restr
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;
     const int m_base = wm * 32, n_base = wn * (C::BN / C::WN);
+    TilePlan<C, false, BM, C::PITCH_A_OC> pa;
+    pa.init(lda);
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        load_tile<C, false, BM, C::PITCH_A_OC>(smem_pipe + s * C::A_STAGE, gA + (int64_t)s * C::BK * lda, lda);
+        pa.issue(smem_pipe + s * C::A_STAGE, gA + (int64_t)s * C::BK * lda);
         lb_cp_async_commit();
     }
     for (int kt = 0; kt < nk; ++kt) {
         lb_cp_async_wait<STAGES - 2>();
         __syncthreads();
-        int nx = kt + STAGES - 1;
-        if (nx < nk) load_tile<C, false, BM, C::PITCH_A_OC>(smem_pipe + (nx % STAGES) * C::A_STAGE, gA + (int64_t)nx * C::BK * lda, lda);
+        const int nx = kt + STAGES - 1;
+        if (nx < nk) pa.issue(smem_pipe + (nx % STAGES) * C::A_STAGE, gA + (int64_t)nx * C::BK * lda);
         lb_cp_async_commit();
         const double* sA = smem_pipe + (kt % STAGES) * C::A_STAGE;
 #pragma unroll
-        for (int k0 = 0; k0 < C::BK; k0 += 8) {
-            double a[2][4];
+        for (int k0 = 0; k0 < C::BK; k0 += 4) {
+            double a[2][2], b[C::NT];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    int m = m_base + mt * 16 + g + 8 * (i & 1);
-                    int k = k0 + t + 4 * (i >> 1);
-                    a[mt][i] = sA[k * C::PITCH_A_OC + m];
-                }
+                for (int i = 0; i < 2; ++i) a[mt][i] = sA[(k0 + t) * C::PITCH_A_OC + m_base + mt * 16 + g + 8 * i];
 #pragma unroll
-            for (int nt = 0; nt < C::NT; ++nt) {
-                double b[2];
+            for (int nt = 0; nt < C::NT; ++nt) b[nt] = sBres[(n_base + nt * 8 + g) * PB + kt * C::BK + k0 + t];
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    int n = n_base + nt * 8 + g;
-                    int k = kt * C::BK + k0 + t + 4 * i;
-                    b[i] = sBres[n * PB + k];
+            for (int nt = 0; nt < C::NT; ++nt)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    lb_dmma_8x8x4(acc.v[mt][nt][0], acc.v[mt][nt][1], a[mt][0], b[nt]);
+                    lb_dmma_8x8x4(acc.v[mt][nt][2], acc.v[mt][nt][3], a[mt][1], b[nt]);
                 }
-                lb_dmma_16x8x8(acc.v[0][nt], a[0], b);
-                lb_dmma_16x8x8(acc.v[1][nt], a[1], b);
-            }
         }
     }
     lb_cp_async_wait<0>();

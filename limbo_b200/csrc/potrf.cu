@@ -27,13 +27,10 @@ template <typename FA, typename FB>
 __device__ __forceinline__ void warp_mma(double (&c)[4], int K, FA fa, FB fb)
 {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    for (int k0 = 0; k0 < K; k0 += 8) {
-        double a[4], b[2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = fa(g + 8 * (i & 1), k0 + t + 4 * (i >> 1));
-#pragma unroll
-        for (int i = 0; i < 2; ++i) b[i] = fb(k0 + t + 4 * i, g);
-        lb_dmma_16x8x8(c, a, b);
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        const double a0 = fa(g, k0 + t), a1 = fa(g + 8, k0 + t), b = fb(k0 + t, g);
+        lb_dmma_8x8x4(c[0], c[1], a0, b);
+        lb_dmma_8x8x4(c[2], c[3], a1, b);
     }
 }
 

@@ -335,10 +335,10 @@ namespace slab {
 constexpr int NTMAX = 9;
 constexpr int SLAB = NTMAX * 8;  // 72
 constexpr int THREADS = 512;
-constexpr int BK = 16;
+constexpr int BK = 32;
 constexpr int STAGES = 3;
-constexpr int PA = 132;  // A stage [16][132]
-constexpr int PBK = 20;  // B stage [SLAB][20]
+constexpr int PA = 132;  // A stage [32][132]
+constexpr int PBK = 36;  // B stage [SLAB][36]
 constexpr int PT = 132;  // resident tile [SLAB][132]
 constexpr int DMAXF = 16;
 constexpr int PMAXF = 4;
@@ -346,8 +346,9 @@ constexpr int A_STAGE = BK * PA;     // 2112
 constexpr int B_STAGE = SLAB * PBK;  // 1440
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + STAGES * A_STAGE;
-constexpr int OFF_T = OFF_B + STAGES * B_STAGE;
-constexpr int OFF_X = OFF_T + SLAB * PT;
+constexpr int OFF_T = OFF_B; // the resident tile overlays the B stages (never live at the same time)
+constexpr int BT_DOUBLES = (STAGES * B_STAGE > SLAB * PT) ? STAGES * B_STAGE : SLAB * PT;
+constexpr int OFF_X = OFF_B + BT_DOUBLES;
 constexpr int OFF_Q = OFF_X + DMAXF * LB_TILE;
 constexpr int OFF_AL = OFF_Q + DMAXF * SLAB;
 constexpr int OFF_RED = OFF_AL + PMAXF * LB_TILE;
@@ -356,31 +357,65 @@ constexpr int OFF_NRM = OFF_MU + PMAXF * SLAB;
 constexpr int SMEM_DOUBLES = OFF_NRM + SLAB;
 constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * sizeof(double);
 
-__device__ __forceinline__ void load_A_stage(double* s, const double* __restrict__ g, int64_t ld)
-{
-    // 16 k-columns x 128 rows (outer-contiguous): 1024 chunks of 16 B, 2 per thread
+// per-thread copy plans (chunk -> offsets computed once, see gemm.cuh TilePlan)
+struct PlanA { // 32 k-columns x 128 rows, outer-contiguous: 2048 chunks, 4 per thread
+    int goff[4];
+    int soff[4];
+    __device__ __forceinline__ void init(int ld)
+    {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        int c = threadIdx.x + q * THREADS;
-        int k = c >> 6, oc = c & 63;
-        lb_cp_async16(s + k * PA + 2 * oc, g + (int64_t)k * ld + 2 * oc);
+        for (int q = 0; q < 4; ++q) {
+            const int c = threadIdx.x + q * THREADS;
+            const int k = c >> 6, oc = c & 63;
+            goff[q] = k * ld + 2 * oc;
+            soff[q] = k * PA + 2 * oc;
+        }
     }
-}
-__device__ __forceinline__ void load_B_stage(double* s, const double* __restrict__ g, int64_t ld, int ncols)
+    __device__ __forceinline__ void issue(double* s, const double* __restrict__ g) const
+    {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) lb_cp_async16(s + soff[q], g + goff[q]);
+    }
+};
+struct PlanB { // ncols candidates x 32 k, k-contiguous: ncols * 16 (<= 1152) chunks, up to 3 per thread
+    int goff[3];
+    int soff[3];
+    __device__ __forceinline__ void init(int ld)
+    {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int c = threadIdx.x + q * THREADS;
+            const int n = c >> 4, kc = c & 15;
+            goff[q] = n * ld + 2 * kc;
+            soff[q] = n * PBK + 2 * kc;
+        }
+    }
+    __device__ __forceinline__ void issue(double* s, const double* __restrict__ g, int ncols) const
+    {
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if ((int)threadIdx.x + q * THREADS < ncols * 16) lb_cp_async16(s + soff[q], g + goff[q]);
+    }
+};
+
+// 32 k-columns of a 128 x 128 inverse diagonal block (ld = 128); offsets recomputed on the fly (4 stages per row block)
+__device__ __forceinline__ void issue_invd_stage(double* s, const double* __restrict__ g)
 {
-    // ncols candidates x 16 k (k-contiguous): ncols * 8 chunks
-    for (int c = threadIdx.x; c < ncols * 8; c += THREADS) { // up to 576 chunks: more than one per thread
-        int n = c >> 3, kc = c & 7;
-        lb_cp_async16(s + n * PBK + 2 * kc, g + (int64_t)n * ld + 2 * kc);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = threadIdx.x + q * THREADS;
+        const int k = c >> 6, oc = c & 63;
+        lb_cp_async16(s + k * PA + 2 * oc, g + k * LB_TILE + 2 * oc);
     }
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
-query_slab_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ invD, const double* __restrict__ Xs,
-    int64_t N, const double* __restrict__ Qs, int64_t Mp, int64_t M, const double* __restrict__ alpha, int P, KernParams kp,
-    double* __restrict__ Vscratch, int nslabs, int64_t ntiles_total, double* __restrict__ mu_out, double* __restrict__ s2_out)
+// NTC > 0: the slab width (in n8 tiles) is a compile-time constant (no predicated DMMAs); NTC == 0: runtime width.
+template <int NTC>
+__device__ __forceinline__ void slab_body(double* sm, const double* __restrict__ L, int64_t ld, const double* __restrict__ invD,
+    const double* __restrict__ Xs, int64_t N, const double* __restrict__ Qs, int64_t Mp, int64_t M,
+    const double* __restrict__ alpha, int P, const KernParams& kp, double* __restrict__ V, int64_t t0, int ntc_rt,
+    double* __restrict__ mu_out, double* __restrict__ s2_out)
 {
-    extern __shared__ __align__(16) double sm[];
     double* sA = sm + OFF_A;
     double* sB = sm + OFF_B;
     double* sT = sm + OFF_T;
@@ -396,13 +431,14 @@ query_slab_kernel(const double* __restrict__ L, int64_t ld, const double* __rest
     const int grp = warp >> 3, wr = warp & 7;
     const int T = (int)(ld / LB_TILE);
     const int D = kp.D;
-    double* V = Vscratch + (int64_t)blockIdx.x * ld * SLAB; // private [c][n], ld per candidate
     const int r_lo = 16 * wr + g; // rows r_lo, r_lo + 8 of the current row block
+    PlanA pA;
+    PlanB pB;
+    pA.init((int)ld);
+    pB.init((int)ld);
 
-    for (int s = blockIdx.x; s < nslabs; s += gridDim.x) {
-        // balanced partition of the n8-tiles over the slabs
-        const int64_t t0 = ntiles_total * s / nslabs, t1 = ntiles_total * (s + 1) / nslabs;
-        const int ntc = (int)(t1 - t0);
+    {
+        const int ntc = (NTC > 0) ? NTC : ntc_rt;
         const int ncols = ntc * 8;
         const int64_t c0 = t0 * 8; // first candidate of the slab
         __syncthreads();
@@ -432,8 +468,8 @@ query_slab_kernel(const double* __restrict__ L, int64_t ld, const double* __rest
 #pragma unroll
             for (int st = 0; st < STAGES - 1; ++st) {
                 if (st < nk) {
-                    load_A_stage(sA + st * A_STAGE, gA + (int64_t)st * BK * ld, ld);
-                    load_B_stage(sB + st * B_STAGE, gB + st * BK, ld, ncols);
+                    pA.issue(sA + st * A_STAGE, gA + (int64_t)st * BK * ld);
+                    pB.issue(sB + st * B_STAGE, gB + st * BK, ncols);
                 }
                 lb_cp_async_commit();
             }
@@ -503,27 +539,30 @@ query_slab_kernel(const double* __restrict__ L, int64_t ld, const double* __rest
             for (int kt = 0; kt < nk; ++kt) {
                 lb_cp_async_wait<STAGES - 2>();
                 __syncthreads();
-                const int nx = kt + STAGES - 1;
-                if (nx < nk) {
-                    load_A_stage(sA + (nx % STAGES) * A_STAGE, gA + (int64_t)nx * BK * ld, ld);
-                    load_B_stage(sB + (nx % STAGES) * B_STAGE, gB + nx * BK, ld, ncols);
-                }
-                lb_cp_async_commit();
                 const double* a_s = sA + (kt % STAGES) * A_STAGE;
                 const double* b_s = sB + (kt % STAGES) * B_STAGE;
-                const int k0 = 8 * grp;
-                double a[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) a[e] = -a_s[(k0 + t + 4 * (e >> 1)) * PA + r_lo + 8 * (e & 1)];
+                for (int kk = 0; kk < 4; ++kk) { // the group's four k4 steps: 2 * ntc independent DMMA.8x8x4 each
+                    const int k0 = 16 * grp + 4 * kk;
+                    const double a0 = -a_s[(k0 + t) * PA + r_lo], a1 = -a_s[(k0 + t) * PA + r_lo + 8];
+                    double b[NTMAX];
 #pragma unroll
-                for (int nt = 0; nt < NTMAX; ++nt) {
-                    if (nt < ntc) {
-                        double b[2];
-                        b[0] = b_s[(8 * nt + g) * PBK + k0 + t];
-                        b[1] = b_s[(8 * nt + g) * PBK + k0 + t + 4];
-                        lb_dmma_16x8x8(acc[nt], a, b);
+                    for (int nt = 0; nt < NTMAX; ++nt) b[nt] = (nt < ntc) ? b_s[(8 * nt + g) * PBK + k0 + t] : 0.0;
+#pragma unroll
+                    for (int nt = 0; nt < NTMAX; ++nt) {
+                        if (nt < ntc) {
+                            lb_dmma_8x8x4(acc[nt][0], acc[nt][1], a0, b[nt]);
+                            lb_dmma_8x8x4(acc[nt][2], acc[nt][3], a1, b[nt]);
+                        }
                     }
                 }
+                // prefetch slab kt+2 behind the DMMA stream (its slot was last read before this iteration's barrier)
+                const int nx = kt + STAGES - 1;
+                if (nx < nk) {
+                    pA.issue(sA + (nx % STAGES) * A_STAGE, gA + (int64_t)nx * BK * ld);
+                    pB.issue(sB + (nx % STAGES) * B_STAGE, gB + nx * BK, ncols);
+                }
+                lb_cp_async_commit();
             }
             lb_cp_async_wait<0>();
             __syncthreads();
@@ -539,7 +578,7 @@ query_slab_kernel(const double* __restrict__ L, int64_t ld, const double* __rest
             const double* gD = invD + (int64_t)i * LB_TILE * LB_TILE;
 #pragma unroll
             for (int st = 0; st < STAGES - 1; ++st) {
-                load_A_stage(sA + st * A_STAGE, gD + (int64_t)st * BK * LB_TILE, LB_TILE);
+                issue_invd_stage(sA + st * A_STAGE, gD + (int64_t)st * BK * LB_TILE);
                 lb_cp_async_commit();
             }
             __syncthreads();
@@ -562,20 +601,20 @@ query_slab_kernel(const double* __restrict__ L, int64_t ld, const double* __rest
                 lb_cp_async_wait<STAGES - 2>();
                 __syncthreads(); // also publishes group 0's sT writes on the first iteration
                 const int nx = kt + STAGES - 1;
-                if (nx < LB_TILE / BK) load_A_stage(sA + (nx % STAGES) * A_STAGE, gD + (int64_t)nx * BK * LB_TILE, LB_TILE);
+                if (nx < LB_TILE / BK) issue_invd_stage(sA + (nx % STAGES) * A_STAGE, gD + (int64_t)nx * BK * LB_TILE);
                 lb_cp_async_commit();
                 const double* a_s = sA + (kt % STAGES) * A_STAGE;
-                const int k0 = 8 * grp;
-                double a[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) a[e] = a_s[(k0 + t + 4 * (e >> 1)) * PA + r_lo + 8 * (e & 1)];
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int k0 = 16 * grp + 4 * kk;
+                    const double a0 = a_s[(k0 + t) * PA + r_lo], a1 = a_s[(k0 + t) * PA + r_lo + 8];
 #pragma unroll
-                for (int nt = 0; nt < NTMAX; ++nt) {
-                    if (nt < ntc) {
-                        double b[2];
-                        b[0] = sT[(8 * nt + g) * PT + kt * BK + k0 + t];
-                        b[1] = sT[(8 * nt + g) * PT + kt * BK + k0 + t + 4];
-                        lb_dmma_16x8x8(acc[nt], a, b);
+                    for (int nt = 0; nt < NTMAX; ++nt) {
+                        if (nt < ntc) {
+                            const double b = sT[(8 * nt + g) * PT + kt * BK + k0 + t];
+                            lb_dmma_8x8x4(acc[nt][0], acc[nt][1], a0, b);
+                            lb_dmma_8x8x4(acc[nt][2], acc[nt][3], a1, b);
+                        }
                     }
                 }
             }
@@ -629,6 +668,24 @@ query_slab_kernel(const double* __restrict__ L, int64_t ld, const double* __rest
             s2_out[c0 + tid] = res + kp.noise; //                        gp.hpp:166
             for (int p = 0; p < P; ++p) mu_out[(c0 + tid) * P + p] = sMu[p * SLAB + tid];
         }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+query_slab_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ invD, const double* __restrict__ Xs,
+    int64_t N, const double* __restrict__ Qs, int64_t Mp, int64_t M, const double* __restrict__ alpha, int P, KernParams kp,
+    double* __restrict__ Vscratch, int nslabs, int64_t ntiles_total, double* __restrict__ mu_out, double* __restrict__ s2_out)
+{
+    extern __shared__ __align__(16) double sm[];
+    double* V = Vscratch + (int64_t)blockIdx.x * ld * SLAB; // private [c][n], ld per candidate
+    for (int s = blockIdx.x; s < nslabs; s += gridDim.x) {
+        // balanced partition of the n8-tiles over the slabs
+        const int64_t t0 = ntiles_total * s / nslabs, t1 = ntiles_total * (s + 1) / nslabs;
+        const int ntc = (int)(t1 - t0);
+        if (ntc == 9) slab_body<9>(sm, L, ld, invD, Xs, N, Qs, Mp, M, alpha, P, kp, V, t0, ntc, mu_out, s2_out);
+        else if (ntc == 8) slab_body<8>(sm, L, ld, invD, Xs, N, Qs, Mp, M, alpha, P, kp, V, t0, ntc, mu_out, s2_out);
+        else slab_body<0>(sm, L, ld, invD, Xs, N, Qs, Mp, M, alpha, P, kp, V, t0, ntc, mu_out, s2_out);
     }
 }
 
