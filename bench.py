@@ -322,7 +322,7 @@ def run_ours(args) -> None:
     Xp = torch.from_numpy(X).pin_memory()
     yp = torch.from_numpy(y[:, None].copy()).pin_memory()
     Xqp = torch.from_numpy(Xq).pin_memory()
-    Xl, yl = list(Xp.numpy()), list(yp.numpy())
+    Xl, yl = Xp.numpy(), yp.numpy()  # pinned host buffers, one point per row
     ucb = acqui.UCB(gp2)
 
     def step_e2e():

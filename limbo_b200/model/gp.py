@@ -65,6 +65,7 @@ class GP:
         g._kernel_function = _copy.deepcopy(self._kernel_function)
         g._mean_function = _copy.deepcopy(self._mean_function)
         g._samples = list(self._samples)
+        g._X = getattr(self, '_X', None)
         g._observations = self._observations.copy()
         g._mean_vector = self._mean_vector.copy()
         g._obs_mean = self._obs_mean.copy()
@@ -87,8 +88,15 @@ class GP:
         own = np.ascontiguousarray(k.params(), dtype=np.float64)
         _lib.check(self._lib.lb_set_kernel(self._h, k.kernel_id, _ptr(own), own.size, k.noise()), "lb_set_kernel")
 
+    def _sample_matrix(self) -> np.ndarray:
+        X = getattr(self, "_X", None)
+        if X is None or X.shape[0] != len(self._samples):
+            X = np.ascontiguousarray(np.stack(self._samples, axis=0), dtype=np.float64)
+            self._X = X
+        return X
+
     def _push_data(self) -> None:
-        X = np.ascontiguousarray(np.stack(self._samples, axis=0), dtype=np.float64)
+        X = self._sample_matrix()
         Y = np.asfortranarray(self._obs_mean, dtype=np.float64)
         _lib.check(self._lib.lb_set_data(self._h, X.shape[0], X.shape[1], Y.shape[1], _ptr(X), _ptr(Y)), "lb_set_data")
 
@@ -97,16 +105,22 @@ class GP:
         assert len(samples) != 0
         assert len(observations) != 0
         assert len(samples) == len(observations)
-        samples = [np.atleast_1d(np.asarray(s, dtype=np.float64)) for s in samples]
-        observations = [np.atleast_1d(np.asarray(o, dtype=np.float64)) for o in observations]
-        if self._dim_in != samples[0].size:
-            self._dim_in = samples[0].size
+        # std::vector<Eigen::VectorXd> in the reference; a 2-D array (one point per row) is taken as is
+        X = np.ascontiguousarray(samples, dtype=np.float64)
+        Y = np.ascontiguousarray(observations, dtype=np.float64)
+        if X.ndim == 1:
+            X = X[:, None]
+        if Y.ndim == 1:
+            Y = Y[:, None]
+        if self._dim_in != X.shape[1]:
+            self._dim_in = X.shape[1]
             self._kernel_function = self._kernel_cls(self._params, self._dim_in)
-        if self._dim_out != observations[0].size:
-            self._dim_out = observations[0].size
+        if self._dim_out != Y.shape[1]:
+            self._dim_out = Y.shape[1]
             self._mean_function = self._mean_cls(self._params, self._dim_out)
-        self._samples = samples
-        self._observations = np.stack(observations, axis=0)
+        self._samples = list(X)  # row views, no copies
+        self._X = X
+        self._observations = Y
         self._mean_observation = self._observations.mean(axis=0)
         self._compute_obs_mean()
         self._fitted = False
@@ -133,6 +147,7 @@ class GP:
             assert sample.size == self._dim_in
             assert observation.size == self._dim_out
         self._samples.append(sample)
+        self._X = None
         self._observations = np.vstack([self._observations, observation[None, :]])
         self._mean_observation = self._observations.mean(axis=0)
         self._compute_obs_mean()
@@ -316,7 +331,7 @@ class GP:
     # ---- protected helpers (same names as the reference) ----
     def _compute_obs_mean(self) -> None:  # gp.hpp:537-548
         assert len(self._samples) != 0
-        X = np.stack(self._samples, axis=0)
+        X = self._sample_matrix()
         assert X.shape[1] == self._dim_in
         self._mean_vector = np.asarray(self._mean_function.batch(X, self), dtype=np.float64).reshape(len(self._samples), self._dim_out)
         self._obs_mean = self._observations - self._mean_vector
