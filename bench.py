@@ -204,6 +204,15 @@ def fp64_tensor_peak() -> tuple[float, str]:
     return 40.0, "nominal B200 fp64 tensor peak (40 TFLOP/s); MEASURED_PEAKS.json has no fp64 figure"
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes of one captured launch (ncu --set full), from the committed profile summary."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[kernel]
+        return j["dram_bytes"], j
+    except Exception:
+        return None, None
+
+
 def hbm_peak() -> tuple[float, str]:
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -358,7 +367,8 @@ def run_ours(args) -> None:
             avg_ms = prof["syrk"]["ms_total"] / prof["syrk"]["launches"]
             ach = per_launch_flops / (avg_ms * 1e-3) / 1e12
             roof = {"kernel": "syrk_kernel (Cholesky trailing update, fp64 DMMA)", "bound": "tensor", "achieved": ach, "peak": peak_t,
-                    "unit": "TFLOP/s", "frac": ach / peak_t, "traffic": None, "peak_source": peak_t_src,
+                    "unit": "TFLOP/s", "frac": ach / peak_t, "traffic": ncu_traffic("syrk_kernel")[0],
+                    "traffic_capture": ncu_traffic("syrk_kernel")[1], "peak_source": peak_t_src,
                     "share_of_step": prof["syrk"]["ms_total"] / t_ms, "avg_launch_ms": avg_ms,
                     "algorithmic_flops_per_launch": per_launch_flops}
         roof_k = {}
@@ -367,7 +377,7 @@ def run_ours(args) -> None:
             avg_ms = prof["kbuild"]["ms_total"] / prof["kbuild"]["launches"]
             ach = byts / (avg_ms * 1e-3) / 1e9
             roof_k = {"kernel": "kbuild_kernel (N x N kernel matrix)", "bound": "hbm", "achieved": ach, "peak": peak_h, "unit": "GB/s",
-                      "frac": ach / peak_h, "traffic": None, "peak_source": peak_h_src, "avg_launch_ms": avg_ms,
+                      "frac": ach / peak_h, "traffic": ncu_traffic("kbuild_kernel")[0], "peak_source": peak_h_src, "avg_launch_ms": avg_ms,
                       "algorithmic_bytes_per_launch": byts}
         # CPU baseline on a bounded sample (rank 0, N=1 only)
         cpu = None
