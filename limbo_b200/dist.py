@@ -61,3 +61,45 @@ def sharded_acq_argmax(acq, Xq_global: np.ndarray, rank: int, world: int, device
 
 def restart_owner(restart: int, world: int) -> int:
     return restart % world
+
+
+class ShardedRepeater:
+    """opt::ParallelRepeater (opt/parallel_repeater.hpp:76-107) with the restarts spread over the ranks:
+    restart r runs on rank r % world (each rank on its own GPU and its own copy of the GP), then one
+    all_gather of (value, restart index) picks the winner and its parameters are broadcast from the owner.
+    Every rank draws the SAME perturbations (common seed), so the result does not depend on `world`."""
+
+    def __init__(self, params=None, optimizer=None, seed: int = 2000, device=None, group=None):
+        from . import opt as _opt
+        from .params import get
+        self._params = params
+        self._optimizer = optimizer if optimizer is not None else _opt.Rprop(params)
+        self._seed, self._device, self._group = seed, device, group
+        self._get = get
+
+    def __call__(self, f, init, bounded: bool):
+        import torch
+        import torch.distributed as dist
+        from . import opt as _opt
+        repeats = int(self._get(self._params, "opt_parallelrepeater", "repeats"))
+        epsilon = float(self._get(self._params, "opt_parallelrepeater", "epsilon"))
+        init = np.asarray(init, dtype=np.float64)
+        on = dist.is_available() and dist.is_initialized()
+        rank = dist.get_rank(self._group) if on else 0
+        world = dist.get_world_size(self._group) if on else 1
+        best_v, best_val, best_r = init.copy(), -float(np.finfo(np.float32).max), -1
+        for r in range(repeats):
+            dev = np.random.default_rng(self._seed + r).random(init.size) * 2.0 * epsilon - epsilon
+            if restart_owner(r, world) != rank:
+                continue
+            v = self._optimizer(f, init + dev, bounded)
+            val = _opt.eval(f, v)
+            if val > best_val:
+                best_v, best_val, best_r = v, val, r
+        if not on or world == 1:
+            return best_v
+        val, win = allgather_argmax(best_val, best_r, device=self._device, group=self._group)
+        owner = restart_owner(win, world) if win >= 0 else 0
+        buf = torch.tensor(best_v if rank == owner else np.zeros_like(init), dtype=torch.float64, device=self._device)
+        dist.broadcast(buf, src=owner, group=self._group)
+        return buf.cpu().numpy()

@@ -35,6 +35,29 @@ dist.destroy_process_group()
 """
 
 
+WORKER_RESTARTS = r"""
+import sys, json
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from limbo_b200 import dist as lbd, opt
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=int(sys.argv[4]))
+class P:
+    class opt_rprop:
+        iterations = 20
+    class opt_parallelrepeater:
+        repeats = 5
+        epsilon = 0.5
+def f(x, g):
+    v = -float(((x - np.array([0.3, -0.7])) ** 2).sum()) + 0.1 * float(np.cos(5 * x).sum())
+    gr = -2 * (x - np.array([0.3, -0.7])) - 0.5 * np.sin(5 * x)
+    return (v, gr) if g else (v, None)
+best = lbd.ShardedRepeater(P, opt.Rprop(P), seed=11)(f, np.zeros(2), False)
+print(json.dumps({"rank": dist.get_rank(), "best": best.tolist()}))
+dist.destroy_process_group()
+"""
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -77,3 +100,36 @@ def test_sharded_argmax_world2_gloo(tmp_path):
     assert all(r["ok"] for r in recs), recs
     assert recs[0]["idx"] == recs[1]["idx"]
     assert recs[0]["hi"] == recs[1]["lo"]
+
+
+def test_sharded_restarts_world2_equals_world1(tmp_path):
+    """ParallelRepeater restarts spread over 2 ranks give the same winner as a single rank."""
+    import json
+    sys.path.insert(0, ROOT)
+    from limbo_b200 import dist as lbd, opt
+
+    class P:
+        class opt_rprop:
+            iterations = 20
+
+        class opt_parallelrepeater:
+            repeats = 5
+            epsilon = 0.5
+
+    def f(x, g):
+        v = -float(((x - np.array([0.3, -0.7])) ** 2).sum()) + 0.1 * float(np.cos(5 * x).sum())
+        gr = -2 * (x - np.array([0.3, -0.7])) - 0.5 * np.sin(5 * x)
+        return (v, gr) if g else (v, None)
+    single = lbd.ShardedRepeater(P, opt.Rprop(P), seed=11)(f, np.zeros(2), False)
+    port = _free_port()
+    script = tmp_path / "worker_r.py"
+    script.write_text(WORKER_RESTARTS)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r), "2"], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True, env=env) for r in range(2)]
+    outs = [p.communicate(timeout=120) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e[-2000:]
+    recs = [json.loads(o.strip().splitlines()[-1]) for o, _ in outs]
+    assert np.allclose(recs[0]["best"], recs[1]["best"], rtol=0, atol=0)
+    assert np.allclose(recs[0]["best"], single, rtol=0, atol=1e-15)
