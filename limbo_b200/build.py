@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "liblimbo_b200.so")
-SOURCES = ["abi.cu", "kbuild.cu", "potrf.cu", "trsv.cu", "query.cu", "lml.cu"]
+SOURCES = ["abi.cu", "kbuild.cu", "potrf.cu", "trsv.cu", "query.cu", "lml.cu", "tf32_query.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--extended-lambda", "-Xcompiler", "-fPIC", "-diag-suppress", "177",
@@ -62,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(r.stdout, r.stderr, file=sys.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(6, os.cpu_count() or 2)) as ex:
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)

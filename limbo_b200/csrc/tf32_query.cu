@@ -1,0 +1,304 @@
+// limbo_b200/csrc/tf32_query.cu — reduced-precision candidate scoring on the 5th-generation tensor cores
+// (BASELINE.json config 4: N = 16384, D = 12, 1M EI candidates, tf32).
+//
+// The per-candidate variance needs |L^-1 k*|^2, i.e. V = L^-1 K* (M N^2 flops, gp.hpp:618-624 once per
+// candidate in the reference).  fp64 has no tcgen05 kind, so the fp64 path runs on DMMA (query.cu).  Here the
+// factor is inverted once in fp64 (lml.cu, recursive trtri), cast to fp32 row-major, and the product
+//     D[c, n] = sum_{k <= n} Kt[c, k] * Linv[n, k]          (Kt = K*^T, candidates x training points)
+// runs as a TF32 GEMM on tcgen05.mma with fp32 accumulators in TMEM; the epilogue never writes D: each of the
+// 128 epilogue threads owns one candidate (one TMEM lane) and accumulates sum_n D[c, n]^2 while the next tile's
+// MMAs run into the other half of TMEM.
+//
+// Structure of one CTA (persistent, 192 threads):
+//   warp 0      : TMA producer  (cp.async.bulk.tensor 2-D, SWIZZLE_128B boxes of 32 k x {128, 256} rows)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane: 4 x tcgen05.mma.kind::tf32 m128 n256 k8 per stage,
+//                 tcgen05.commit -> "slot free" / "accumulator full" mbarriers)
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b, squares, per-candidate running sum)
+// 4-stage smem ring (48 KB per stage), 2 x 256 TMEM columns.
+// Every mbarrier wait is bounded: on timeout an error flag is raised instead of hanging the GPU.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace tf32q {
+
+constexpr int BM = 128;       // candidates per tile (UMMA M)
+constexpr int BN = 256;       // outputs (rows of L^-1) per tile (UMMA N)
+constexpr int BKE = 32;       // k elements per stage = 128 B = one swizzle atom row
+constexpr int UMMA_K = 8;     // tf32
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BKE * 4;  // 16 KB
+constexpr int B_BYTES = BN * BKE * 4;  // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int THREADS = 192;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr long long SPIN_LIMIT = 1LL << 24;
+
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t n)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lb_smem_u32(b)), "r"(n));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lb_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(lb_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* b, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(lb_smem_u32(b)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: returns false (and raises *err) instead of spinning forever
+__device__ __forceinline__ bool mbar_wait(uint64_t* b, uint32_t parity, int* err)
+{
+    long long spins = 0;
+    while (!mbar_try(b, parity)) {
+        if (++spins > SPIN_LIMIT || *(volatile int*)err) {
+            atomicExch(err, 1);
+            return false;
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     lb_smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(lb_smem_u32(bar))
+                 : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1) |
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B -> 64) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4, a/b format TF32 = 2 @7/@10,
+// a/b K-major (0) @15/@16, N >> 3 @17, M >> 4 @24
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(lb_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// D[c, n] = sum_k A[c, k] B[n, k]; tri != 0: k only up to the end of the n-tile (B lower triangular).
+// norm2[c] += sum_n D[c, n]^2 ; Dout (optional, row-major M x N) receives D for validation.
+__global__ void __launch_bounds__(THREADS, 1)
+tf32_gemm_norm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int64_t M, int64_t N,
+    int64_t K, int tri, float* __restrict__ norm2, float* __restrict__ Dout, int* __restrict__ err)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023); // SWIZZLE_128B needs 1024-byte alignment
+    uint64_t* full = (uint64_t*)(smem + (size_t)STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;   // [2]
+    uint64_t* tempty = tfull + 2;       // [2]
+    uint32_t* tmem_base_s = (uint32_t*)(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (int)(M / BM), n_tiles = (int)(N / BN);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) { // TMEM: 512 columns (2 accumulators of 256)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(lb_smem_u32(tmem_base_s)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0; bool ok = true;
+            for (int mt = blockIdx.x; mt < m_tiles && ok; mt += gridDim.x) {
+                for (int nt = 0; nt < n_tiles && ok; ++nt) {
+                    const int64_t kend = tri ? (int64_t)(nt + 1) * BN : K;
+                    const int kblocks = (int)((kend < K ? kend : K) / BKE);
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        if (!mbar_wait(&empty[s], ph ^ 1, err)) { ok = false; break; }
+                        uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
+                        mbar_expect_tx(&full[s], STAGE_BYTES);
+                        tma_load_2d(sa, &mapA, kb * BKE, mt * BM, &full[s]);
+                        tma_load_2d(sa + A_BYTES, &mapB, kb * BKE, nt * BN, &full[s]);
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    }
+    else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0; bool ok = true;
+            int buf = 0; uint32_t tph[2] = {0, 0};
+            for (int mt = blockIdx.x; mt < m_tiles && ok; mt += gridDim.x) {
+                for (int nt = 0; nt < n_tiles && ok; ++nt) {
+                    const int64_t kend = tri ? (int64_t)(nt + 1) * BN : K;
+                    const int kblocks = (int)((kend < K ? kend : K) / BKE);
+                    if (!mbar_wait(&tempty[buf], tph[buf] ^ 1, err)) { ok = false; break; } // epilogue drained this accumulator
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        if (!mbar_wait(&full[s], ph, err)) { ok = false; break; }
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sa = lb_smem_u32(smem + (size_t)s * STAGE_BYTES);
+                        const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BKE / UMMA_K; ++k) // +32 B per UMMA_K step inside the 128 B swizzle row: +2 in the >>4 address field
+                            umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0);
+                        umma_commit(&empty[s]); // frees the smem slot when these MMAs have read it
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                    umma_commit(&tfull[buf]); // accumulator complete
+                    tph[buf] ^= 1;
+                    buf ^= 1;
+                }
+            }
+        }
+    }
+    else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane; // candidate inside the tile == TMEM lane
+        int buf = 0; uint32_t tph[2] = {0, 0}; bool ok = true;
+        for (int mt = blockIdx.x; mt < m_tiles && ok; mt += gridDim.x) {
+            float acc = 0.f;
+            for (int nt = 0; nt < n_tiles && ok; ++nt) {
+                if (!mbar_wait(&tfull[buf], tph[buf], err)) { ok = false; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float d = __uint_as_float(v[j]);
+                        acc = fmaf(d, d, acc);
+                        if (Dout) Dout[((int64_t)mt * BM + row) * N + (int64_t)nt * BN + c + j] = d;
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]); // 4 arrivals (one per epilogue warp) release the accumulator
+                tph[buf] ^= 1;
+                buf ^= 1;
+            }
+            if (ok) norm2[(int64_t)mt * BM + row] = acc;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// row-major (rows x K) fp32 matrix, boxes of 32 k x box_rows rows, 128-byte swizzle, tf32 rounding on load
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t ld, int box_rows)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return LB_ERR_UNSUPPORTED;
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? LB_OK : LB_ERR_CUDA;
+}
+
+bool g_attr = false;
+
+} // namespace tf32q
+
+// A: M x K (ld lda), B: N x K (ld ldb), fp32 row-major in device memory; M % 128 == 0, N % 256 == 0, K % 32 == 0.
+int lb_launch_tf32_gemm_norm(cudaStream_t st, const float* dA, int64_t lda, const float* dB, int64_t ldb, int64_t M, int64_t N, int64_t K,
+    int tri, float* dNorm2, float* dDout, int* dErr, int grid)
+{
+    using namespace tf32q;
+    if (M % BM || N % BN || K % BKE) return LB_ERR_ARG;
+    if (!g_attr) {
+        LB_CUDA(cudaFuncSetAttribute(tf32_gemm_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        g_attr = true;
+    }
+    alignas(64) CUtensorMap mapA, mapB;
+    int rc;
+    if ((rc = make_map(&mapA, dA, M, K, lda, BM))) return rc;
+    if ((rc = make_map(&mapB, dB, N, K, ldb, BN))) return rc;
+    const int m_tiles = (int)(M / BM);
+    if (grid > m_tiles) grid = m_tiles;
+    tf32_gemm_norm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mapA, mapB, M, N, K, tri, dNorm2, dDout, dErr);
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+extern "C" int lb_debug_tf32_gemm(const float* dA, const float* dB, long long M, long long N, long long K, int tri, float* dNorm2,
+    float* dDout, int grid)
+{
+    int* dErr = nullptr;
+    LB_CUDA(cudaMalloc(&dErr, sizeof(int)));
+    LB_CUDA(cudaMemset(dErr, 0, sizeof(int)));
+    int rc = lb_launch_tf32_gemm_norm(0, dA, K, dB, K, M, N, K, tri, dNorm2, dDout, dErr, grid);
+    if (rc) { cudaFree(dErr); return rc; }
+    LB_CUDA(cudaDeviceSynchronize());
+    int herr = 0;
+    LB_CUDA(cudaMemcpy(&herr, dErr, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(dErr);
+    return herr ? LB_ERR_TIMEOUT : LB_OK;
+}
