@@ -61,6 +61,9 @@ typedef struct lb_gp lb_gp;
 
 /* precision modes */
 #define LB_PREC_FP64 0
+/* fit / likelihood in fp64; lb_query and lb_acq_argmax compute sigma^2 on the tf32 tensor cores (tcgen05, fp32
+ * accumulation) from an fp64-inverted factor: |d sigma^2| ~ 1e-3 k(v,v), stated in tests/test_gpu_tf32.py */
+#define LB_PREC_TF32 1
 
 /* Lifetime.  Replaces GP(int dim_in, int dim_out) / ~GP / the copy constructor
  * KernelLFOptimization relies on (model/gp/kernel_lf_opt.hpp:79). */

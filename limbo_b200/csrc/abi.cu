@@ -77,6 +77,9 @@ struct QueryWs { // per-handle query workspace (guarded by qmutex)
     double* dBest = nullptr; // [0] value ; long long index follows
     long long* dBestIdx = nullptr;
     double* dMean = nullptr; size_t mean_bytes = 0;
+    float* dKt = nullptr; size_t kt_bytes = 0;         // TF32 path: K*^T chunk (Mc x Np fp32)
+    float* dNorm2 = nullptr; size_t norm2_bytes = 0;
+    int* dErr = nullptr;
 };
 
 struct Extra {
@@ -212,13 +215,15 @@ void free_ws(QueryWs& w)
 {
     cudaFree(w.dQraw); cudaFree(w.dQs); cudaFree(w.dV); cudaFree(w.dMu); cudaFree(w.dS2); cudaFree(w.dAcq);
     cudaFree(w.dBlkVal); cudaFree(w.dBlkIdx); cudaFree(w.dBest); cudaFree(w.dBestIdx); cudaFree(w.dMean);
+    cudaFree(w.dKt); cudaFree(w.dNorm2); cudaFree(w.dErr);
     w = QueryWs();
 }
 
 void free_model(lb_gp* h)
 {
     cudaFree(h->dX); cudaFree(h->dXs); cudaFree(h->dY); cudaFree(h->dL); cudaFree(h->dInvD); cudaFree(h->dAlpha);
-    cudaFree(h->dLinv); cudaFree(h->dKinv); cudaFree(h->dFlags);
+    cudaFree(h->dLinv); cudaFree(h->dKinv); cudaFree(h->dFlags); cudaFree(h->dLinv32);
+    h->dLinv32 = nullptr; h->linv32_valid = false; h->linv32_rows = 0;
     h->dX = h->dXs = h->dY = h->dL = h->dInvD = h->dAlpha = h->dLinv = h->dKinv = nullptr;
     h->dFlags = nullptr;
     h->Np = 0;
@@ -268,7 +273,7 @@ int lb_profile_enable(lb_gp* h, int on);
 int lb_create(lb_gp** out, int device, int precision)
 {
     if (!out) return LB_ERR_ARG;
-    if (precision != LB_PREC_FP64) return LB_ERR_UNSUPPORTED;
+    if (precision != LB_PREC_FP64 && precision != LB_PREC_TF32) return LB_ERR_UNSUPPORTED;
     int ndev = 0;
     LB_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return LB_ERR_ARG;
@@ -351,7 +356,7 @@ static int set_data_common(lb_gp* h, int64_t N, int D, int P, const double* X, c
     }
     h->N = N; h->D = D; h->P = P;
     h->kp.D = D;
-    h->fitted = false; h->linv_valid = false; h->kinv_valid = false;
+    h->fitted = false; h->linv_valid = false; h->kinv_valid = false; h->linv32_valid = false;
     const double* dXr = X;
     const double* dYr = Y;
     if (!dev && N > 0) {
@@ -405,7 +410,7 @@ int lb_set_kernel(lb_gp* h, int kernel_id, const double* p, int n_hparams, doubl
     else if (kernel_id == LB_K_EXP) kp.c1 = 1.0 / (kp.l * kp.l);
     h->n_hparams = n_hparams;
     h->kernel_set = true;
-    h->fitted = false; h->linv_valid = false; h->kinv_valid = false;
+    h->fitted = false; h->linv_valid = false; h->kinv_valid = false; h->linv32_valid = false;
     return LB_OK;
 }
 
@@ -419,7 +424,7 @@ int lb_fit(lb_gp* h)
     if ((rc = lb_launch_scale_x(h))) return rc;
     if ((rc = lb_launch_kbuild(h, h->dL))) return rc;
     if ((rc = lb_launch_potrf(h))) return rc;
-    h->fitted = true; h->linv_valid = false; h->kinv_valid = false;
+    h->fitted = true; h->linv_valid = false; h->kinv_valid = false; h->linv32_valid = false;
     if ((rc = lb_launch_solve_alpha(h))) return rc;
     return check_info(h);
 }
@@ -432,7 +437,7 @@ int lb_fit_async(lb_gp* h) // same as lb_fit without the final host sync / info 
     if ((rc = lb_launch_scale_x(h))) return rc;
     if ((rc = lb_launch_kbuild(h, h->dL))) return rc;
     if ((rc = lb_launch_potrf(h))) return rc;
-    h->fitted = true; h->linv_valid = false; h->kinv_valid = false;
+    h->fitted = true; h->linv_valid = false; h->kinv_valid = false; h->linv32_valid = false;
     return lb_launch_solve_alpha(h);
 }
 
@@ -535,7 +540,7 @@ int lb_append(lb_gp* h, const double* x, const double* Yall)
     append_row_kernel<<<1, 256, 0, h->stream>>>(h->dL, Np, n, dk, knn, h->dInfo);
     h->launches++;
     if ((rc = lb_launch_potf2_block(h, (int)(n / LB_TILE), 0))) return rc;
-    h->linv_valid = false; h->kinv_valid = false;
+    h->linv_valid = false; h->kinv_valid = false; h->linv32_valid = false;
     if ((rc = lb_launch_solve_alpha(h))) return rc;
     return check_info(h);
 }
@@ -572,7 +577,33 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
             LB_CUDA(cudaMemcpyAsync(w.dQraw, Xq, sizeof(double) * M * D, cudaMemcpyHostToDevice, st));
             dQraw = w.dQraw;
         }
-        if (lb_query_fused_supported(h) && !h->force_unfused) {
+        if (h->precision == LB_PREC_TF32) {
+            // reduced-precision variance on tcgen05 (tf32_query.cu); mu accumulates in fp64 from fp32 kernel values
+            if ((rc = lb_tf32_prepare(h))) return rc;
+            const int64_t cap = std::max<int64_t>(LB_TILE, ((int64_t)4 << 30) / (4 * h->Np) / LB_TILE * LB_TILE);
+            const int64_t Mc = std::min(Mp, cap);
+            if ((rc = ensure(&w.dQs, &w.qs_bytes, sizeof(double) * D * Mc))) return rc;
+            if ((rc = ensure(&w.dKt, &w.kt_bytes, sizeof(float) * (size_t)Mc * h->Np))) return rc;
+            if ((rc = ensure(&w.dNorm2, &w.norm2_bytes, sizeof(float) * (size_t)Mc))) return rc;
+            if (!w.dErr) LB_CUDA(cudaMalloc(&w.dErr, sizeof(int)));
+            LB_CUDA(cudaMemsetAsync(w.dErr, 0, sizeof(int), st));
+            for (int64_t m0 = 0; m0 < M; m0 += Mc) {
+                const int64_t mc = std::min(Mc, M - m0);
+                const int64_t mcp = (mc + LB_TILE - 1) / LB_TILE * LB_TILE;
+                dim3 g1((unsigned)((mcp + 255) / 256), (unsigned)D);
+                pack_soa_kernel<<<g1, 256, 0, st>>>(dQraw + m0 * D, mc, D, w.dQs, mcp, h->kp, 1);
+                h->launches++;
+                if ((rc = lb_launch_query_tf32(h, st, mc, w.dQs, mcp, w.dKt, w.dNorm2, w.dErr, w.dMu + m0 * P, w.dS2 + m0, &h->launches)))
+                    return rc;
+            }
+            if (!out_dev) {
+                int herr = 0;
+                LB_CUDA(cudaMemcpyAsync(&herr, w.dErr, sizeof(int), cudaMemcpyDeviceToHost, st));
+                LB_CUDA(cudaStreamSynchronize(st));
+                if (herr) return LB_ERR_TIMEOUT;
+            }
+        }
+        else if (lb_query_fused_supported(h) && !h->force_unfused) {
             // fused persistent path: one CTA per candidate slab, private V scratch per CTA
             int sms = 0;
             LB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));

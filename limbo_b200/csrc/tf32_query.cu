@@ -302,3 +302,187 @@ extern "C" int lb_debug_tf32_gemm(const float* dA, const float* dB, long long M,
     cudaFree(dErr);
     return herr ? LB_ERR_TIMEOUT : LB_OK;
 }
+
+// ===========================================================================
+// TF32 prediction path: K*^T (fp32, K-major) build, mu GEMV, L^-1 cast/transposed, sigma^2 from the row norms.
+// ===========================================================================
+namespace tf32q {
+
+constexpr int DCH = 16;
+
+// Kt[c * ldk + n] = (float) k(x_n, q_c)  for one tile of 128 candidates x 128 training points; zero for n >= N.
+// grid: (Np/128, Mc/128).  Same thread mapping as kbuild_kernel: the two consecutive "rows" of a thread are two
+// consecutive n, stored as one float2 (n is the contiguous, K-major index of the GEMM's A operand).
+__global__ void __launch_bounds__(256, 2)
+kstar_t32_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, const double* __restrict__ Qs, int64_t Mp, int64_t M,
+    float* __restrict__ Kt, int64_t ldk, KernParams kp)
+{
+    __shared__ __align__(128) double sxi[DCH][LB_TILE];
+    __shared__ __align__(128) double sxj[DCH][LB_TILE];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int li = lane & 7, lj = lane >> 3;
+    const int D = kp.D;
+    const int64_t i0 = (int64_t)blockIdx.x * LB_TILE, j0 = (int64_t)blockIdx.y * LB_TILE; // i: training, j: candidates
+    const int r0 = warp * 16 + 2 * li;
+    if (tid == 0) {
+        lb_mbar_init(&bar, 1);
+        lb_fence_barrier_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    const int npass = (D + DCH - 1) / DCH;
+    for (int h = 0; h < 2; ++h) {
+        double z[8][4];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) z[c][e] = 0.0;
+        for (int pass = 0; pass < npass; ++pass) {
+            const int d0 = pass * DCH;
+            const int dc = min(DCH, D - d0);
+            if (!(npass == 1 && h == 1)) {
+                __syncthreads();
+                if (tid == 0) {
+                    lb_fence_proxy_async();
+                    lb_mbar_expect_tx(&bar, (uint32_t)(2 * dc * LB_TILE * sizeof(double)));
+                    for (int d = 0; d < dc; ++d) {
+                        lb_bulk_g2s(&sxi[d][0], Xs + (int64_t)(d0 + d) * Np + i0, LB_TILE * sizeof(double), &bar);
+                        lb_bulk_g2s(&sxj[d][0], Qs + (int64_t)(d0 + d) * Mp + j0, LB_TILE * sizeof(double), &bar);
+                    }
+                }
+                lb_mbar_wait(&bar, phase);
+                phase ^= 1;
+            }
+            for (int d = 0; d < dc; ++d) {
+                const double2 xi = *reinterpret_cast<const double2*>(&sxi[d][r0]);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const double2 xj = *reinterpret_cast<const double2*>(&sxj[d][h * 64 + c * 8 + 2 * lj]);
+                    double q;
+                    q = xi.x - xj.x; z[c][0] = fma(q, q, z[c][0]);
+                    q = xi.y - xj.x; z[c][1] = fma(q, q, z[c][1]);
+                    q = xi.x - xj.y; z[c][2] = fma(q, q, z[c][2]);
+                    q = xi.y - xj.y; z[c][3] = fma(q, q, z[c][3]);
+                }
+            }
+        }
+        const int64_t gi = i0 + r0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int64_t gj = j0 + h * 64 + c * 8 + 2 * lj;
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t ii = gi + (e & 1), jj = gj + (e >> 1);
+                double k = lb_kernel_from_z(kp.id, z[c][e], kp);
+                if (ii >= N || jj >= M) k = 0.0;
+                v[e] = (float)k;
+            }
+            *reinterpret_cast<float2*>(&Kt[gj * ldk + gi]) = make_float2(v[0], v[1]);
+            *reinterpret_cast<float2*>(&Kt[(gj + 1) * ldk + gi]) = make_float2(v[2], v[3]);
+        }
+    }
+}
+
+// mu[c*P + p] = sum_n Kt[c, n] alpha[n, p]   (one warp per candidate, fp64 accumulation, fixed order)
+__global__ void __launch_bounds__(256)
+mu_t32_kernel(const float* __restrict__ Kt, int64_t ldk, int64_t Np, const double* __restrict__ alpha, int P, int64_t M,
+    double* __restrict__ mu)
+{
+    const int64_t c = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= M) return;
+    const float* row = Kt + c * ldk;
+    for (int p = 0; p < P; ++p) {
+        const double* a = alpha + (int64_t)p * Np;
+        double s = 0.0;
+        for (int64_t n = lane * 4; n < Np; n += 128) {
+            const float4 k4 = *reinterpret_cast<const float4*>(row + n);
+            s = fma((double)k4.x, a[n], s);
+            s = fma((double)k4.y, a[n + 1], s);
+            s = fma((double)k4.z, a[n + 2], s);
+            s = fma((double)k4.w, a[n + 3], s);
+        }
+        s = lb_warp_sum(s);
+        if (lane == 0) mu[c * P + p] = s;
+    }
+}
+
+// LinvR[n * ldr + k] = (float) Linv[n + k * ld]  (column-major fp64 -> row-major fp32, 32 x 32 smem transpose)
+__global__ void __launch_bounds__(256)
+linv_to_f32_rowmajor_kernel(const double* __restrict__ Linv, int64_t ld, float* __restrict__ R, int64_t ldr)
+{
+    __shared__ float tile[32][33];
+    const int64_t n0 = (int64_t)blockIdx.x * 32, k0 = (int64_t)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int kk = ty; kk < 32; kk += 8) tile[kk][tx] = (k0 + kk <= n0 + tx) ? (float)Linv[n0 + tx + (k0 + kk) * ld] : 0.f;
+    __syncthreads();
+    for (int nn = ty; nn < 32; nn += 8) R[(n0 + nn) * ldr + k0 + tx] = tile[tx][nn];
+}
+
+__global__ void __launch_bounds__(256)
+sigma2_t32_kernel(const float* __restrict__ norm2, int64_t M, double kvv, double noise, double* __restrict__ s2)
+{
+    const int64_t c = blockIdx.x * (int64_t)256 + threadIdx.x;
+    if (c >= M) return;
+    double res = kvv - (double)norm2[c];
+    res = (res <= 2.220446049250313e-16) ? 0.0 : res; // gp.hpp:623
+    s2[c] = res + noise;                               // gp.hpp:166
+}
+
+} // namespace tf32q
+
+int lb_launch_linv(lb_gp* h);
+
+// Prepare the fp32 row-major copy of L^-1 (rows padded to a multiple of 256 with zeros).
+int lb_tf32_prepare(lb_gp* h)
+{
+    using namespace tf32q;
+    if (h->linv32_valid) return LB_OK;
+    int rc;
+    if (!h->linv_valid && (rc = lb_launch_linv(h))) return rc;
+    const int64_t Np = h->Np, Nr = (Np + BN - 1) / BN * BN;
+    if (!h->dLinv32 || h->linv32_rows != Nr) {
+        if (h->dLinv32) cudaFree(h->dLinv32);
+        LB_CUDA(cudaMalloc(&h->dLinv32, sizeof(float) * Nr * Np));
+        h->linv32_rows = Nr;
+    }
+    if (Nr > Np) LB_CUDA(cudaMemsetAsync(h->dLinv32 + Np * Np, 0, sizeof(float) * (Nr - Np) * Np, h->stream));
+    dim3 grid((unsigned)(Np / 32), (unsigned)(Np / 32));
+    LbProfScope ps(h, h->stream, LB_PC_OTHER);
+    linv_to_f32_rowmajor_kernel<<<grid, 256, 0, h->stream>>>(h->dLinv, Np, h->dLinv32, Np);
+    h->launches++;
+    LB_CUDA(cudaGetLastError());
+    h->linv32_valid = true;
+    return LB_OK;
+}
+
+// mu (M x P, fp64) and sigma2 (M, fp64 container of a TF32-accurate value) for one chunk of Mc <= capacity candidates.
+int lb_launch_query_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const double* dQs, int64_t Mcp, float* dKt, float* dNorm2,
+    int* dErr, double* dMu, double* dS2, long long* launches)
+{
+    using namespace tf32q;
+    const int64_t Np = h->Np;
+    dim3 g1((unsigned)(Np / LB_TILE), (unsigned)(Mcp / LB_TILE));
+    {
+        LbProfScope ps(h, st, LB_PC_KSTAR);
+        kstar_t32_kernel<<<g1, 256, 0, st>>>(h->dXs, Np, h->N, dQs, Mcp, Mc, dKt, Np, h->kp);
+    }
+    {
+        LbProfScope ps(h, st, LB_PC_QREDUCE);
+        mu_t32_kernel<<<(unsigned)((Mc + 7) / 8), 256, 0, st>>>(dKt, Np, Np, h->dAlpha, h->P, Mc, dMu);
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    int rc;
+    {
+        LbProfScope ps(h, st, LB_PC_QSTEP);
+        rc = lb_launch_tf32_gemm_norm(st, dKt, Np, h->dLinv32, Np, Mcp, h->linv32_rows, Np, 1, dNorm2, nullptr, dErr, sms);
+    }
+    if (rc) return rc;
+    sigma2_t32_kernel<<<(unsigned)((Mc + 255) / 256), 256, 0, st>>>(dNorm2, Mc, h->kp.sf2, h->kp.noise, dS2);
+    if (launches) *launches += 4;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}

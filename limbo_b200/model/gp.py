@@ -22,7 +22,7 @@ def _ptr(a: np.ndarray) -> int:
 
 class GP:
     def __init__(self, dim_in: int = -1, dim_out: int = -1, params=None, kernel=_kernel.MaternFiveHalves,
-                 mean=_mean.Data, hp_opt=None, device: int = 0):
+                 mean=_mean.Data, hp_opt=None, device: int = 0, precision: str = "fp64"):
         # gp.hpp:84-88
         self._params = params
         self._kernel_cls, self._mean_cls = kernel, mean
@@ -44,7 +44,8 @@ class GP:
         self._device = device
         self._lib = _lib.load()
         h = C.c_void_p()
-        _lib.check(self._lib.lb_create(C.byref(h), device, 0), "lb_create")
+        self._precision = {"fp64": 0, "tf32": 1}[precision]
+        _lib.check(self._lib.lb_create(C.byref(h), device, self._precision), "lb_create")
         self._h = h
         self._host_cache: dict[str, np.ndarray] = {}
 

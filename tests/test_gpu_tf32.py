@@ -1,0 +1,33 @@
+"""TF32 prediction path (BASELINE.json config 4): sigma^2 from a tcgen05 tf32 GEMM with fp32 accumulation, against the
+fp64 DMMA path on the same model.  Stated tolerances (tf32 has a 10-bit mantissa; sigma^2 = k(v,v) - |L^-1 k*|^2
+subtracts two O(1) numbers):  |d sigma^2| <= 4e-3 k(v,v),  |d mu| <= 1e-4 (fp32 kernel values x alpha ~ 1e2, fp64 sum);
+the acquisition argmax is judged on the EI value, not on index equality."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kname,N,D,M", [("SquaredExpARD", 1000, 12, 3000), ("MaternFiveHalves", 700, 6, 1500), ("SquaredExpARD", 130, 3, 257)])
+def test_tf32_query_close_to_fp64(kname, N, D, M):
+    from limbo_b200 import acqui, kernel, mean, model, synth
+    X = synth.points(1234, N, D)
+    y = synth.targets(X)
+    Xq = synth.points(1235, M, D)
+    kw = dict(kernel=getattr(kernel, kname), mean=mean.Data)
+    g64 = model.GP(D, 1, **kw)
+    g32 = model.GP(D, 1, precision="tf32", **kw)
+    g64.compute(X, y[:, None])
+    g32.compute(X, y[:, None])
+    # the fit itself is fp64 in both modes
+    assert np.array_equal(g64.alpha(), g32.alpha())
+    mu64, s64 = g64.query_batch(Xq)
+    mu32, s32 = g32.query_batch(Xq)
+    assert np.abs(mu64 - mu32).max() <= 1e-4
+    assert np.abs(s64 - s32).max() <= 4e-3
+    assert np.all(s32 >= 0.01 - 1e-12)
+    best64, i64, v64 = acqui.EI(g64).argmax_batch(Xq, return_values=True)
+    best32, i32, v32 = acqui.EI(g32).argmax_batch(Xq, return_values=True)
+    # the tf32 winner must be (nearly) as good under the fp64 model
+    assert v64[i32] >= best64 - 5e-3 * max(1.0, abs(best64))
+    assert np.abs(v64 - v32).max() <= 2e-2
