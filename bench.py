@@ -36,6 +36,10 @@ if ROOT not in sys.path:
 
 N_TRAIN, DIM, M_CAND = 16384, 6, 10000
 KERNEL_NAME = "SquaredExpARD"
+WORKLOADS = {  # --workload: BASELINE.json configs that fit one GPU; the default is the configuration the metric is quoted on
+    "n16384_se_ard": (16384, 6, 10000, "SquaredExpARD"),
+    "config2_n4096_matern": (4096, 6, 10000, "MaternFiveHalves"),
+}
 NOISE = 0.01
 UCB_ALPHA = 0.5
 METRIC = "GP fit+query/s at N=16384,D=6 (fit = K-build+Cholesky+alpha, query = 10k UCB candidates+argmax, fp64)"
@@ -116,7 +120,8 @@ def cpu_sample(n_s: int, m_s: int, threads: int) -> dict:
     Xq = synth.points(1235, m_s, DIM)
     g = O.OracleGP()
     g.set_data(X, (y - y.mean())[:, None])
-    g.set_kernel(O.K_SE_ARD, np.zeros(DIM + 1), NOISE)
+    kid = {"SquaredExpARD": O.K_SE_ARD, "MaternFiveHalves": O.K_MATERN52}[KERNEL_NAME]
+    g.set_kernel(kid, np.zeros(DIM + 1 if kid == O.K_SE_ARD else 2), NOISE)
     t0 = time.perf_counter()
     g.fit()
     t_fit = time.perf_counter() - t0
@@ -254,7 +259,9 @@ def run_ours(args) -> None:
     y = synth.targets(X)
     Xq = synth.points(1235 + rank, m, d)  # each rank owns its shard of the global candidate batch
 
-    gp = model.GP(d, 1, kernel=kernel.SquaredExpARD, mean=mean.Data, device=local_rank)
+    kcls = getattr(kernel, KERNEL_NAME)
+    kid_dev = kcls.kernel_id
+    gp = model.GP(d, 1, kernel=kcls, mean=mean.Data, device=local_rank)
     h = gp._h
     # a real (non-default) stream: the library and the timing events must share it
     stream = torch.cuda.Stream(dev)
@@ -270,13 +277,13 @@ def run_ours(args) -> None:
     dBest = torch.zeros(1, dtype=torch.float64, device=dev)
     dIdx = torch.zeros(1, dtype=torch.int64, device=dev)
     ap = np.array([UCB_ALPHA, 0.0])
-    hp = np.zeros(d + 1)
+    hp = np.zeros(d + 1 if KERNEL_NAME == "SquaredExpARD" else 2)
     mean_const = float(y.mean())
     gather_buf = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
 
     def step_dev():
         _lib.check(lib.lb_set_data_dev(h, n, d, 1, dX.data_ptr(), dY.data_ptr()), "set_data_dev")
-        _lib.check(lib.lb_set_kernel(h, 0, hp.ctypes.data, d + 1, NOISE), "set_kernel")
+        _lib.check(lib.lb_set_kernel(h, kid_dev, hp.ctypes.data, hp.size, NOISE), "set_kernel")
         _lib.check(lib.lb_fit_async(h), "fit_async")
         _lib.check(lib.lb_acq_argmax_dev(h, 0, ap.ctypes.data, m, dXq.data_ptr(), None, mean_const, None, dBest.data_ptr(),
                                          dIdx.data_ptr()), "acq_argmax_dev")
@@ -326,7 +333,7 @@ def run_ours(args) -> None:
     value = world / (ms_per_step * 1e-3)
 
     # ---------------- end-to-end leg through the public host API ----------------
-    gp2 = model.GP(d, 1, kernel=kernel.SquaredExpARD, mean=mean.Data, device=local_rank)
+    gp2 = model.GP(d, 1, kernel=kcls, mean=mean.Data, device=local_rank)
     gp2.set_stream(stream.cuda_stream)
     Xp = torch.from_numpy(X).pin_memory()
     yp = torch.from_numpy(y[:, None].copy()).pin_memory()
@@ -411,7 +418,12 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
+    ap.add_argument("--workload", default="n16384_se_ard", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    global N_TRAIN, DIM, M_CAND, KERNEL_NAME, METRIC
+    N_TRAIN, DIM, M_CAND, KERNEL_NAME = WORKLOADS[args.workload]
+    if args.workload != "n16384_se_ard":
+        METRIC = f"GP fit+query/s at N={N_TRAIN},D={DIM} ({KERNEL_NAME}; fit = K-build+Cholesky+alpha, query = {M_CAND} UCB candidates+argmax, fp64)"
     if args.impl == "reference":
         run_reference(args)
     else:
