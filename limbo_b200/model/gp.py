@@ -170,6 +170,8 @@ class GP:
         Xq = np.ascontiguousarray(np.atleast_2d(Xq), dtype=np.float64)
         M = Xq.shape[0]
         P = max(self._dim_out, 1)
+        if M == 0 or Xq.size == 0:
+            return np.zeros((0, P)), np.zeros(0)
         if len(self._samples) == 0:
             # gp.hpp:161-163: mean(v) and k(v,v) + noise; the kernel state is still needed on the device
             self._ensure_dims_for_prior(Xq.shape[1])

@@ -334,3 +334,67 @@ def test_query_slab_nine_tiles(oracle_mod):
     mu_o, s2_o = og.query(Xq, nthreads=8)
     assert np.abs(mu - (mu_o + Y.mean(axis=0))).max() <= TOL_ABS
     assert np.abs(s2 - s2_o).max() <= TOL_ABS
+
+
+def test_identical_samples_full_vs_incremental(oracle_mod):
+    """test_gp.cpp:513-566: 10 identical samples (K is only regularised by the noise): full vs incremental Cholesky."""
+    from limbo_b200 import kernel, mean, model
+    O = oracle_mod
+    X = np.tile(np.array([[0.3, 0.7]]), (10, 1))
+    y = np.linspace(0.9, 1.1, 10)[:, None]
+    gp = model.GP(2, 1, kernel=kernel.MaternFiveHalves, mean=mean.Data)
+    gp.compute(X, y)
+    gi = model.GP(2, 1, kernel=kernel.MaternFiveHalves, mean=mean.Data)
+    gi.compute(X[:1], y[:1])
+    for i in range(1, 10):
+        gi.add_sample(X[i], y[i])
+    K, L, Li = gp.kernel_matrix(), gp.matrixL(), gi.matrixL()
+    assert np.abs(L @ L.T - K).max() <= 1e-12 and np.abs(Li @ Li.T - K).max() <= 1e-12  # isApprox(1e-5) there
+    q = np.array([[0.3, 0.7], [0.31, 0.69]])
+    (m1, s1), (m2, s2) = gp.query_batch(q), gi.query_batch(q)
+    assert np.abs(m1 - m2).max() <= 1e-9 and np.abs(s1 - s2).max() <= 1e-10  # 1e-4 there
+    og = O.OracleGP()
+    og.set_data(X, y - y.mean())
+    og.set_kernel(O.K_MATERN52, np.zeros(2), 0.01)
+    og.fit()
+    mo, so = og.query(q)
+    assert np.abs(m1 - (mo + y.mean())).max() <= 1e-9 and np.abs(s1 - so).max() <= TOL_ABS
+
+
+@pytest.mark.parametrize("N", [1, 2, 127, 128, 129, 256, 257])
+def test_padding_boundaries(N, oracle_mod):
+    """Sizes around the 128-padding quantum, single sample included."""
+    from limbo_b200 import synth
+    gp, og, X, Y = _make("SquaredExpARD", N, 3)
+    Xq = synth.points(8, 9, 3)
+    mu, s2 = gp.query_batch(Xq)
+    mu_o, s2_o = og.query(Xq)
+    assert np.abs(mu - (mu_o + Y.mean(axis=0))).max() <= TOL_ABS and np.abs(s2 - s2_o).max() <= TOL_ABS
+    assert abs(gp.compute_log_lik() - og.log_lik()) <= 1e-11 * max(1.0, abs(og.log_lik()))
+    g, go = gp.compute_kernel_grad_log_lik(), og.grad()
+    assert np.abs(g - go).max() <= 1e-9 * max(1.0, np.abs(go).max())
+
+
+def test_max_input_dimension_and_single_query(oracle_mod):
+    """D = 64 (LB_MAX_D; four TMA passes of 16 dimensions) and a one-candidate batch."""
+    from limbo_b200 import synth
+    gp, og, X, Y = _make("SquaredExpARD", 200, 64, hp=np.concatenate([np.full(64, 1.2), [0.1]]))
+    Xq = synth.points(3, 1, 64)
+    mu, s2 = gp.query_batch(Xq)
+    mu_o, s2_o = og.query(Xq)
+    assert np.abs(mu - (mu_o + Y.mean(axis=0))).max() <= TOL_ABS and np.abs(s2 - s2_o).max() <= TOL_ABS
+    assert np.abs(gp.kernel_matrix() - og.get(0)).max() <= TOL_ABS
+    g, go = gp.compute_kernel_grad_log_lik(), og.grad()
+    assert np.abs(g - go).max() <= 1e-9 * max(1.0, np.abs(go).max())
+    from limbo_b200 import kernel, mean, model
+    with pytest.raises(Exception):
+        model.GP(65, 1, kernel=kernel.SquaredExpARD, mean=mean.Data).compute(np.zeros((4, 65)), np.zeros((4, 1)))
+
+
+def test_empty_candidate_batch_and_reuse(oracle_mod):
+    gp, og, X, Y = _make("Exp", 40, 2)
+    mu, s2 = gp.query_batch(np.zeros((0, 2)))
+    assert mu.shape == (0, 1) and s2.shape == (0,)
+    # refit with different data of another size on the same handle (buffers are re-allocated)
+    gp.compute(X[:17], Y[:17])
+    assert gp.nb_samples() == 17 and gp.matrixL().shape == (17, 17)
