@@ -97,6 +97,10 @@ int lb_refit_alpha(lb_gp* h, const double* obs_mean_colmajor);
  * x is the new sample (D), obs_mean_all the refreshed (N+1) x P obs_mean. */
 int lb_append(lb_gp* h, const double* x, const double* obs_mean_all_colmajor);
 
+/* GP::load(archive, recompute = false) (gp.hpp:505-509): adopt a stored factor (N x N column-major, lower) and alpha
+ * (N x P) for the data / kernel already set, instead of refactorising. */
+int lb_load_factor(lb_gp* h, const double* L_colmajor, const double* alpha_colmajor);
+
 /* Batched GP::query (gp.hpp:159-167) for M candidates (row-major M x D):
  * mu_minus_mean is M x P row-major (k^T alpha, WITHOUT mean(v));
  * sigma2 is M (clamped as gp.hpp:623, + noise as gp.hpp:166).

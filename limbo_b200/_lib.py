@@ -19,7 +19,7 @@ GET_K, GET_L, GET_ALPHA, GET_KINV = 0, 1, 2, 3
 # every symbol include/limbo_b200.h declares
 DECLARED_SYMBOLS = [
     "lb_create", "lb_destroy", "lb_clone", "lb_set_stream", "lb_sync", "lb_launch_count", "lb_set_data",
-    "lb_set_data_dev", "lb_set_kernel", "lb_fit", "lb_refit_alpha", "lb_append", "lb_query", "lb_query_dev",
+    "lb_set_data_dev", "lb_set_kernel", "lb_fit", "lb_load_factor", "lb_refit_alpha", "lb_append", "lb_query", "lb_query_dev",
     "lb_acq_argmax", "lb_acq_argmax_dev", "lb_log_lik", "lb_kernel_grad_log_lik", "lb_compute_inv_kernel", "lb_get",
     "lb_nb_samples", "lb_strerror", "lb_last_cuda_error",
 ]
@@ -68,6 +68,7 @@ def load() -> C.CDLL:
         "lb_stage_potrf": ([p], i32),
         "lb_stage_alpha": ([p], i32),
         "lb_refit_alpha": ([p, dp], i32),
+        "lb_load_factor": ([p, dp, dp], i32),
         "lb_append": ([p, dp, dp], i32),
         "lb_query": ([p, i64, dp, dp, dp], i32),
         "lb_query_dev": ([p, i64, dp, dp, dp], i32),

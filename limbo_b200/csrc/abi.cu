@@ -468,6 +468,30 @@ int lb_stage_alpha(lb_gp* h)
     return lb_launch_solve_alpha(h);
 }
 
+// GP::load(archive, recompute = false) (gp.hpp:505-509): take a stored factor and alpha instead of refactorising.
+// Data and kernel must already be set (lb_set_data / lb_set_kernel); the diagonal-block inverses are rebuilt.
+int lb_load_factor(lb_gp* h, const double* L_colmajor, const double* alpha_colmajor)
+{
+    if (!h || !L_colmajor || !alpha_colmajor) return LB_ERR_ARG;
+    if (!h->kernel_set || h->N == 0 || h->Np == 0) return LB_ERR_STATE;
+    LB_CUDA(cudaSetDevice(h->device));
+    const int64_t N = h->N, Np = h->Np;
+    const int T = (int)(Np / LB_TILE);
+    int rc;
+    if ((rc = lb_launch_scale_x(h))) return rc;
+    LB_CUDA(cudaMemsetAsync(h->dL, 0, sizeof(double) * Np * Np, h->stream));
+    LB_CUDA(cudaMemcpy2DAsync(h->dL, Np * 8, L_colmajor, N * 8, N * 8, N, cudaMemcpyHostToDevice, h->stream));
+    identity_pad_kernel<<<1024, 256, 0, h->stream>>>(h->dL, Np, N);
+    LB_CUDA(cudaMemsetAsync(h->dAlpha, 0, sizeof(double) * Np * h->P, h->stream));
+    LB_CUDA(cudaMemcpy2DAsync(h->dAlpha, Np * 8, alpha_colmajor, N * 8, N * 8, h->P, cudaMemcpyHostToDevice, h->stream));
+    LB_CUDA(cudaMemsetAsync(h->dInfo, 0, 2 * sizeof(int), h->stream));
+    h->launches++;
+    for (int k = 0; k < T; ++k)
+        if ((rc = lb_launch_potf2_block(h, k, 0))) return rc;
+    h->fitted = true; h->linv_valid = false; h->kinv_valid = false; h->linv32_valid = false;
+    return check_info(h);
+}
+
 int lb_refit_alpha(lb_gp* h, const double* Y)
 {
     if (!h || !Y) return LB_ERR_ARG;

@@ -331,6 +331,51 @@ class GP:
     def inv_kernel_computed(self) -> bool:
         return self._inv_kernel_updated
 
+    # ---- gp.hpp:439-511 save / load ----
+    def save(self, archive) -> None:
+        from ..serialize import TextArchive
+        if isinstance(archive, str):
+            archive = TextArchive(archive)
+        if self._kernel_function.h_params_size() > 0:
+            archive.save(self._kernel_function.h_params(), "kernel_params")
+        if self._mean_function.h_params_size() > 0:
+            archive.save(self._mean_function.h_params(), "mean_params")
+        archive.save(self._samples, "samples")
+        archive.save(self._observations, "observations")
+        archive.save(self.matrixL(), "matrixL")
+        archive.save(self.alpha(), "alpha")
+
+    def load(self, archive, recompute: bool = True) -> None:
+        from ..serialize import TextArchive
+        if isinstance(archive, str):
+            archive = TextArchive(archive)
+        self._samples = archive.load_vector_list("samples")
+        self._X = None
+        self._observations = archive.load_matrix("observations")
+        self._dim_in = self._samples[0].size
+        self._kernel_function = self._kernel_cls(self._params, self._dim_in)
+        if self._kernel_function.h_params_size() > 0:
+            hp = archive.load_vector("kernel_params")
+            assert hp.size == self._kernel_function.h_params_size()
+            self._kernel_function.set_h_params(hp)
+        self._dim_out = self._observations.shape[1]
+        self._mean_function = self._mean_cls(self._params, self._dim_out)
+        if self._mean_function.h_params_size() > 0:
+            hp = archive.load_vector("mean_params")
+            assert hp.size == self._mean_function.h_params_size()
+            self._mean_function.set_h_params(hp)
+        self._mean_observation = self._observations.mean(axis=0)
+        if recompute:
+            self.recompute(True, True)
+        else:  # gp.hpp:505-509: adopt the stored factor and alpha
+            self._compute_obs_mean()
+            self._push_data()
+            self._push_kernel()
+            L = np.asfortranarray(archive.load_matrix("matrixL"))
+            A = np.asfortranarray(archive.load_matrix("alpha").reshape(len(self._samples), self._dim_out))
+            _lib.check(self._lib.lb_load_factor(self._h, _ptr(L), _ptr(A)), "lb_load_factor")
+            self._inv_kernel_updated = False
+
     # ---- protected helpers (same names as the reference) ----
     def _compute_obs_mean(self) -> None:  # gp.hpp:537-548
         assert len(self._samples) != 0

@@ -1,0 +1,86 @@
+"""The rows §8(f) marks "next": callers and data formats either side of the path.
+ * serialisation round trip (test_serialize.cpp:120-179: 1e-10 on mu and sigma^2, both load modes);
+ * MultiGP vs plain GP (test_gp.cpp:949-952: 1e-6);
+ * a Bayesian-optimisation run through the batched acquisition optimiser (test_boptimizer.cpp:202-281 style)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_save_load_roundtrip(tmp_path):
+    from limbo_b200 import kernel, mean, model, serialize, synth
+    X = synth.points(1, 300, 4)
+    y = np.stack([synth.targets(X), np.cos(3 * X[:, 0])], axis=1)
+    gp = model.GP(4, 2, kernel=kernel.SquaredExpARD, mean=mean.Data)
+    gp.kernel_function().set_h_params(np.array([0.2, -0.1, 0.3, 0.0, 0.1]))
+    gp.compute(X, y)
+    d = str(tmp_path / "gp_text")
+    gp.save(d)
+    for name in ("kernel_params", "samples", "observations", "matrixL", "alpha"):  # gp.hpp:448-460 (mean::Data has no params)
+        assert (tmp_path / "gp_text" / (name + ".dat")).exists()
+    Xq = synth.points(2, 1000, 4)
+    mu, s2 = gp.query_batch(Xq)
+    for recompute in (True, False):
+        g2 = model.GP(-1, -1, kernel=kernel.SquaredExpARD, mean=mean.Data)
+        g2.load(serialize.TextArchive(d), recompute=recompute)
+        assert g2.nb_samples() == 300 and g2.dim_in() == 4 and g2.dim_out() == 2
+        m2, v2 = g2.query_batch(Xq)
+        assert np.abs(mu - m2).max() <= 1e-10 and np.abs(s2 - v2).max() <= 1e-10
+        assert abs(g2.compute_log_lik() - gp.compute_log_lik()) <= 1e-10 * abs(gp.compute_log_lik())
+
+
+def test_multi_gp_matches_plain_gps():
+    from limbo_b200 import kernel, mean, model, synth
+    X = synth.points(3, 150, 3)
+    Y = np.stack([synth.targets(X), np.sin(4 * X[:, 1]), X[:, 2] ** 2], axis=1)
+    mgp = model.MultiGP(3, 3, kernel=kernel.MaternFiveHalves, mean=mean.Data)
+    mgp.compute(X[:140], Y[:140])
+    for i in range(140, 150):
+        mgp.add_sample(X[i], Y[i])
+    Xq = synth.points(4, 200, 3)
+    mu, s2 = mgp.query_batch(Xq)
+    assert mu.shape == (200, 3) and s2.shape == (200, 3)
+    for p in range(3):
+        gp = model.GP(3, 1, kernel=kernel.MaternFiveHalves, mean=mean.Data)
+        gp.compute(X, Y[:, p:p + 1])
+        m, s = gp.query_batch(Xq)
+        assert np.abs(m[:, 0] - mu[:, p]).max() <= 1e-6 and np.abs(s - s2[:, p]).max() <= 1e-6
+    m1, s1 = mgp.query(Xq[0])
+    assert np.array_equal(m1, mu[0]) and np.array_equal(s1, s2[0])
+
+
+@pytest.mark.parametrize("acq", ["UCB", "EI"])
+def test_bo_loop_converges(acq):
+    from limbo_b200 import acqui, bayes_opt, kernel, mean, model
+
+    class P:
+        class kernel:
+            noise = 1e-6
+
+        class kernel_maternfivehalves:
+            sigma_sq = 1.0
+            l = 0.3
+
+        class init_randomsampling:
+            samples = 10
+
+        class stop_maxiterations:
+            iterations = 30
+
+        class opt_batchedrandom:
+            candidates = 20000
+            refinements = 2
+            shrink = 0.1
+
+        class acqui_ucb:
+            alpha = 0.2
+    sol = np.array([0.25, 0.75])
+
+    def f(x):
+        return -float(((x - sol) ** 2).sum())
+    gp = model.GP(2, 1, params=P, kernel=kernel.MaternFiveHalves, mean=mean.Data)
+    bo = bayes_opt.BOptimizer(gp, params=P, acqui=getattr(acqui, acq), rng=np.random.default_rng(0))
+    bo.optimize(f, 2)
+    assert len(bo.samples()) == 40 and gp.nb_samples() == 40
+    assert ((bo.best_sample() - sol) ** 2).sum() < 1e-3
