@@ -93,56 +93,36 @@ namespace limbo_b200 {
             }
             ~GP() { if (_h) lb_destroy(_h); }
 
-            // gp.hpp:88-116
+            // Same contract as limbo::model::GP::compute (gp.hpp:88-116): takes ownership of a copy of the data, (re)builds
+            // the policy functors when a dimension changed, forms obs_mean on the host (the mean is a host functor) and,
+            // unless told otherwise, runs the device fit.
             void compute(const std::vector<Eigen::VectorXd>& samples, const std::vector<Eigen::VectorXd>& observations,
                 bool compute_kernel = true)
             {
-                assert(samples.size() != 0);
-                assert(observations.size() != 0);
-                assert(samples.size() == observations.size());
-                if (_dim_in != samples[0].size()) {
-                    _dim_in = samples[0].size();
-                    _kernel_function = KernelFunction(_dim_in);
-                }
-                if (_dim_out != observations[0].size()) {
-                    _dim_out = observations[0].size();
-                    _mean_function = MeanFunction(_dim_out);
-                }
+                assert(!samples.empty() && !observations.empty() && samples.size() == observations.size());
+                _adopt_dims(samples.front().size(), observations.front().size());
                 _samples = samples;
-                _observations.resize(observations.size(), _dim_out);
-                for (int i = 0; i < _observations.rows(); ++i)
-                    _observations.row(i) = observations[i];
-                _mean_observation = _observations.colwise().mean();
-                this->_compute_obs_mean();
-                if (compute_kernel)
-                    this->_compute_full_kernel();
+                _pack_rows(observations, _observations);
+                _refresh_means();
+                if (compute_kernel) _compute_full_kernel();
             }
 
             void optimize_hyperparams() { _hp_optimize(*this); } // gp.hpp:119-122
 
-            // gp.hpp:126-152
+            // Incremental update (gp.hpp:126-152): one kernel row, one forward solve and a new alpha on the device
+            // (lb_append) instead of a refit.
             void add_sample(const Eigen::VectorXd& sample, const Eigen::VectorXd& observation)
             {
-                if (_samples.empty()) {
-                    if (_dim_in != sample.size()) {
-                        _dim_in = sample.size();
-                        _kernel_function = KernelFunction(_dim_in);
-                    }
-                    if (_dim_out != observation.size()) {
-                        _dim_out = observation.size();
-                        _mean_function = MeanFunction(_dim_out);
-                    }
-                }
-                else {
-                    assert(sample.size() == _dim_in);
-                    assert(observation.size() == _dim_out);
-                }
+                if (_samples.empty())
+                    _adopt_dims(sample.size(), observation.size());
+                else
+                    assert(sample.size() == _dim_in && observation.size() == _dim_out);
                 _samples.push_back(sample);
-                _observations.conservativeResize(_observations.rows() + 1, _dim_out);
-                for (int p = 0; p < _dim_out; ++p) _observations(_observations.rows() - 1, p) = observation(p);
-                _mean_observation = _observations.colwise().mean();
-                this->_compute_obs_mean();
-                this->_compute_incremental_kernel();
+                const long n = (long)_samples.size();
+                _observations.conservativeResize(n, _dim_out);
+                for (int p = 0; p < _dim_out; ++p) _observations(n - 1, p) = observation(p);
+                _refresh_means();
+                _compute_incremental_kernel();
             }
 
             // gp.hpp:159-191 — one point; the batched extensions below are what a device-aware optimiser calls
@@ -202,18 +182,18 @@ namespace limbo_b200 {
             const MeanFunction& mean_function() const { return _mean_function; }
             MeanFunction& mean_function() { return _mean_function; }
 
-            Eigen::VectorXd max_observation() const // gp.hpp:207-214
+            Eigen::VectorXd max_observation() const // gp.hpp:207-214 (meaningful for dim_out == 1 only)
             {
-                if (_observations.cols() > 1)
-                    std::cout << "WARNING max_observation with multi dimensional observations doesn't make sense" << std::endl;
-                Eigen::VectorXd r(1);
-                r(0) = _observations.maxCoeff();
-                return r;
+                if (_observations.cols() > 1) std::cout << "WARNING max_observation with multi dimensional observations doesn't make sense" << std::endl;
+                Eigen::VectorXd best(1);
+                best(0) = _observations.maxCoeff();
+                return best;
             }
-            Eigen::VectorXd mean_observation() const // gp.hpp:217-222
+            Eigen::VectorXd mean_observation() const // gp.hpp:217-222: zero until there is data
             {
                 assert(_dim_out > 0);
-                return _samples.size() > 0 ? _mean_observation : Eigen::VectorXd::Zero(_dim_out);
+                if (_samples.empty()) return Eigen::VectorXd::Zero(_dim_out);
+                return _mean_observation;
             }
             const Eigen::MatrixXd& mean_vector() const { return _mean_vector; }
             const Eigen::MatrixXd& obs_mean() const { return _obs_mean; }
@@ -306,42 +286,40 @@ namespace limbo_b200 {
             /// LAPACK-style info of the last factorisation (0 ok, > 0 failing pivot); the reference never checks LLT::info()
             int cholesky_info() const { return _info; }
 
-            // gp.hpp:439-511 — same six objects, same archive calls
-            template <typename A> void save(const std::string& directory) const { A archive(directory); save(archive); }
+            // Same six archive objects as the reference (gp.hpp:448-460), so directories written by either side load in the
+            // other; matrixL / alpha are fetched from the device when saving.
+            template <typename A> void save(const std::string& directory) const { save(A(directory)); }
             template <typename A> void save(const A& archive) const
             {
-                if (_kernel_function.h_params_size() > 0) archive.save(_kernel_function.h_params(), "kernel_params");
-                if (_mean_function.h_params_size() > 0) archive.save(_mean_function.h_params(), "mean_params");
+                const bool has_k = _kernel_function.h_params_size() > 0, has_m = _mean_function.h_params_size() > 0;
+                if (has_k) archive.save(_kernel_function.h_params(), "kernel_params");
+                if (has_m) archive.save(_mean_function.h_params(), "mean_params");
                 archive.save(_samples, "samples");
                 archive.save(_observations, "observations");
                 archive.save(matrixL(), "matrixL");
                 archive.save(alpha(), "alpha");
             }
-            template <typename A> void load(const std::string& directory, bool recompute = true) { A archive(directory); load(archive, recompute); }
-            template <typename A> void load(const A& archive, bool /*recompute*/ = true)
+            template <typename A> void load(const std::string& directory, bool recompute = true) { load(A(directory), recompute); }
+            // recompute == false adopts the stored factor (lb_load_factor) instead of refactorising (gp.hpp:505-509)
+            template <typename A> void load(const A& archive, bool recompute = true)
             {
                 _samples.clear();
                 archive.load(_samples, "samples");
                 archive.load(_observations, "observations");
-                _dim_in = _samples[0].size();
-                _kernel_function = KernelFunction(_dim_in);
-                if (_kernel_function.h_params_size() > 0) {
-                    Eigen::VectorXd h_params;
-                    archive.load(h_params, "kernel_params");
-                    assert(h_params.size() == (int)_kernel_function.h_params_size());
-                    _kernel_function.set_h_params(h_params);
-                }
-                _dim_out = _observations.cols();
-                _mean_function = MeanFunction(_dim_out);
-                if (_mean_function.h_params_size() > 0) {
-                    Eigen::VectorXd h_params;
-                    archive.load(h_params, "mean_params");
-                    assert(h_params.size() == (int)_mean_function.h_params_size());
-                    _mean_function.set_h_params(h_params);
-                }
-                _mean_observation = _observations.colwise().mean();
-                // the factor is cheap to rebuild on the device; a stored matrixL / alpha is not uploaded
-                this->recompute(true, true);
+                _dim_in = -1;
+                _dim_out = -1;
+                _adopt_dims(_samples.front().size(), _observations.cols());
+                _restore_params(archive, _kernel_function, "kernel_params");
+                _restore_params(archive, _mean_function, "mean_params");
+                _refresh_means();
+                if (recompute) { _compute_full_kernel(); return; }
+                Eigen::MatrixXd L, a;
+                archive.load(L, "matrixL");
+                archive.load(a, "alpha");
+                _upload_data();
+                _push_kernel();
+                lb_check(lb_load_factor(_h, L.data(), a.data()), "lb_load_factor");
+                _inv_kernel_updated = false;
             }
 
             void swap(GP& o)
@@ -396,23 +374,55 @@ namespace limbo_b200 {
                 lb_check(lb_set_data(_h, 0, D, _dim_out > 0 ? _dim_out : 1, nullptr, nullptr), "lb_set_data");
                 _push_kernel();
             }
+            // (re)build the policy functors when a dimension changes (what gp.hpp:95-103 / 127-136 do inline)
+            void _adopt_dims(long d_in, long d_out)
+            {
+                if (_dim_in != d_in) { _dim_in = (int)d_in; _kernel_function = KernelFunction(_dim_in); }
+                if (_dim_out != d_out) { _dim_out = (int)d_out; _mean_function = MeanFunction(_dim_out); }
+            }
+            static void _pack_rows(const std::vector<Eigen::VectorXd>& rows, Eigen::MatrixXd& out)
+            {
+                out.resize(rows.size(), rows.front().size());
+                for (size_t i = 0; i < rows.size(); ++i)
+                    for (long c = 0; c < (long)rows[i].size(); ++c) out(i, c) = rows[i](c);
+            }
+            // column means of the observations, then the host mean functor at every sample: obs_mean = Y - M
+            void _refresh_means()
+            {
+                _mean_observation = _observations.colwise().mean();
+                _compute_obs_mean();
+            }
             void _compute_obs_mean() // gp.hpp:537-548
             {
-                assert(!_samples.empty());
-                _mean_vector.resize(_samples.size(), _dim_out);
-                for (int i = 0; i < _mean_vector.rows(); i++) {
-                    assert(_samples[i].rows() == _dim_in);
-                    _mean_vector.row(i) = _mean_function(_samples[i], *this);
+                const long n = (long)_samples.size();
+                assert(n > 0);
+                _mean_vector.resize(n, _dim_out);
+                for (long i = 0; i < n; ++i) {
+                    const Eigen::VectorXd m = _mean_function(_samples[i], *this);
+                    for (int p = 0; p < _dim_out; ++p) _mean_vector(i, p) = m(p);
                 }
                 _obs_mean = _observations - _mean_vector;
             }
-            void _compute_full_kernel() // gp.hpp:550-571
+            template <typename A, typename Functor>
+            static void _restore_params(const A& archive, Functor& fn, const char* name)
+            {
+                if (fn.h_params_size() == 0) return;
+                Eigen::VectorXd hp;
+                archive.load(hp, name);
+                assert((size_t)hp.size() == (size_t)fn.h_params_size());
+                fn.set_h_params(hp);
+            }
+            void _upload_data()
             {
                 const long n = (long)_samples.size();
                 std::vector<double> X((size_t)n * _dim_in);
                 for (long i = 0; i < n; ++i)
                     for (int d = 0; d < _dim_in; ++d) X[(size_t)i * _dim_in + d] = _samples[i](d);
                 lb_check(lb_set_data(_h, n, _dim_in, _dim_out, X.data(), _obs_mean.data()), "lb_set_data");
+            }
+            void _compute_full_kernel() // gp.hpp:550-571: K -> L -> alpha, all on the device
+            {
+                _upload_data();
                 _push_kernel();
                 _info = lb_fit(_h);
                 lb_check(_info, "lb_fit");

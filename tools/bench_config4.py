@@ -60,6 +60,10 @@ def main():
 
     step()  # warm-up: inverts the factor, allocates
     torch.cuda.synchronize(dev)
+    PC = ["kbuild", "potf2", "trsm_panel", "syrk", "syrk_col", "trsv", "kstar", "qstep", "qreduce", "acq", "trtri", "lauum", "grad", "other"]
+    lib.lb_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    lib.lb_profile_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.lb_profile_enable(gp._h, 1)
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -69,6 +73,9 @@ def main():
     e1.record(st)
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / a.steps
+    pms = (C.c_double * len(PC))(); pcnt = (C.c_longlong * len(PC))()
+    lib.lb_profile_read(gp._h, pms, pcnt, 1)
+    stage = {PC[i]: pms[i] / a.steps for i in range(len(PC)) if pcnt[i]}
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -77,7 +84,7 @@ def main():
         flops = float(a.m_total) * N * N  # M N^2 (triangular GEMM, 2 flops per MAC on N^2/2)
         print(json.dumps({"config": f"N={N}, D={D}, {a.precision}, EI over {a.m_total} candidates on {world} GPU(s)",
                           "candidates_per_s": a.m_total / (ms * 1e-3), "ms_per_batch": ms, "fit_s": t_fit, "tflops_total": flops / (ms * 1e-3) / 1e12,
-                          "tflops_per_gpu": flops / (ms * 1e-3) / 1e12 / world, "best": best, "n_gpus": world}))
+                          "tflops_per_gpu": flops / (ms * 1e-3) / 1e12 / world, "best": best, "n_gpus": world, "stage_ms_rank0": stage}))
     if world > 1:
         dist.destroy_process_group()
 
