@@ -608,7 +608,7 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
             const int64_t Mc = std::min(Mp, cap);
             if ((rc = ensure(&w.dQs, &w.qs_bytes, sizeof(double) * D * Mc))) return rc;
             if ((rc = ensure(&w.dKt, &w.kt_bytes, sizeof(float) * (size_t)Mc * h->Np))) return rc;
-            if ((rc = ensure(&w.dNorm2, &w.norm2_bytes, sizeof(float) * (size_t)Mc))) return rc;
+            if ((rc = ensure(&w.dNorm2, &w.norm2_bytes, sizeof(float) * (size_t)Mc * 4))) return rc; // up to 4 cluster partials
             if (!w.dErr) LB_CUDA(cudaMalloc(&w.dErr, sizeof(int)));
             LB_CUDA(cudaMemsetAsync(w.dErr, 0, sizeof(int), st));
             for (int64_t m0 = 0; m0 < M; m0 += Mc) {

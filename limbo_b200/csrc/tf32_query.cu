@@ -18,6 +18,7 @@
 // Every mbarrier wait is bounded: on timeout an error flag is raised instead of hanging the GPU.
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace tf32q {
 
@@ -234,6 +235,161 @@ tf32_gemm_norm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Clustered variant: CL CTAs (CL = 2 or 4) share one candidate tile and split the n-tiles between them.  The A
+// tile (K*^T, private to a candidate tile, streamed from HBM once per n-tile) is loaded ONCE per cluster and
+// TMA-multicast into every CTA's shared memory, which divides the dominant HBM stream by CL; each CTA keeps its own
+// B tiles, TMEM accumulators, MMA issuer and epilogue.  Slot reuse is cluster-wide: every MMA commit multicasts its
+// "slot free" arrival to all CTAs of the cluster (empty barriers count CL arrivals).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mcast(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(lb_smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(lb_smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     lb_smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+
+// norm2 is [CL][M]: each CTA of a cluster writes the partial sum over its own n-tiles (summed later, fixed order).
+template <int CL>
+__global__ void __launch_bounds__(THREADS, 1)
+tf32_gemm_norm_cluster_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int64_t M, int64_t N,
+    int64_t K, int tri, float* __restrict__ norm2, int* __restrict__ err)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + (size_t)STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_base_s = (uint32_t*)(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int cluster_id = blockIdx.x / CL, nclusters = gridDim.x / CL;
+    const int m_tiles = (int)(M / BM), n_groups = (int)(N / BN) / CL; // N is a multiple of BN * CL
+    constexpr uint16_t ALL = (uint16_t)((1u << CL) - 1);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(lb_smem_u32(tmem_base_s)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all(); // every CTA's barriers are initialised before any remote arrival / multicast can target them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) { // ===== TMA producer: own B tile; rank 0 additionally multicasts the shared A tile =====
+            int s = 0; uint32_t ph = 0; bool ok = true;
+            for (int mt = cluster_id; mt < m_tiles && ok; mt += nclusters) {
+                for (int grp = 0; grp < n_groups && ok; ++grp) {
+                    const int nt = grp * CL + rank;
+                    const int64_t kend = tri ? (int64_t)(grp + 1) * CL * BN : K; // the whole cluster walks the same k range
+                    const int kblocks = (int)((kend < K ? kend : K) / BKE);
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        if (!mbar_wait(&empty[s], ph ^ 1, err)) { ok = false; break; } // freed by ALL CTAs of the cluster
+                        uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
+                        mbar_expect_tx(&full[s], STAGE_BYTES);
+                        if (rank == 0) tma_load_2d_mcast(sa, &mapA, kb * BKE, mt * BM, &full[s], ALL);
+                        tma_load_2d(sa + A_BYTES, &mapB, kb * BKE, nt * BN, &full[s]);
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    }
+    else if (warp == 1) {
+        if (lane == 0) { // ===== MMA issuer =====
+            int s = 0; uint32_t ph = 0; bool ok = true;
+            int buf = 0; uint32_t tph[2] = {0, 0};
+            for (int mt = cluster_id; mt < m_tiles && ok; mt += nclusters) {
+                for (int grp = 0; grp < n_groups && ok; ++grp) {
+                    const int64_t kend = tri ? (int64_t)(grp + 1) * CL * BN : K;
+                    const int kblocks = (int)((kend < K ? kend : K) / BKE);
+                    if (!mbar_wait(&tempty[buf], tph[buf] ^ 1, err)) { ok = false; break; }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        if (!mbar_wait(&full[s], ph, err)) { ok = false; break; }
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sa = lb_smem_u32(smem + (size_t)s * STAGE_BYTES);
+                        const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BKE / UMMA_K; ++k)
+                            umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0);
+                        umma_commit_mcast(&empty[s], ALL); // this CTA is done with slot s: tell every producer of the cluster
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                    umma_commit(&tfull[buf]);
+                    tph[buf] ^= 1;
+                    buf ^= 1;
+                }
+            }
+        }
+    }
+    else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int buf = 0; uint32_t tph[2] = {0, 0}; bool ok = true;
+        for (int mt = cluster_id; mt < m_tiles && ok; mt += nclusters) {
+            float acc = 0.f;
+            for (int grp = 0; grp < n_groups && ok; ++grp) {
+                if (!mbar_wait(&tfull[buf], tph[buf], err)) { ok = false; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float d = __uint_as_float(v[j]);
+                        acc = fmaf(d, d, acc);
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]);
+                tph[buf] ^= 1;
+                buf ^= 1;
+            }
+            if (ok) norm2[(int64_t)rank * M + (int64_t)mt * BM + row] = acc;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all(); // nobody leaves while a peer may still multicast into its shared memory / barriers
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -286,6 +442,63 @@ int lb_launch_tf32_gemm_norm(cudaStream_t st, const float* dA, int64_t lda, cons
     tf32_gemm_norm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mapA, mapB, M, N, K, tri, dNorm2, dDout, dErr);
     LB_CUDA(cudaGetLastError());
     return LB_OK;
+}
+
+// Clustered launch: N must be a multiple of 256 * CL; dNorm2 holds CL partial rows of M floats.
+template <int CL>
+static int launch_cluster(cudaStream_t st, const CUtensorMap& mapA, const CUtensorMap& mapB, int64_t M, int64_t N, int64_t K, int tri,
+    float* dNorm2, int* dErr, int grid)
+{
+    using namespace tf32q;
+    static bool attr_done = false;
+    if (!attr_done) {
+        LB_CUDA(cudaFuncSetAttribute(tf32_gemm_norm_cluster_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    LB_CUDA(cudaLaunchKernelEx(&cfg, tf32_gemm_norm_cluster_kernel<CL>, mapA, mapB, M, N, K, tri, dNorm2, dErr));
+    return LB_OK;
+}
+
+int lb_launch_tf32_gemm_norm_cluster(cudaStream_t st, const float* dA, int64_t lda, const float* dB, int64_t ldb, int64_t M, int64_t N,
+    int64_t K, int tri, float* dNorm2, int* dErr, int sms, int cl)
+{
+    using namespace tf32q;
+    if (M % BM || N % (BN * cl) || K % BKE || (cl != 2 && cl != 4)) return LB_ERR_ARG;
+    alignas(64) CUtensorMap mapA, mapB;
+    int rc;
+    if ((rc = make_map(&mapA, dA, M, K, lda, BM))) return rc;
+    if ((rc = make_map(&mapB, dB, N, K, ldb, BN))) return rc;
+    const int m_tiles = (int)(M / BM);
+    int nclusters = sms / cl;
+    if (nclusters > m_tiles) nclusters = m_tiles;
+    const int grid = nclusters * cl;
+    return cl == 2 ? launch_cluster<2>(st, mapA, mapB, M, N, K, tri, dNorm2, dErr, grid)
+                   : launch_cluster<4>(st, mapA, mapB, M, N, K, tri, dNorm2, dErr, grid);
+}
+
+extern "C" int lb_debug_tf32_gemm_cluster(const float* dA, const float* dB, long long M, long long N, long long K, int tri, float* dNorm2,
+    int cl)
+{
+    int* dErr = nullptr;
+    LB_CUDA(cudaMalloc(&dErr, sizeof(int)));
+    LB_CUDA(cudaMemset(dErr, 0, sizeof(int)));
+    int rc = lb_launch_tf32_gemm_norm_cluster(0, dA, K, dB, K, M, N, K, tri, dNorm2, dErr, 148, cl);
+    if (rc) { cudaFree(dErr); return rc; }
+    LB_CUDA(cudaDeviceSynchronize());
+    int herr = 0;
+    LB_CUDA(cudaMemcpy(&herr, dErr, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(dErr);
+    return herr ? LB_ERR_TIMEOUT : LB_OK;
 }
 
 extern "C" int lb_debug_tf32_gemm(const float* dA, const float* dB, long long M, long long N, long long K, int tri, float* dNorm2,
@@ -422,11 +635,14 @@ linv_to_f32_rowmajor_kernel(const double* __restrict__ Linv, int64_t ld, float* 
 }
 
 __global__ void __launch_bounds__(256)
-sigma2_t32_kernel(const float* __restrict__ norm2, int64_t M, double kvv, double noise, double* __restrict__ s2)
+sigma2_t32_kernel(const float* __restrict__ norm2, int nparts, int64_t part_stride, int64_t M, double kvv, double noise,
+    double* __restrict__ s2)
 {
     const int64_t c = blockIdx.x * (int64_t)256 + threadIdx.x;
     if (c >= M) return;
-    double res = kvv - (double)norm2[c];
+    double nrm = 0.0;
+    for (int p = 0; p < nparts; ++p) nrm += (double)norm2[(int64_t)p * part_stride + c]; // partial sums of the cluster's CTAs
+    double res = kvv - nrm;
     res = (res <= 2.220446049250313e-16) ? 0.0 : res; // gp.hpp:623
     s2[c] = res + noise;                               // gp.hpp:166
 }
@@ -434,6 +650,22 @@ sigma2_t32_kernel(const float* __restrict__ norm2, int64_t M, double kvv, double
 } // namespace tf32q
 
 int lb_launch_linv(lb_gp* h);
+int lb_launch_tf32_gemm_norm_cluster(cudaStream_t st, const float* dA, int64_t lda, const float* dB, int64_t ldb, int64_t M, int64_t N,
+    int64_t K, int tri, float* dNorm2, int* dErr, int sms, int cl);
+
+// CTAs per cluster sharing one candidate tile (A operand multicast).  Measured at N=16384, 1M candidates: 1 -> 518 ms,
+// 2 -> 467 ms, 4 -> 726 ms (lock-step coupling of four CTAs costs more than the saved HBM stream): default 2;
+// LB_TF32_CLUSTER=1|2|4 overrides.
+int lb_tf32_cluster_size()
+{
+    static int cl = 0;
+    if (!cl) {
+        const char* e = getenv("LB_TF32_CLUSTER");
+        cl = e ? atoi(e) : 2;
+        if (cl != 1 && cl != 2 && cl != 4) cl = 2;
+    }
+    return cl;
+}
 
 // Prepare the fp32 row-major copy of L^-1 (rows padded to a multiple of 256 with zeros).
 int lb_tf32_prepare(lb_gp* h)
@@ -442,7 +674,8 @@ int lb_tf32_prepare(lb_gp* h)
     if (h->linv32_valid) return LB_OK;
     int rc;
     if (!h->linv_valid && (rc = lb_launch_linv(h))) return rc;
-    const int64_t Np = h->Np, Nr = (Np + BN - 1) / BN * BN;
+    const int cl = lb_tf32_cluster_size();
+    const int64_t Np = h->Np, Nr = (Np + BN * cl - 1) / (BN * cl) * (BN * cl);
     if (!h->dLinv32 || h->linv32_rows != Nr) {
         if (h->dLinv32) cudaFree(h->dLinv32);
         LB_CUDA(cudaMalloc(&h->dLinv32, sizeof(float) * Nr * Np));
@@ -476,12 +709,14 @@ int lb_launch_query_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const doub
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     int rc;
+    const int cl = lb_tf32_cluster_size();
     {
         LbProfScope ps(h, st, LB_PC_QSTEP);
-        rc = lb_launch_tf32_gemm_norm(st, dKt, Np, h->dLinv32, Np, Mcp, h->linv32_rows, Np, 1, dNorm2, nullptr, dErr, sms);
+        if (cl == 1) rc = lb_launch_tf32_gemm_norm(st, dKt, Np, h->dLinv32, Np, Mcp, h->linv32_rows, Np, 1, dNorm2, nullptr, dErr, sms);
+        else rc = lb_launch_tf32_gemm_norm_cluster(st, dKt, Np, h->dLinv32, Np, Mcp, h->linv32_rows, Np, 1, dNorm2, dErr, sms, cl);
     }
     if (rc) return rc;
-    sigma2_t32_kernel<<<(unsigned)((Mc + 255) / 256), 256, 0, st>>>(dNorm2, Mc, h->kp.sf2, h->kp.noise, dS2);
+    sigma2_t32_kernel<<<(unsigned)((Mc + 255) / 256), 256, 0, st>>>(dNorm2, cl, Mcp, Mc, h->kp.sf2, h->kp.noise, dS2);
     if (launches) *launches += 4;
     LB_CUDA(cudaGetLastError());
     return LB_OK;

@@ -30,4 +30,20 @@ for tri in (0, 1):
     nerr = ((nrm.double() - (ref ** 2).sum(1)).abs() / (ref ** 2).sum(1)).max().item()
     print(f"tri={tri} rc={rc} max|D-ref|={err:.3e} (scale {scale:.2f}, rel {err / scale:.2e}) norm rel err {nerr:.2e} time {dt * 1e3:.1f} ms")
     assert rc == 0 and err / scale < 5e-3 and nerr < 5e-3
+lib.lb_debug_tf32_gemm_cluster.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_int]
+for cl in (2, 4):
+    if N % (256 * cl):
+        continue
+    for tri in (0, 1):
+        Bt = torch.tril(B) if tri else B
+        part = torch.zeros(cl, M, device="cuda", dtype=torch.float32)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        rc = lib.lb_debug_tf32_gemm_cluster(A.data_ptr(), Bt.data_ptr(), M, N, K, tri, part.data_ptr(), cl)
+        dt = time.time() - t0
+        ref = (A.double() @ Bt.double().T)
+        nrm = part.double().sum(0)
+        nerr = ((nrm - (ref ** 2).sum(1)).abs() / (ref ** 2).sum(1)).max().item()
+        print(f"cluster={cl} tri={tri} rc={rc} norm rel err {nerr:.2e} time {dt * 1e3:.1f} ms")
+        assert rc == 0 and nerr < 5e-3
 print("TF32 GEMM OK")
