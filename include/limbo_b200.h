@@ -64,6 +64,9 @@ typedef struct lb_gp lb_gp;
 /* fit / likelihood in fp64; lb_query and lb_acq_argmax compute sigma^2 on the tf32 tensor cores (tcgen05, fp32
  * accumulation) from an fp64-inverted factor: |d sigma^2| ~ 1e-3 k(v,v), stated in tests/test_gpu_tf32.py */
 #define LB_PREC_TF32 1
+/* same path with fp16 operands (same 11-bit significand as tf32, half the operand bytes, twice the tensor rate);
+ * K* is scaled by 1/sigma_f^2 and L^-1 by a power of two so that both stay inside the fp16 range */
+#define LB_PREC_FP16 2
 
 /* Lifetime.  Replaces GP(int dim_in, int dim_out) / ~GP / the copy constructor
  * KernelLFOptimization relies on (model/gp/kernel_lf_opt.hpp:79). */

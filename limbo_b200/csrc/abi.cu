@@ -273,7 +273,7 @@ int lb_profile_enable(lb_gp* h, int on);
 int lb_create(lb_gp** out, int device, int precision)
 {
     if (!out) return LB_ERR_ARG;
-    if (precision != LB_PREC_FP64 && precision != LB_PREC_TF32) return LB_ERR_UNSUPPORTED;
+    if (precision != LB_PREC_FP64 && precision != LB_PREC_TF32 && precision != LB_PREC_FP16) return LB_ERR_UNSUPPORTED;
     int ndev = 0;
     LB_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return LB_ERR_ARG;
@@ -601,14 +601,15 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
             LB_CUDA(cudaMemcpyAsync(w.dQraw, Xq, sizeof(double) * M * D, cudaMemcpyHostToDevice, st));
             dQraw = w.dQraw;
         }
-        if (h->precision == LB_PREC_TF32) {
-            // reduced-precision variance on tcgen05 (tf32_query.cu); mu accumulates in fp64 from fp32 kernel values
+        if (h->precision == LB_PREC_TF32 || h->precision == LB_PREC_FP16) {
+            // reduced-precision variance on tcgen05 (tf32_query.cu); mu is accumulated in fp64 from the fp64 kernel values
             if ((rc = lb_tf32_prepare(h))) return rc;
             const int64_t cap = std::max<int64_t>(LB_TILE, ((int64_t)4 << 30) / (4 * h->Np) / LB_TILE * LB_TILE);
             const int64_t Mc = std::min(Mp, cap);
             if ((rc = ensure(&w.dQs, &w.qs_bytes, sizeof(double) * D * Mc))) return rc;
             if ((rc = ensure(&w.dKt, &w.kt_bytes, sizeof(float) * (size_t)Mc * h->Np))) return rc;
             if ((rc = ensure(&w.dNorm2, &w.norm2_bytes, sizeof(float) * (size_t)Mc * 4))) return rc; // up to 4 cluster partials
+            if ((rc = ensure(&w.dV, &w.v_bytes, sizeof(double) * (size_t)P * (h->Np / LB_TILE) * Mc))) return rc; // mean partials per training tile
             if (!w.dErr) LB_CUDA(cudaMalloc(&w.dErr, sizeof(int)));
             LB_CUDA(cudaMemsetAsync(w.dErr, 0, sizeof(int), st));
             for (int64_t m0 = 0; m0 < M; m0 += Mc) {
@@ -617,7 +618,7 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
                 dim3 g1((unsigned)((mcp + 255) / 256), (unsigned)D);
                 pack_soa_kernel<<<g1, 256, 0, st>>>(dQraw + m0 * D, mc, D, w.dQs, mcp, h->kp, 1);
                 h->launches++;
-                if ((rc = lb_launch_query_tf32(h, st, mc, w.dQs, mcp, w.dKt, w.dNorm2, w.dErr, w.dMu + m0 * P, w.dS2 + m0, &h->launches)))
+                if ((rc = lb_launch_query_tf32(h, st, mc, w.dQs, mcp, w.dKt, w.dNorm2, w.dErr, w.dV, w.dMu + m0 * P, w.dS2 + m0, &h->launches)))
                     return rc;
             }
             if (!out_dev) {

@@ -232,7 +232,7 @@ struct lb_gp {
     double* dAlpha = nullptr; // Np x P
     double* dLinv = nullptr; // Np x Np (lazy: L^-1)
     double* dKinv = nullptr; // Np x Np (lazy: K^-1, lower valid + mirrored)
-    float* dLinv32 = nullptr; int64_t linv32_rows = 0; bool linv32_valid = false; // TF32 path: row-major fp32 L^-1
+    float* dLinv32 = nullptr; int64_t linv32_rows = 0; bool linv32_valid = false; double linv32_scale = 1.0; // reduced-precision path: row-major fp32 / fp16 L^-1
     int* dInfo = nullptr;    // [0] first failing pivot (1-based) or 0; [1] solver error
     int* dFlags = nullptr;   // T+1 ints: trsv progress flags / ticket
     double* dScratch = nullptr; size_t scratch_bytes = 0;
@@ -273,7 +273,10 @@ int lb_launch_kinv(lb_gp* h);
 int lb_launch_grad(lb_gp* h, int optimize_noise, double* dGrad);
 int lb_ensure_scratch(lb_gp* h, size_t bytes);
 int lb_tf32_prepare(lb_gp* h);
-int lb_launch_tf32_gemm_norm(cudaStream_t st, const float* dA, int64_t lda, const float* dB, int64_t ldb, int64_t M, int64_t N, int64_t K,
-    int tri, float* dNorm2, float* dDout, int* dErr, int grid);
+int lb_launch_tf32_gemm_norm(cudaStream_t st, const void* dA, int64_t lda, const void* dB, int64_t ldb, int64_t M, int64_t N, int64_t K,
+    int tri, float* dNorm2, float* dDout, int* dErr, int grid, int f16);
+int lb_launch_tf32_gemm_norm_cluster(cudaStream_t st, const void* dA, int64_t lda, const void* dB, int64_t ldb, int64_t M, int64_t N,
+    int64_t K, int tri, float* dNorm2, int* dErr, int sms, int cl, int f16);
+int lb_tf32_cluster_size();
 int lb_launch_query_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const double* dQs, int64_t Mcp, float* dKt, float* dNorm2,
-    int* dErr, double* dMu, double* dS2, long long* launches);
+    int* dErr, double* dMuPart, double* dMu, double* dS2, long long* launches);

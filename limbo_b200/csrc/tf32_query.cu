@@ -18,17 +18,20 @@
 // Every mbarrier wait is bounded: on timeout an error flag is raised instead of hanging the GPU.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
+#include <cmath>
 #include <cstdlib>
 
 namespace tf32q {
 
 constexpr int BM = 128;       // candidates per tile (UMMA M)
 constexpr int BN = 256;       // outputs (rows of L^-1) per tile (UMMA N)
-constexpr int BKE = 32;       // k elements per stage = 128 B = one swizzle atom row
-constexpr int UMMA_K = 8;     // tf32
+// k elements per stage = 128 B = one swizzle atom row: 32 tf32 or 64 fp16; one stage is always 4 MMAs (K = 8 tf32 / 16 fp16)
+template <bool F16> __host__ __device__ constexpr int bke() { return F16 ? 64 : 32; }
+constexpr int MMAS_PER_STAGE = 4;
 constexpr int STAGES = 4;
-constexpr int A_BYTES = BM * BKE * 4;  // 16 KB
-constexpr int B_BYTES = BN * BKE * 4;  // 32 KB
+constexpr int A_BYTES = BM * 128;  // 16 KB
+constexpr int B_BYTES = BN * 128;  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int THREADS = 192;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -86,16 +89,30 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4, a/b format TF32 = 2 @7/@10,
 // a/b K-major (0) @15/@16, N >> 3 @17, M >> 4 @24
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
+// a/b format: F16 = 0, TF32 = 2
+template <bool F16>
+__host__ __device__ constexpr uint32_t idesc()
 {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
-        : "memory");
+    return (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <bool F16>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
+{
+    if (F16)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc<true>()), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc<false>()), "r"(accumulate)
+            : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar)
 {
@@ -116,6 +133,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 
 // D[c, n] = sum_k A[c, k] B[n, k]; tri != 0: k only up to the end of the n-tile (B lower triangular).
 // norm2[c] += sum_n D[c, n]^2 ; Dout (optional, row-major M x N) receives D for validation.
+template <bool F16>
 __global__ void __launch_bounds__(THREADS, 1)
 tf32_gemm_norm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int64_t M, int64_t N,
     int64_t K, int tri, float* __restrict__ norm2, float* __restrict__ Dout, int* __restrict__ err)
@@ -152,13 +170,13 @@ tf32_gemm_norm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
             for (int mt = blockIdx.x; mt < m_tiles && ok; mt += gridDim.x) {
                 for (int nt = 0; nt < n_tiles && ok; ++nt) {
                     const int64_t kend = tri ? (int64_t)(nt + 1) * BN : K;
-                    const int kblocks = (int)((kend < K ? kend : K) / BKE);
+                    const int kblocks = (int)((kend < K ? kend : K) / bke<F16>());
                     for (int kb = 0; kb < kblocks; ++kb) {
                         if (!mbar_wait(&empty[s], ph ^ 1, err)) { ok = false; break; }
                         uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
                         mbar_expect_tx(&full[s], STAGE_BYTES);
-                        tma_load_2d(sa, &mapA, kb * BKE, mt * BM, &full[s]);
-                        tma_load_2d(sa + A_BYTES, &mapB, kb * BKE, nt * BN, &full[s]);
+                        tma_load_2d(sa, &mapA, kb * bke<F16>(), mt * BM, &full[s]);
+                        tma_load_2d(sa + A_BYTES, &mapB, kb * bke<F16>(), nt * BN, &full[s]);
                         if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
                 }
@@ -173,7 +191,7 @@ tf32_gemm_norm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
             for (int mt = blockIdx.x; mt < m_tiles && ok; mt += gridDim.x) {
                 for (int nt = 0; nt < n_tiles && ok; ++nt) {
                     const int64_t kend = tri ? (int64_t)(nt + 1) * BN : K;
-                    const int kblocks = (int)((kend < K ? kend : K) / BKE);
+                    const int kblocks = (int)((kend < K ? kend : K) / bke<F16>());
                     if (!mbar_wait(&tempty[buf], tph[buf] ^ 1, err)) { ok = false; break; } // epilogue drained this accumulator
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
@@ -183,8 +201,8 @@ tf32_gemm_norm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                         const uint32_t sa = lb_smem_u32(smem + (size_t)s * STAGE_BYTES);
                         const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + A_BYTES);
 #pragma unroll
-                        for (int k = 0; k < BKE / UMMA_K; ++k) // +32 B per UMMA_K step inside the 128 B swizzle row: +2 in the >>4 address field
-                            umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0);
+                        for (int k = 0; k < MMAS_PER_STAGE; ++k) // +32 B per MMA inside the 128 B swizzle row: +2 in the >>4 address field
+                            umma<F16>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0);
                         umma_commit(&empty[s]); // frees the smem slot when these MMAs have read it
                         if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
@@ -268,7 +286,7 @@ __device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask)
 }
 
 // norm2 is [CL][M]: each CTA of a cluster writes the partial sum over its own n-tiles (summed later, fixed order).
-template <int CL>
+template <int CL, bool F16>
 __global__ void __launch_bounds__(THREADS, 1)
 tf32_gemm_norm_cluster_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int64_t M, int64_t N,
     int64_t K, int tri, float* __restrict__ norm2, int* __restrict__ err)
@@ -309,13 +327,13 @@ tf32_gemm_norm_cluster_kernel(const __grid_constant__ CUtensorMap mapA, const __
                 for (int grp = 0; grp < n_groups && ok; ++grp) {
                     const int nt = grp * CL + rank;
                     const int64_t kend = tri ? (int64_t)(grp + 1) * CL * BN : K; // the whole cluster walks the same k range
-                    const int kblocks = (int)((kend < K ? kend : K) / BKE);
+                    const int kblocks = (int)((kend < K ? kend : K) / bke<F16>());
                     for (int kb = 0; kb < kblocks; ++kb) {
                         if (!mbar_wait(&empty[s], ph ^ 1, err)) { ok = false; break; } // freed by ALL CTAs of the cluster
                         uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
                         mbar_expect_tx(&full[s], STAGE_BYTES);
-                        if (rank == 0) tma_load_2d_mcast(sa, &mapA, kb * BKE, mt * BM, &full[s], ALL);
-                        tma_load_2d(sa + A_BYTES, &mapB, kb * BKE, nt * BN, &full[s]);
+                        if (rank == 0) tma_load_2d_mcast(sa, &mapA, kb * bke<F16>(), mt * BM, &full[s], ALL);
+                        tma_load_2d(sa + A_BYTES, &mapB, kb * bke<F16>(), nt * BN, &full[s]);
                         if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
                 }
@@ -329,7 +347,7 @@ tf32_gemm_norm_cluster_kernel(const __grid_constant__ CUtensorMap mapA, const __
             for (int mt = cluster_id; mt < m_tiles && ok; mt += nclusters) {
                 for (int grp = 0; grp < n_groups && ok; ++grp) {
                     const int64_t kend = tri ? (int64_t)(grp + 1) * CL * BN : K;
-                    const int kblocks = (int)((kend < K ? kend : K) / BKE);
+                    const int kblocks = (int)((kend < K ? kend : K) / bke<F16>());
                     if (!mbar_wait(&tempty[buf], tph[buf] ^ 1, err)) { ok = false; break; }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
@@ -339,8 +357,8 @@ tf32_gemm_norm_cluster_kernel(const __grid_constant__ CUtensorMap mapA, const __
                         const uint32_t sa = lb_smem_u32(smem + (size_t)s * STAGE_BYTES);
                         const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + A_BYTES);
 #pragma unroll
-                        for (int k = 0; k < BKE / UMMA_K; ++k)
-                            umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0);
+                        for (int k = 0; k < MMAS_PER_STAGE; ++k)
+                            umma<F16>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0);
                         umma_commit_mcast(&empty[s], ALL); // this CTA is done with slot s: tell every producer of the cluster
                         if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
@@ -406,15 +424,15 @@ static EncodeTiledFn get_encode()
 }
 
 // row-major (rows x K) fp32 matrix, boxes of 32 k x box_rows rows, 128-byte swizzle, tf32 rounding on load
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t ld, int box_rows)
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows, bool f16)
 {
     EncodeTiledFn enc = get_encode();
     if (!enc) return LB_ERR_UNSUPPORTED;
     cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)box_rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * (f16 ? 2 : 4)};
+    cuuint32_t box[2] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? LB_OK : LB_ERR_CUDA;
 }
@@ -423,36 +441,38 @@ bool g_attr = false;
 
 } // namespace tf32q
 
-// A: M x K (ld lda), B: N x K (ld ldb), fp32 row-major in device memory; M % 128 == 0, N % 256 == 0, K % 32 == 0.
-int lb_launch_tf32_gemm_norm(cudaStream_t st, const float* dA, int64_t lda, const float* dB, int64_t ldb, int64_t M, int64_t N, int64_t K,
-    int tri, float* dNorm2, float* dDout, int* dErr, int grid)
+// A: M x K (ld lda), B: N x K (ld ldb), row-major fp32 (tf32 MMA) or fp16 in device memory; M % 128 == 0, N % 256 == 0, K % 64 == 0.
+int lb_launch_tf32_gemm_norm(cudaStream_t st, const void* dA, int64_t lda, const void* dB, int64_t ldb, int64_t M, int64_t N, int64_t K,
+    int tri, float* dNorm2, float* dDout, int* dErr, int grid, int f16)
 {
     using namespace tf32q;
-    if (M % BM || N % BN || K % BKE) return LB_ERR_ARG;
+    if (M % BM || N % BN || K % 64) return LB_ERR_ARG;
     if (!g_attr) {
-        LB_CUDA(cudaFuncSetAttribute(tf32_gemm_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        LB_CUDA(cudaFuncSetAttribute(tf32_gemm_norm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        LB_CUDA(cudaFuncSetAttribute(tf32_gemm_norm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         g_attr = true;
     }
     alignas(64) CUtensorMap mapA, mapB;
     int rc;
-    if ((rc = make_map(&mapA, dA, M, K, lda, BM))) return rc;
-    if ((rc = make_map(&mapB, dB, N, K, ldb, BN))) return rc;
+    if ((rc = make_map(&mapA, dA, M, K, lda, BM, f16 != 0))) return rc;
+    if ((rc = make_map(&mapB, dB, N, K, ldb, BN, f16 != 0))) return rc;
     const int m_tiles = (int)(M / BM);
     if (grid > m_tiles) grid = m_tiles;
-    tf32_gemm_norm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mapA, mapB, M, N, K, tri, dNorm2, dDout, dErr);
+    if (f16) tf32_gemm_norm_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(mapA, mapB, M, N, K, tri, dNorm2, dDout, dErr);
+    else tf32_gemm_norm_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(mapA, mapB, M, N, K, tri, dNorm2, dDout, dErr);
     LB_CUDA(cudaGetLastError());
     return LB_OK;
 }
 
 // Clustered launch: N must be a multiple of 256 * CL; dNorm2 holds CL partial rows of M floats.
-template <int CL>
+template <int CL, bool F16>
 static int launch_cluster(cudaStream_t st, const CUtensorMap& mapA, const CUtensorMap& mapB, int64_t M, int64_t N, int64_t K, int tri,
     float* dNorm2, int* dErr, int grid)
 {
     using namespace tf32q;
     static bool attr_done = false;
     if (!attr_done) {
-        LB_CUDA(cudaFuncSetAttribute(tf32_gemm_norm_cluster_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        LB_CUDA(cudaFuncSetAttribute(tf32_gemm_norm_cluster_kernel<CL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr_done = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -465,34 +485,37 @@ static int launch_cluster(cudaStream_t st, const CUtensorMap& mapA, const CUtens
     at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    LB_CUDA(cudaLaunchKernelEx(&cfg, tf32_gemm_norm_cluster_kernel<CL>, mapA, mapB, M, N, K, tri, dNorm2, dErr));
+    LB_CUDA(cudaLaunchKernelEx(&cfg, tf32_gemm_norm_cluster_kernel<CL, F16>, mapA, mapB, M, N, K, tri, dNorm2, dErr));
     return LB_OK;
 }
 
-int lb_launch_tf32_gemm_norm_cluster(cudaStream_t st, const float* dA, int64_t lda, const float* dB, int64_t ldb, int64_t M, int64_t N,
-    int64_t K, int tri, float* dNorm2, int* dErr, int sms, int cl)
+int lb_launch_tf32_gemm_norm_cluster(cudaStream_t st, const void* dA, int64_t lda, const void* dB, int64_t ldb, int64_t M, int64_t N,
+    int64_t K, int tri, float* dNorm2, int* dErr, int sms, int cl, int f16)
 {
     using namespace tf32q;
-    if (M % BM || N % (BN * cl) || K % BKE || (cl != 2 && cl != 4)) return LB_ERR_ARG;
+    if (M % BM || N % (BN * cl) || K % 64 || (cl != 2 && cl != 4)) return LB_ERR_ARG;
     alignas(64) CUtensorMap mapA, mapB;
     int rc;
-    if ((rc = make_map(&mapA, dA, M, K, lda, BM))) return rc;
-    if ((rc = make_map(&mapB, dB, N, K, ldb, BN))) return rc;
+    if ((rc = make_map(&mapA, dA, M, K, lda, BM, f16 != 0))) return rc;
+    if ((rc = make_map(&mapB, dB, N, K, ldb, BN, f16 != 0))) return rc;
     const int m_tiles = (int)(M / BM);
     int nclusters = sms / cl;
     if (nclusters > m_tiles) nclusters = m_tiles;
     const int grid = nclusters * cl;
-    return cl == 2 ? launch_cluster<2>(st, mapA, mapB, M, N, K, tri, dNorm2, dErr, grid)
-                   : launch_cluster<4>(st, mapA, mapB, M, N, K, tri, dNorm2, dErr, grid);
+    if (f16)
+        return cl == 2 ? launch_cluster<2, true>(st, mapA, mapB, M, N, K, tri, dNorm2, dErr, grid)
+                       : launch_cluster<4, true>(st, mapA, mapB, M, N, K, tri, dNorm2, dErr, grid);
+    return cl == 2 ? launch_cluster<2, false>(st, mapA, mapB, M, N, K, tri, dNorm2, dErr, grid)
+                   : launch_cluster<4, false>(st, mapA, mapB, M, N, K, tri, dNorm2, dErr, grid);
 }
 
-extern "C" int lb_debug_tf32_gemm_cluster(const float* dA, const float* dB, long long M, long long N, long long K, int tri, float* dNorm2,
-    int cl)
+extern "C" int lb_debug_tf32_gemm_cluster(const void* dA, const void* dB, long long M, long long N, long long K, int tri, float* dNorm2,
+    int cl, int f16)
 {
     int* dErr = nullptr;
     LB_CUDA(cudaMalloc(&dErr, sizeof(int)));
     LB_CUDA(cudaMemset(dErr, 0, sizeof(int)));
-    int rc = lb_launch_tf32_gemm_norm_cluster(0, dA, K, dB, K, M, N, K, tri, dNorm2, dErr, 148, cl);
+    int rc = lb_launch_tf32_gemm_norm_cluster(0, dA, K, dB, K, M, N, K, tri, dNorm2, dErr, 148, cl, f16);
     if (rc) { cudaFree(dErr); return rc; }
     LB_CUDA(cudaDeviceSynchronize());
     int herr = 0;
@@ -501,13 +524,13 @@ extern "C" int lb_debug_tf32_gemm_cluster(const float* dA, const float* dB, long
     return herr ? LB_ERR_TIMEOUT : LB_OK;
 }
 
-extern "C" int lb_debug_tf32_gemm(const float* dA, const float* dB, long long M, long long N, long long K, int tri, float* dNorm2,
-    float* dDout, int grid)
+extern "C" int lb_debug_tf32_gemm(const void* dA, const void* dB, long long M, long long N, long long K, int tri, float* dNorm2,
+    float* dDout, int grid, int f16)
 {
     int* dErr = nullptr;
     LB_CUDA(cudaMalloc(&dErr, sizeof(int)));
     LB_CUDA(cudaMemset(dErr, 0, sizeof(int)));
-    int rc = lb_launch_tf32_gemm_norm(0, dA, K, dB, K, M, N, K, tri, dNorm2, dDout, dErr, grid);
+    int rc = lb_launch_tf32_gemm_norm(0, dA, K, dB, K, M, N, K, tri, dNorm2, dDout, dErr, grid, f16);
     if (rc) { cudaFree(dErr); return rc; }
     LB_CUDA(cudaDeviceSynchronize());
     int herr = 0;
@@ -526,12 +549,16 @@ constexpr int DCH = 16;
 // Kt[c * ldk + n] = (float) k(x_n, q_c)  for one tile of 128 candidates x 128 training points; zero for n >= N.
 // grid: (Np/128, Mc/128).  Same thread mapping as kbuild_kernel: the two consecutive "rows" of a thread are two
 // consecutive n, stored as one float2 (n is the contiguous, K-major index of the GEMM's A operand).
+// F16: values are scaled by kscale (= 1 / sigma_f^2, so they lie in (0, 1]) and stored as half.
+template <bool F16>
 __global__ void __launch_bounds__(256, 2)
 kstar_t32_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, const double* __restrict__ Qs, int64_t Mp, int64_t M,
-    float* __restrict__ Kt, int64_t ldk, KernParams kp)
+    void* __restrict__ Kt_, int64_t ldk, KernParams kp, double kscale, const double* __restrict__ alpha, int P,
+    double* __restrict__ mu_part)
 {
     __shared__ __align__(128) double sxi[DCH][LB_TILE];
     __shared__ __align__(128) double sxj[DCH][LB_TILE];
+    __shared__ double spm[8][64];
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int li = lane & 7, lj = lane >> 3;
@@ -590,59 +617,105 @@ kstar_t32_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, const dou
                 const int64_t ii = gi + (e & 1), jj = gj + (e >> 1);
                 double k = lb_kernel_from_z(kp.id, z[c][e], kp);
                 if (ii >= N || jj >= M) k = 0.0;
-                v[e] = (float)k;
+                z[c][e] = k;
+                v[e] = (float)(k * kscale);
             }
-            *reinterpret_cast<float2*>(&Kt[gj * ldk + gi]) = make_float2(v[0], v[1]);
-            *reinterpret_cast<float2*>(&Kt[(gj + 1) * ldk + gi]) = make_float2(v[2], v[3]);
+            if (F16) {
+                __half* Kt = reinterpret_cast<__half*>(Kt_);
+                *reinterpret_cast<__half2*>(&Kt[gj * ldk + gi]) = __floats2half2_rn(v[0], v[1]);
+                *reinterpret_cast<__half2*>(&Kt[(gj + 1) * ldk + gi]) = __floats2half2_rn(v[2], v[3]);
+            }
+            else {
+                float* Kt = reinterpret_cast<float*>(Kt_);
+                *reinterpret_cast<float2*>(&Kt[gj * ldk + gi]) = make_float2(v[0], v[1]);
+                *reinterpret_cast<float2*>(&Kt[(gj + 1) * ldk + gi]) = make_float2(v[2], v[3]);
+            }
+        }
+        // mean partials from the fp64 kernel values: mu_part[(p * ntiles + tile) * Mp + candidate] = sum over this tile's
+        // 128 training points (lanes -> warps in a fixed order; the tiles are summed in order by mu_reduce_kernel)
+        for (int p = 0; p < P; ++p) {
+            const double a0 = alpha[(int64_t)p * Np + gi], a1 = alpha[(int64_t)p * Np + gi + 1];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                double s0 = fma(z[c][1], a1, z[c][0] * a0), s1 = fma(z[c][3], a1, z[c][2] * a0);
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                }
+                if (li == 0) {
+                    spm[warp][c * 8 + 2 * lj] = s0;
+                    spm[warp][c * 8 + 2 * lj + 1] = s1;
+                }
+            }
+            __syncthreads();
+            if (tid < 64) {
+                double s = spm[0][tid];
+#pragma unroll
+                for (int w = 1; w < 8; ++w) s += spm[w][tid];
+                mu_part[((int64_t)p * gridDim.x + blockIdx.x) * Mp + j0 + h * 64 + tid] = s;
+            }
+            __syncthreads();
         }
     }
 }
 
-// mu[c*P + p] = sum_n Kt[c, n] alpha[n, p]   (one warp per candidate, fp64 accumulation, fixed order)
+// mu[c*P + p] = sum over the training tiles of the partials written by kstar_t32_kernel (fixed order)
 __global__ void __launch_bounds__(256)
-mu_t32_kernel(const float* __restrict__ Kt, int64_t ldk, int64_t Np, const double* __restrict__ alpha, int P, int64_t M,
-    double* __restrict__ mu)
+mu_reduce_kernel(const double* __restrict__ part, int ntiles, int64_t Mp, int P, int64_t M, double* __restrict__ mu)
 {
-    const int64_t c = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (c >= M) return;
-    const float* row = Kt + c * ldk;
     for (int p = 0; p < P; ++p) {
-        const double* a = alpha + (int64_t)p * Np;
+        const double* q = part + (int64_t)p * ntiles * Mp + c;
         double s = 0.0;
-        for (int64_t n = lane * 4; n < Np; n += 128) {
-            const float4 k4 = *reinterpret_cast<const float4*>(row + n);
-            s = fma((double)k4.x, a[n], s);
-            s = fma((double)k4.y, a[n + 1], s);
-            s = fma((double)k4.z, a[n + 2], s);
-            s = fma((double)k4.w, a[n + 3], s);
-        }
-        s = lb_warp_sum(s);
-        if (lane == 0) mu[c * P + p] = s;
+        for (int t = 0; t < ntiles; ++t) s += q[(int64_t)t * Mp];
+        mu[c * P + p] = s;
+    }
+}
+
+// max |Linv| (for the fp16 scale): one value per block, reduced on the host (tiny)
+__global__ void __launch_bounds__(256)
+absmax_kernel(const double* __restrict__ A, int64_t n, double* __restrict__ out)
+{
+    __shared__ double red[8];
+    double m = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) m = fmax(m, fabs(A[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmax(m, red[w]);
+        out[blockIdx.x] = m;
     }
 }
 
 // LinvR[n * ldr + k] = (float) Linv[n + k * ld]  (column-major fp64 -> row-major fp32, 32 x 32 smem transpose)
+template <bool F16>
 __global__ void __launch_bounds__(256)
-linv_to_f32_rowmajor_kernel(const double* __restrict__ Linv, int64_t ld, float* __restrict__ R, int64_t ldr)
+linv_to_rowmajor_kernel(const double* __restrict__ Linv, int64_t ld, void* __restrict__ R_, int64_t ldr, double scale)
 {
     __shared__ float tile[32][33];
     const int64_t n0 = (int64_t)blockIdx.x * 32, k0 = (int64_t)blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int kk = ty; kk < 32; kk += 8) tile[kk][tx] = (k0 + kk <= n0 + tx) ? (float)Linv[n0 + tx + (k0 + kk) * ld] : 0.f;
+    for (int kk = ty; kk < 32; kk += 8) tile[kk][tx] = (k0 + kk <= n0 + tx) ? (float)(Linv[n0 + tx + (k0 + kk) * ld] * scale) : 0.f;
     __syncthreads();
-    for (int nn = ty; nn < 32; nn += 8) R[(n0 + nn) * ldr + k0 + tx] = tile[tx][nn];
+    for (int nn = ty; nn < 32; nn += 8) {
+        if (F16) reinterpret_cast<__half*>(R_)[(n0 + nn) * ldr + k0 + tx] = __float2half_rn(tile[tx][nn]);
+        else reinterpret_cast<float*>(R_)[(n0 + nn) * ldr + k0 + tx] = tile[tx][nn];
+    }
 }
 
 __global__ void __launch_bounds__(256)
 sigma2_t32_kernel(const float* __restrict__ norm2, int nparts, int64_t part_stride, int64_t M, double kvv, double noise,
-    double* __restrict__ s2)
+    double norm_unscale, double* __restrict__ s2)
 {
     const int64_t c = blockIdx.x * (int64_t)256 + threadIdx.x;
     if (c >= M) return;
     double nrm = 0.0;
     for (int p = 0; p < nparts; ++p) nrm += (double)norm2[(int64_t)p * part_stride + c]; // partial sums of the cluster's CTAs
-    double res = kvv - nrm;
+    double res = kvv - nrm * norm_unscale;
     res = (res <= 2.220446049250313e-16) ? 0.0 : res; // gp.hpp:623
     s2[c] = res + noise;                               // gp.hpp:166
 }
@@ -650,8 +723,7 @@ sigma2_t32_kernel(const float* __restrict__ norm2, int nparts, int64_t part_stri
 } // namespace tf32q
 
 int lb_launch_linv(lb_gp* h);
-int lb_launch_tf32_gemm_norm_cluster(cudaStream_t st, const float* dA, int64_t lda, const float* dB, int64_t ldb, int64_t M, int64_t N,
-    int64_t K, int tri, float* dNorm2, int* dErr, int sms, int cl);
+
 
 // CTAs per cluster sharing one candidate tile (A operand multicast).  Measured at N=16384, 1M candidates: 1 -> 518 ms,
 // 2 -> 467 ms, 4 -> 726 ms (lock-step coupling of four CTAs costs more than the saved HBM stream): default 2;
@@ -667,44 +739,66 @@ int lb_tf32_cluster_size()
     return cl;
 }
 
-// Prepare the fp32 row-major copy of L^-1 (rows padded to a multiple of 256 with zeros).
+// Prepare the row-major reduced-precision copy of L^-1 (rows padded with zeros to a multiple of 256 * cluster size).
+// fp32 (tf32 MMA) stores L^-1 as is; fp16 stores L^-1 * 2^e with e chosen so that max |.| <= 2^14.
 int lb_tf32_prepare(lb_gp* h)
 {
     using namespace tf32q;
     if (h->linv32_valid) return LB_OK;
+    const bool f16 = (h->precision == 2);
     int rc;
     if (!h->linv_valid && (rc = lb_launch_linv(h))) return rc;
     const int cl = lb_tf32_cluster_size();
     const int64_t Np = h->Np, Nr = (Np + BN * cl - 1) / (BN * cl) * (BN * cl);
+    const size_t esz = f16 ? 2 : 4;
     if (!h->dLinv32 || h->linv32_rows != Nr) {
         if (h->dLinv32) cudaFree(h->dLinv32);
-        LB_CUDA(cudaMalloc(&h->dLinv32, sizeof(float) * Nr * Np));
+        h->dLinv32 = nullptr;
+        LB_CUDA(cudaMalloc((void**)&h->dLinv32, esz * Nr * Np));
         h->linv32_rows = Nr;
     }
-    if (Nr > Np) LB_CUDA(cudaMemsetAsync(h->dLinv32 + Np * Np, 0, sizeof(float) * (Nr - Np) * Np, h->stream));
+    double scale = 1.0;
+    if (f16) {
+        if ((rc = lb_ensure_scratch(h, sizeof(double) * 1024))) return rc;
+        absmax_kernel<<<1024, 256, 0, h->stream>>>(h->dLinv, Np * Np, h->dScratch);
+        h->launches++;
+        double part[1024];
+        LB_CUDA(cudaMemcpyAsync(part, h->dScratch, sizeof(part), cudaMemcpyDeviceToHost, h->stream));
+        LB_CUDA(cudaStreamSynchronize(h->stream));
+        double mx = 0.0;
+        for (double v : part) mx = v > mx ? v : mx;
+        if (!(mx > 0.0) || !std::isfinite(mx)) return LB_ERR_STATE;
+        scale = std::ldexp(1.0, 14 - (int)std::ceil(std::log2(mx)));
+    }
+    h->linv32_scale = scale;
+    if (Nr > Np) LB_CUDA(cudaMemsetAsync((char*)h->dLinv32 + esz * Np * Np, 0, esz * (Nr - Np) * Np, h->stream));
     dim3 grid((unsigned)(Np / 32), (unsigned)(Np / 32));
     LbProfScope ps(h, h->stream, LB_PC_OTHER);
-    linv_to_f32_rowmajor_kernel<<<grid, 256, 0, h->stream>>>(h->dLinv, Np, h->dLinv32, Np);
+    if (f16) linv_to_rowmajor_kernel<true><<<grid, 256, 0, h->stream>>>(h->dLinv, Np, h->dLinv32, Np, scale);
+    else linv_to_rowmajor_kernel<false><<<grid, 256, 0, h->stream>>>(h->dLinv, Np, h->dLinv32, Np, 1.0);
     h->launches++;
     LB_CUDA(cudaGetLastError());
     h->linv32_valid = true;
     return LB_OK;
 }
 
-// mu (M x P, fp64) and sigma2 (M, fp64 container of a TF32-accurate value) for one chunk of Mc <= capacity candidates.
+// mu (M x P, fp64) and sigma2 (M, fp64 container of a reduced-precision value) for one chunk of Mc <= capacity candidates.
 int lb_launch_query_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const double* dQs, int64_t Mcp, float* dKt, float* dNorm2,
-    int* dErr, double* dMu, double* dS2, long long* launches)
+    int* dErr, double* dMuPart, double* dMu, double* dS2, long long* launches)
 {
     using namespace tf32q;
+    const bool f16 = (h->precision == 2);
     const int64_t Np = h->Np;
+    const double kscale = f16 ? 1.0 / h->kp.sf2 : 1.0;
     dim3 g1((unsigned)(Np / LB_TILE), (unsigned)(Mcp / LB_TILE));
     {
         LbProfScope ps(h, st, LB_PC_KSTAR);
-        kstar_t32_kernel<<<g1, 256, 0, st>>>(h->dXs, Np, h->N, dQs, Mcp, Mc, dKt, Np, h->kp);
+        if (f16) kstar_t32_kernel<true><<<g1, 256, 0, st>>>(h->dXs, Np, h->N, dQs, Mcp, Mc, dKt, Np, h->kp, kscale, h->dAlpha, h->P, dMuPart);
+        else kstar_t32_kernel<false><<<g1, 256, 0, st>>>(h->dXs, Np, h->N, dQs, Mcp, Mc, dKt, Np, h->kp, kscale, h->dAlpha, h->P, dMuPart);
     }
     {
         LbProfScope ps(h, st, LB_PC_QREDUCE);
-        mu_t32_kernel<<<(unsigned)((Mc + 7) / 8), 256, 0, st>>>(dKt, Np, Np, h->dAlpha, h->P, Mc, dMu);
+        mu_reduce_kernel<<<(unsigned)((Mc + 255) / 256), 256, 0, st>>>(dMuPart, (int)(Np / LB_TILE), Mcp, h->P, Mc, dMu);
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
@@ -712,11 +806,13 @@ int lb_launch_query_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const doub
     const int cl = lb_tf32_cluster_size();
     {
         LbProfScope ps(h, st, LB_PC_QSTEP);
-        if (cl == 1) rc = lb_launch_tf32_gemm_norm(st, dKt, Np, h->dLinv32, Np, Mcp, h->linv32_rows, Np, 1, dNorm2, nullptr, dErr, sms);
-        else rc = lb_launch_tf32_gemm_norm_cluster(st, dKt, Np, h->dLinv32, Np, Mcp, h->linv32_rows, Np, 1, dNorm2, dErr, sms, cl);
+        if (cl == 1) rc = lb_launch_tf32_gemm_norm(st, dKt, Np, h->dLinv32, Np, Mcp, h->linv32_rows, Np, 1, dNorm2, nullptr, dErr, sms, f16);
+        else rc = lb_launch_tf32_gemm_norm_cluster(st, dKt, Np, h->dLinv32, Np, Mcp, h->linv32_rows, Np, 1, dNorm2, dErr, sms, cl, f16);
     }
     if (rc) return rc;
-    sigma2_t32_kernel<<<(unsigned)((Mc + 255) / 256), 256, 0, st>>>(dNorm2, cl, Mcp, Mc, h->kp.sf2, h->kp.noise, dS2);
+    // D was computed from (K* kscale) and (L^-1 scale): |V|^2 = norm / (kscale scale)^2
+    const double unscale = 1.0 / ((kscale * h->linv32_scale) * (kscale * h->linv32_scale));
+    sigma2_t32_kernel<<<(unsigned)((Mc + 255) / 256), 256, 0, st>>>(dNorm2, cl, Mcp, Mc, h->kp.sf2, h->kp.noise, unscale, dS2);
     if (launches) *launches += 4;
     LB_CUDA(cudaGetLastError());
     return LB_OK;

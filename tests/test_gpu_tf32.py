@@ -8,15 +8,16 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("prec", ["tf32", "fp16"])
 @pytest.mark.parametrize("kname,N,D,M", [("SquaredExpARD", 1000, 12, 3000), ("MaternFiveHalves", 700, 6, 1500), ("SquaredExpARD", 130, 3, 257)])
-def test_tf32_query_close_to_fp64(kname, N, D, M):
+def test_tf32_query_close_to_fp64(kname, N, D, M, prec):
     from limbo_b200 import acqui, kernel, mean, model, synth
     X = synth.points(1234, N, D)
     y = synth.targets(X)
     Xq = synth.points(1235, M, D)
     kw = dict(kernel=getattr(kernel, kname), mean=mean.Data)
     g64 = model.GP(D, 1, **kw)
-    g32 = model.GP(D, 1, precision="tf32", **kw)
+    g32 = model.GP(D, 1, precision=prec, **kw)
     g64.compute(X, y[:, None])
     g32.compute(X, y[:, None])
     # the fit itself is fp64 in both modes
