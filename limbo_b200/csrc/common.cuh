@@ -118,6 +118,55 @@ __device__ __forceinline__ double lb_kernel_from_z(int id, double z, const KernP
     }
 }
 
+// exp(t) for t <= 0, branch-free: n = rint(t log2 e), r = t - n ln 2 (two-term), degree-13 Taylor in |r| <= 0.347
+// (truncation < 5e-18), 2^n by an exponent-field add.  Relative error < 3e-16 for t >= -708, exactly 0 below (where
+// the reference's std::exp returns a denormal < 2.3e-308).  Used by the reduced-precision K* build, which is bound by
+// the fp64 pipe: ~18 fp64 instructions and no slow-path branch, so the 32 evaluations of a thread interleave.
+__device__ __forceinline__ double lb_exp_nonpos(double t)
+{
+    const double MAGIC = 6755399441055744.0; // 1.5 * 2^52
+    double fn = fma(t, 1.4426950408889634074, MAGIC);
+    const int n = __double2loint(fn);
+    fn -= MAGIC;
+    double r = fma(fn, -6.93147180369123816490e-01, t);
+    r = fma(fn, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821614599e-10; // 1/13!
+    p = fma(p, r, 2.0876756987868098979e-09);
+    p = fma(p, r, 2.5052108385441718775e-08);
+    p = fma(p, r, 2.7557319223985890653e-07);
+    p = fma(p, r, 2.7557319223985890653e-06);
+    p = fma(p, r, 2.4801587301587301587e-05);
+    p = fma(p, r, 1.9841269841269841270e-04);
+    p = fma(p, r, 1.3888888888888888889e-03);
+    p = fma(p, r, 8.3333333333333333333e-03);
+    p = fma(p, r, 4.1666666666666666667e-02);
+    p = fma(p, r, 1.6666666666666666667e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int hi = __double2hiint(p) + (n << 20);
+    const double e = __hiloint2double(hi, __double2loint(p));
+    return t < -708.0 ? 0.0 : e;
+}
+
+// Normalised kernel value (sigma_f^2 = 1) from the (scaled) squared distance, kernel id as a template parameter.
+template <int KID>
+__device__ __forceinline__ double lb_unit_kernel_from_z(double z, const KernParams& kp)
+{
+    if (KID == LB_K_SE_ARD) return lb_exp_nonpos(-0.5 * z);
+    if (KID == LB_K_MATERN52) {
+        const double d = (z > 0.0) ? z * lb_rsqrt_nr(z) : 0.0;
+        const double term1 = kp.c1 * d;
+        return (1 + term1 + kp.c2 * (d * d)) * lb_exp_nonpos(-term1);
+    }
+    if (KID == LB_K_MATERN32) {
+        const double d = (z > 0.0) ? z * lb_rsqrt_nr(z) : 0.0;
+        const double term = kp.c1 * d;
+        return (1 + term) * lb_exp_nonpos(-term);
+    }
+    return lb_exp_nonpos(-0.5 * (z * kp.c1));
+}
+
 // ---------------------------------------------------------------------------
 // PTX helpers
 // ---------------------------------------------------------------------------

@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cmath>
+#include <type_traits>
 #include <cstdlib>
 
 namespace tf32q {
@@ -509,6 +510,21 @@ int lb_launch_tf32_gemm_norm_cluster(cudaStream_t st, const void* dA, int64_t ld
                    : launch_cluster<4, false>(st, mapA, mapB, M, N, K, tri, dNorm2, dErr, grid);
 }
 
+__global__ void debug_exp_kernel(const double* in, double* out, long long n)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = lb_exp_nonpos(in[i]);
+}
+
+// test hook: out[i] = lb_exp_nonpos(in[i]) (device pointers)
+extern "C" int lb_debug_exp(const double* dIn, double* dOut, long long n)
+{
+    debug_exp_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dIn, dOut, n);
+    LB_CUDA(cudaGetLastError());
+    LB_CUDA(cudaDeviceSynchronize());
+    return LB_OK;
+}
+
 extern "C" int lb_debug_tf32_gemm_cluster(const void* dA, const void* dB, long long M, long long N, long long K, int tri, float* dNorm2,
     int cl, int f16)
 {
@@ -549,12 +565,12 @@ constexpr int DCH = 16;
 // Kt[c * ldk + n] = (float) k(x_n, q_c)  for one tile of 128 candidates x 128 training points; zero for n >= N.
 // grid: (Np/128, Mc/128).  Same thread mapping as kbuild_kernel: the two consecutive "rows" of a thread are two
 // consecutive n, stored as one float2 (n is the contiguous, K-major index of the GEMM's A operand).
-// F16: values are scaled by kscale (= 1 / sigma_f^2, so they lie in (0, 1]) and stored as half.
-template <bool F16>
+// F16: the stored values are k / sigma_f^2 (in (0, 1]) as half.  EDGE: the tile crosses N or M (zero beyond).
+template <int KID, bool F16, bool EDGE>
 __global__ void __launch_bounds__(256, 2)
 kstar_t32_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, const double* __restrict__ Qs, int64_t Mp, int64_t M,
-    void* __restrict__ Kt_, int64_t ldk, KernParams kp, double kscale, const double* __restrict__ alpha, int P,
-    double* __restrict__ mu_part)
+    void* __restrict__ Kt_, int64_t ldk, KernParams kp, const double* __restrict__ alpha, int P,
+    double* __restrict__ mu_part, int64_t i_first, int64_t j_first)
 {
     __shared__ __align__(128) double sxi[DCH][LB_TILE];
     __shared__ __align__(128) double sxj[DCH][LB_TILE];
@@ -563,7 +579,8 @@ kstar_t32_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, const dou
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int li = lane & 7, lj = lane >> 3;
     const int D = kp.D;
-    const int64_t i0 = (int64_t)blockIdx.x * LB_TILE, j0 = (int64_t)blockIdx.y * LB_TILE; // i: training, j: candidates
+    const int64_t ti = i_first + blockIdx.x; // training tile index (also the slot of the mean partial)
+    const int64_t i0 = ti * LB_TILE, j0 = (j_first + blockIdx.y) * LB_TILE; // i: training, j: candidates
     const int r0 = warp * 16 + 2 * li;
     if (tid == 0) {
         lb_mbar_init(&bar, 1);
@@ -614,11 +631,14 @@ kstar_t32_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, const dou
             float v[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int64_t ii = gi + (e & 1), jj = gj + (e >> 1);
-                double k = lb_kernel_from_z(kp.id, z[c][e], kp);
-                if (ii >= N || jj >= M) k = 0.0;
+                double u = lb_unit_kernel_from_z<KID>(z[c][e], kp);
+                if (EDGE) {
+                    const int64_t ii = gi + (e & 1), jj = gj + (e >> 1);
+                    if (ii >= N || jj >= M) u = 0.0;
+                }
+                const double k = kp.sf2 * u;
                 z[c][e] = k;
-                v[e] = (float)(k * kscale);
+                v[e] = (float)(F16 ? u : k);
             }
             if (F16) {
                 __half* Kt = reinterpret_cast<__half*>(Kt_);
@@ -653,7 +673,7 @@ kstar_t32_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, const dou
                 double s = spm[0][tid];
 #pragma unroll
                 for (int w = 1; w < 8; ++w) s += spm[w][tid];
-                mu_part[((int64_t)p * gridDim.x + blockIdx.x) * Mp + j0 + h * 64 + tid] = s;
+                mu_part[((int64_t)p * (Np / LB_TILE) + ti) * Mp + j0 + h * 64 + tid] = s;
             }
             __syncthreads();
         }
@@ -790,11 +810,33 @@ int lb_launch_query_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const doub
     const bool f16 = (h->precision == 2);
     const int64_t Np = h->Np;
     const double kscale = f16 ? 1.0 / h->kp.sf2 : 1.0;
-    dim3 g1((unsigned)(Np / LB_TILE), (unsigned)(Mcp / LB_TILE));
     {
         LbProfScope ps(h, st, LB_PC_KSTAR);
-        if (f16) kstar_t32_kernel<true><<<g1, 256, 0, st>>>(h->dXs, Np, h->N, dQs, Mcp, Mc, dKt, Np, h->kp, kscale, h->dAlpha, h->P, dMuPart);
-        else kstar_t32_kernel<false><<<g1, 256, 0, st>>>(h->dXs, Np, h->N, dQs, Mcp, Mc, dKt, Np, h->kp, kscale, h->dAlpha, h->P, dMuPart);
+        // interior tiles without bounds checks; the last tile row / column (when N or Mc is not a multiple of 128) with
+        const int64_t nti = Np / LB_TILE, ntj = Mcp / LB_TILE;
+        const int64_t fi = h->N / LB_TILE, fj = Mc / LB_TILE; // number of full tiles
+        auto go = [&](auto kid, auto f16c, auto edgec, int64_t ia, int64_t ib, int64_t ja, int64_t jb) {
+            if (ib <= ia || jb <= ja) return;
+            dim3 g((unsigned)(ib - ia), (unsigned)(jb - ja));
+            kstar_t32_kernel<decltype(kid)::value, decltype(f16c)::value, decltype(edgec)::value><<<g, 256, 0, st>>>(h->dXs, Np, h->N, dQs, Mcp, Mc,
+                dKt, Np, h->kp, h->dAlpha, h->P, dMuPart, ia, ja);
+            if (launches) ++*launches;
+        };
+        auto go_prec = [&](auto kid) {
+            auto run = [&](auto f16c) {
+                go(kid, f16c, std::false_type{}, 0, fi, 0, fj);
+                go(kid, f16c, std::true_type{}, fi, nti, 0, ntj);
+                go(kid, f16c, std::true_type{}, 0, fi, fj, ntj);
+            };
+            if (f16) run(std::true_type{});
+            else run(std::false_type{});
+        };
+        switch (h->kp.id) {
+        case LB_K_SE_ARD: go_prec(std::integral_constant<int, LB_K_SE_ARD>{}); break;
+        case LB_K_MATERN52: go_prec(std::integral_constant<int, LB_K_MATERN52>{}); break;
+        case LB_K_MATERN32: go_prec(std::integral_constant<int, LB_K_MATERN32>{}); break;
+        default: go_prec(std::integral_constant<int, LB_K_EXP>{}); break;
+        }
     }
     {
         LbProfScope ps(h, st, LB_PC_QREDUCE);
@@ -813,7 +855,7 @@ int lb_launch_query_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const doub
     // D was computed from (K* kscale) and (L^-1 scale): |V|^2 = norm / (kscale scale)^2
     const double unscale = 1.0 / ((kscale * h->linv32_scale) * (kscale * h->linv32_scale));
     sigma2_t32_kernel<<<(unsigned)((Mc + 255) / 256), 256, 0, st>>>(dNorm2, cl, Mcp, Mc, h->kp.sf2, h->kp.noise, unscale, dS2);
-    if (launches) *launches += 4;
+    if (launches) *launches += 3;
     LB_CUDA(cudaGetLastError());
     return LB_OK;
 }

@@ -32,3 +32,26 @@ def test_tf32_query_close_to_fp64(kname, N, D, M, prec):
     # the tf32 winner must be (nearly) as good under the fp64 model
     assert v64[i32] >= best64 - 5e-3 * max(1.0, abs(best64))
     assert np.abs(v64 - v32).max() <= 2e-2
+
+
+@pytest.mark.gpu
+def test_device_exp_matches_libm():
+    """lb_exp_nonpos (branch-free exp of the reduced-precision K* build) against numpy: <= 4e-16 relative on [-708, 0],
+    exactly 0 below."""
+    import ctypes as C
+    import torch
+    from limbo_b200 import _lib
+    lib = _lib.load()
+    lib.lb_debug_exp.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
+    rng = np.random.default_rng(5)
+    t = np.concatenate([-rng.uniform(0, 40, 200000), -rng.uniform(0, 708, 200000), -np.logspace(-300, 2.8, 2000),
+                        np.array([0.0, -0.0, -708.0, -708.0001, -745.0, -1e4, -np.log(2) * 0.5, -np.log(2) * 1.5])])
+    din = torch.from_numpy(t).cuda()
+    dout = torch.empty_like(din)
+    assert lib.lb_debug_exp(din.data_ptr(), dout.data_ptr(), t.size) == 0
+    got = dout.cpu().numpy()
+    ref = np.exp(t)
+    inside = t >= -708.0
+    rel = np.abs(got[inside] - ref[inside]) / ref[inside]
+    assert rel.max() <= 4e-16, rel.max()
+    assert np.all(got[~inside] == 0.0)
