@@ -130,6 +130,15 @@ int lb_kernel_grad_log_lik(lb_gp* h, int optimize_noise, double* grad);
 /* GP::compute_inv_kernel (gp.hpp:254-264) */
 int lb_compute_inv_kernel(lb_gp* h);
 
+/* GP::compute_log_loo_cv (gp.hpp:339-351): leave-one-out log predictive probability from diag(K^-1) and alpha */
+int lb_log_loo_cv(lb_gp* h, double* out);
+/* GP::compute_kernel_grad_log_loo_cv (gp.hpp:353-399), the gradient KernelLooOpt (model/gp/kernel_loo_opt.hpp:57-97)
+ * climbs; grad has n_hparams (+1 when optimize_noise) entries. */
+int lb_kernel_grad_log_loo_cv(lb_gp* h, int optimize_noise, double* grad);
+/* obs_mean^T K^-1 of GP::compute_mean_grad_log_lik (gp.hpp:313-330): out = K^-1 * obs_mean, N x P column-major; the
+ * caller contracts it with its mean functor's gradient (mean/mean.hpp:72-76), which is host code. */
+int lb_kinv_obs_mean(lb_gp* h, double* out_colmajor);
+
 /* accessors matrixL(), alpha(), ... (gp.hpp:411-436): dst is column-major,
  * N x N (K, L, KINV) or N x P (ALPHA). */
 int lb_get(lb_gp* h, int what, double* dst_colmajor);

@@ -227,35 +227,37 @@ namespace limbo_b200 {
                 for (int i = 0; i < nh; ++i) grad(i) = g[(size_t)i];
                 return grad;
             }
-            Eigen::VectorXd compute_mean_grad_log_lik() // gp.hpp:314-330 (host: mean gradients are host functors)
+            Eigen::VectorXd compute_mean_grad_log_lik() // gp.hpp:313-330; obs_mean^T K^-1 on the device, functor gradient on the host
             {
                 const long n = (long)_samples.size();
-                const Eigen::MatrixXd& Kinv = inv_kernel();
+                std::vector<double> w((size_t)n * _dim_out);
+                lb_check(lb_kinv_obs_mean(_h, w.data()), "lb_kinv_obs_mean");
+                _inv_kernel_updated = true;
                 Eigen::VectorXd grad = Eigen::VectorXd::Zero(_mean_function.h_params_size());
-                for (int i_obs = 0; i_obs < _dim_out; ++i_obs)
-                    for (long n_obs = 0; n_obs < n; n_obs++) {
-                        double w = 0;
-                        for (long r = 0; r < n; ++r) w += _obs_mean(r, i_obs) * Kinv(r, n_obs);
-                        Eigen::MatrixXd mg = _mean_function.grad(_samples[n_obs], *this);
-                        for (long q = 0; q < (long)grad.size(); ++q) grad(q) += w * mg(i_obs, q);
-                    }
+                for (long n_obs = 0; n_obs < n; n_obs++) {
+                    Eigen::MatrixXd mg = _mean_function.grad(_samples[n_obs], *this);
+                    for (int i_obs = 0; i_obs < _dim_out; ++i_obs)
+                        for (long q = 0; q < (long)grad.size(); ++q) grad(q) += w[(size_t)i_obs * n + n_obs] * mg(i_obs, q);
+                }
                 return grad;
             }
             double get_log_lik() const { return _log_lik; }
             void set_log_lik(double v) { _log_lik = v; }
-            double compute_log_loo_cv() // gp.hpp:339-351, from the device K^-1 and alpha
+            double compute_log_loo_cv() // gp.hpp:339-351
             {
-                const Eigen::MatrixXd& Kinv = inv_kernel();
-                const Eigen::MatrixXd& a = alpha();
-                const long n = (long)_samples.size();
-                double tot = 0;
-                for (int p = 0; p < _dim_out; ++p)
-                    for (long i = 0; i < n; ++i) {
-                        double inv_diag = 1.0 / Kinv(i, i);
-                        tot += -0.5 * a(i, p) * a(i, p) * inv_diag - 0.5 * std::log(inv_diag) - 0.5 * std::log(2 * M_PI);
-                    }
-                _log_loo_cv = tot;
-                return tot;
+                lb_check(lb_log_loo_cv(_h, &_log_loo_cv), "lb_log_loo_cv");
+                _inv_kernel_updated = true;
+                return _log_loo_cv;
+            }
+            Eigen::VectorXd compute_kernel_grad_log_loo_cv() // gp.hpp:353-399
+            {
+                const int nh = (int)_kernel_function.h_params_size();
+                std::vector<double> g((size_t)nh);
+                lb_check(lb_kernel_grad_log_loo_cv(_h, Params::kernel::optimize_noise() ? 1 : 0, g.data()), "lb_kernel_grad_log_loo_cv");
+                _inv_kernel_updated = true;
+                Eigen::VectorXd grad(nh);
+                for (int i = 0; i < nh; ++i) grad(i) = g[(size_t)i];
+                return grad;
             }
             double get_log_loo_cv() const { return _log_loo_cv; }
             void set_log_loo_cv(double v) { _log_loo_cv = v; }

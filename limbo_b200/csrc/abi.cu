@@ -15,6 +15,9 @@ int lb_launch_potf2_block(lb_gp* h, int k, int do_factor);
 int lb_debug_potf2_clocks(lb_gp* h, int k, long long* out_host, int n);
 int lb_launch_linv(lb_gp* h);
 int lb_launch_symmetrize(lb_gp* h, double* dA);
+int lb_launch_loo_value(lb_gp* h, double* dOut);
+int lb_launch_loo_grad(lb_gp* h, int optimize_noise, double* dGrad);
+int lb_launch_kinv_obs(lb_gp* h, double* dOut);
 int lb_query_fused_supported(const lb_gp* h);
 size_t lb_query_fused_scratch_doubles(const lb_gp* h, int grid);
 int lb_launch_query_fused(const lb_gp* h, cudaStream_t st, int64_t M, const double* dQs, int64_t Mp, double* dVscratch,
@@ -222,7 +225,8 @@ void free_ws(QueryWs& w)
 void free_model(lb_gp* h)
 {
     cudaFree(h->dX); cudaFree(h->dXs); cudaFree(h->dY); cudaFree(h->dL); cudaFree(h->dInvD); cudaFree(h->dAlpha);
-    cudaFree(h->dLinv); cudaFree(h->dKinv); cudaFree(h->dFlags); cudaFree(h->dLinv32);
+    cudaFree(h->dLinv); cudaFree(h->dKinv); cudaFree(h->dFlags); cudaFree(h->dLinv32); cudaFree(h->dWork);
+    h->dWork = nullptr; h->work_np = 0;
     h->dLinv32 = nullptr; h->linv32_valid = false; h->linv32_rows = 0;
     h->dX = h->dXs = h->dY = h->dL = h->dInvD = h->dAlpha = h->dLinv = h->dKinv = nullptr;
     h->dFlags = nullptr;
@@ -777,6 +781,48 @@ int lb_kernel_grad_log_lik(lb_gp* hh, int optimize_noise, double* grad)
     return LB_OK;
 }
 
+int lb_log_loo_cv(lb_gp* hh, double* out)
+{
+    if (!hh || !out) return LB_ERR_ARG;
+    if (!hh->fitted) return LB_ERR_STATE;
+    lb_gp_full* h = full(hh);
+    int rc = lb_launch_loo_value(h, h->ex.dMisc + 4);
+    if (rc) return rc;
+    LB_CUDA(cudaMemcpyAsync(out, h->ex.dMisc + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    LB_CUDA(cudaStreamSynchronize(h->stream));
+    return LB_OK;
+}
+
+int lb_kernel_grad_log_loo_cv(lb_gp* hh, int optimize_noise, double* grad)
+{
+    if (!hh || !grad) return LB_ERR_ARG;
+    if (!hh->fitted) return LB_ERR_STATE;
+    lb_gp_full* h = full(hh);
+    const int nh = h->n_hparams + (optimize_noise ? 1 : 0);
+    if (nh > 128) return LB_ERR_ARG;
+    int rc = lb_launch_loo_grad(h, optimize_noise, h->ex.dMisc + 8);
+    if (rc) return rc;
+    LB_CUDA(cudaMemcpyAsync(grad, h->ex.dMisc + 8, sizeof(double) * nh, cudaMemcpyDeviceToHost, h->stream));
+    LB_CUDA(cudaStreamSynchronize(h->stream));
+    return LB_OK;
+}
+
+int lb_kinv_obs_mean(lb_gp* h, double* out)
+{
+    if (!h || !out) return LB_ERR_ARG;
+    if (!h->fitted) return LB_ERR_STATE;
+    double* dOut = nullptr;
+    LB_CUDA(cudaMalloc(&dOut, sizeof(double) * h->N * h->P));
+    int rc = lb_launch_kinv_obs(h, dOut);
+    if (!rc) {
+        if (cudaMemcpyAsync(out, dOut, sizeof(double) * h->N * h->P, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess
+            || cudaStreamSynchronize(h->stream) != cudaSuccess)
+            rc = LB_ERR_CUDA;
+    }
+    cudaFree(dOut);
+    return rc;
+}
+
 int lb_get(lb_gp* h, int what, double* dst)
 {
     if (!h || !dst) return LB_ERR_ARG;
@@ -808,7 +854,10 @@ int lb_get(lb_gp* h, int what, double* dst)
     else if (what == LB_GET_KINV) {
         if (!h->fitted) return LB_ERR_STATE;
         if (!h->kinv_valid && (rc = lb_launch_kinv(h))) return rc;
-        if ((rc = lb_launch_symmetrize(h, h->dKinv))) return rc;
+        if (!h->kinv_sym) {
+            if ((rc = lb_launch_symmetrize(h, h->dKinv))) return rc;
+            h->kinv_sym = true;
+        }
         src = h->dKinv;
     }
     else

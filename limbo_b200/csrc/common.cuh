@@ -289,6 +289,8 @@ struct lb_gp {
     bool fitted = false;
     bool linv_valid = false;
     bool kinv_valid = false;
+    bool kinv_sym = false;   // upper triangle of dKinv mirrored (needed by the LOO products and lb_get)
+    double* dWork = nullptr; int64_t work_np = 0; // Np x Np workspace (dK/dtheta of the LOO gradient)
     bool force_unfused = false; // tests: use the multi-launch query path
 
     // counters for bench.py ("gpu_launches")

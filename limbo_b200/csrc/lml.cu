@@ -419,6 +419,7 @@ int lb_launch_kinv(lb_gp* h)
     h->launches++;
     LB_CUDA(cudaGetLastError());
     h->kinv_valid = true;
+    h->kinv_sym = false;
     return LB_OK;
 }
 

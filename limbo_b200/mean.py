@@ -85,3 +85,57 @@ class Data(BaseMean):
 
     def is_constant(self) -> bool:
         return True
+
+
+class FunctionARD(BaseMean):
+    """mean/function_ard.hpp:58-128: affine transform (dim_out x (dim_out + 1) matrix, tunable) of an inner mean."""
+
+    def __init__(self, params=None, dim_out: int = 1, inner=None):
+        super().__init__(params, dim_out)
+        self._mean_function = inner if inner is not None else NullFunction(params, dim_out)
+        self._tr = np.zeros((dim_out, dim_out + 1))
+        h = np.zeros(dim_out * (dim_out + 1) + self._mean_function.h_params_size())
+        for i in range(dim_out):
+            h[i * (dim_out + 2)] = 1.0
+        if self._mean_function.h_params_size() > 0:
+            h[-self._mean_function.h_params_size():] = self._mean_function.h_params()
+        self.set_h_params(h)
+
+    def h_params_size(self) -> int:
+        return self._tr.size + self._mean_function.h_params_size()
+
+    def h_params(self) -> np.ndarray:
+        return np.concatenate([self._h_params, self._mean_function.h_params()])
+
+    def set_h_params(self, p) -> None:
+        p = np.asarray(p, dtype=np.float64)
+        self._h_params = p[: self._tr.size].copy()
+        self._tr = self._h_params.reshape(self._tr.shape).copy()  # _tr(r, c) = p[r * cols + c]
+        if self._mean_function.h_params_size() > 0:
+            self._mean_function.set_h_params(p[-self._mean_function.h_params_size():])
+
+    def grad(self, x, gp) -> np.ndarray:
+        rows, cols = self._tr.shape
+        grad = np.zeros((rows, self.h_params_size()))
+        m = np.asarray(self._mean_function(x, gp), dtype=np.float64)
+        for i in range(rows):
+            grad[i, i * cols:i * cols + cols - 1] = m
+            grad[i, (i + 1) * cols - 1] = 1.0
+        ni = self._mean_function.h_params_size()
+        if ni > 0:
+            m_grad = np.zeros((rows + 1, ni))
+            m_grad[:rows] = self._mean_function.grad(x, gp)
+            grad[:, self.h_params_size() - ni:] = self._tr @ m_grad
+        return grad
+
+    def __call__(self, v, gp) -> np.ndarray:
+        m = np.asarray(self._mean_function(v, gp), dtype=np.float64)
+        return self._tr @ np.concatenate([m, [1.0]])
+
+
+def function_ard(inner_cls):
+    """Factory usable as the ``mean=`` policy of model.GP: FunctionARD<Params, inner_cls> (mean/function_ard.hpp:58)."""
+    def make(params=None, dim_out: int = 1):
+        return FunctionARD(params, dim_out, inner_cls(params, dim_out))
+    make.__name__ = f"FunctionARD_{inner_cls.__name__}"
+    return make

@@ -279,17 +279,40 @@ class GP:
         self._inv_kernel_updated = True
         return g
 
-    # ---- gp.hpp:314-330 (host: needs K^-1 columns; mean gradients are host functors) ----
+    # ---- gp.hpp:313-330: obs_mean^T K^-1 on the device (lb_kinv_obs_mean); the mean functor's gradient is host code ----
     def compute_mean_grad_log_lik(self) -> np.ndarray:
-        if not self._inv_kernel_updated:
-            self.compute_inv_kernel()
-        Kinv = self._get(_lib.GET_KINV, (self.nb_samples(), self.nb_samples()))
+        n = self.nb_samples()
+        w = np.empty((n, self._dim_out), order="F")
+        _lib.check(self._lib.lb_kinv_obs_mean(self._h, _ptr(w)), "lb_kinv_obs_mean")
+        self._inv_kernel_updated = True
         grad = np.zeros(self._mean_function.h_params_size())
-        for i_obs in range(self._dim_out):
-            w = self._obs_mean[:, i_obs] @ Kinv
-            for n_obs in range(self.nb_samples()):
-                grad += w[n_obs] * self._mean_function.grad(self._samples[n_obs], self)[i_obs]
+        for n_obs in range(n):
+            mg = np.asarray(self._mean_function.grad(self._samples[n_obs], self), dtype=np.float64)
+            for i_obs in range(self._dim_out):
+                grad += w[n_obs, i_obs] * mg[i_obs]
         return grad
+
+    # ---- gp.hpp:339-351 ----
+    def compute_log_loo_cv(self) -> float:
+        out = C.c_double()
+        _lib.check(self._lib.lb_log_loo_cv(self._h, C.addressof(out)), "lb_log_loo_cv")
+        self._inv_kernel_updated = True
+        self._log_loo_cv = out.value
+        return self._log_loo_cv
+
+    # ---- gp.hpp:353-399 ----
+    def compute_kernel_grad_log_loo_cv(self) -> np.ndarray:
+        k = self._kernel_function
+        g = np.empty(k.h_params_size())
+        _lib.check(self._lib.lb_kernel_grad_log_loo_cv(self._h, int(k.optimize_noise()), _ptr(g)), "lb_kernel_grad_log_loo_cv")
+        self._inv_kernel_updated = True
+        return g
+
+    def get_log_loo_cv(self) -> float:
+        return self._log_loo_cv
+
+    def set_log_loo_cv(self, v: float) -> None:
+        self._log_loo_cv = v
 
     def get_log_lik(self) -> float:
         return self._log_lik

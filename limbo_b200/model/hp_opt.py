@@ -52,3 +52,96 @@ class _KernelLFOptimization:
         if not compute_grad:
             return _opt.no_grad(lik)
         return lik, gp.compute_kernel_grad_log_lik()
+
+
+class KernelLooOpt(HPOpt):
+    """model/gp/kernel_loo_opt.hpp:57-97: maximise the leave-one-out log predictive probability over the kernel
+    h-params (lb_log_loo_cv / lb_kernel_grad_log_loo_cv)."""
+
+    def __call__(self, gp) -> None:
+        self._called = True
+        optimization = _KernelLooOptimization(gp)
+        params = self._optimizer(optimization, gp.kernel_function().h_params(), False)
+        gp.kernel_function().set_h_params(params)
+        gp.recompute(False)
+        gp.compute_log_loo_cv()
+
+
+class _KernelLooOptimization:
+    def __init__(self, gp):
+        self._original_gp = gp
+        self._work = None
+
+    def __call__(self, params, compute_grad: bool):
+        if self._work is None:  # kernel_loo_opt.hpp:79 copies the GP per evaluation; one workspace copy is equivalent
+            self._work = self._original_gp.copy()
+        gp = self._work
+        gp.kernel_function().set_h_params(np.asarray(params, dtype=np.float64))
+        gp.recompute(False)
+        loo = gp.compute_log_loo_cv()
+        if not compute_grad:
+            return _opt.no_grad(loo)
+        return loo, gp.compute_kernel_grad_log_loo_cv()
+
+
+class KernelMeanLFOpt(HPOpt):
+    """model/gp/kernel_mean_lf_opt.hpp:57-122: likelihood over [kernel h-params, mean h-params] jointly."""
+
+    def __call__(self, gp) -> None:
+        self._called = True
+        optimization = _KernelMeanLFOptimization(gp)
+        nk = gp.kernel_function().h_params_size()
+        init = np.concatenate([gp.kernel_function().h_params(), gp.mean_function().h_params()])
+        params = self._optimizer(optimization, init, False)
+        gp.kernel_function().set_h_params(params[:nk])
+        gp.mean_function().set_h_params(params[nk:])
+        gp.recompute(True)
+        gp.compute_log_lik()
+
+
+class _KernelMeanLFOptimization:
+    def __init__(self, gp):
+        self._original_gp = gp
+        self._work = None
+
+    def __call__(self, params, compute_grad: bool):
+        if self._work is None:
+            self._work = self._original_gp.copy()
+        gp = self._work
+        params = np.asarray(params, dtype=np.float64)
+        nk = gp.kernel_function().h_params_size()
+        gp.kernel_function().set_h_params(params[:nk])
+        gp.mean_function().set_h_params(params[nk:])
+        gp.recompute(True)
+        lik = gp.compute_log_lik()
+        if not compute_grad:
+            return _opt.no_grad(lik)
+        return lik, np.concatenate([gp.compute_kernel_grad_log_lik(), gp.compute_mean_grad_log_lik()])
+
+
+class MeanLFOpt(HPOpt):
+    """model/gp/mean_lf_opt.hpp:57-118: likelihood over the mean h-params only; the factor is kept
+    (recompute(true, false) = lb_refit_alpha)."""
+
+    def __call__(self, gp) -> None:
+        self._called = True
+        optimization = _MeanLFOptimization(gp)
+        params = self._optimizer(optimization, gp.mean_function().h_params(), False)
+        gp.mean_function().set_h_params(params)
+        gp.recompute(True, False)
+        gp.compute_log_lik()
+
+
+class _MeanLFOptimization:
+    def __init__(self, gp):
+        self._work = gp.copy()  # mean_lf_opt.hpp:96-99: own copy with K^-1 precomputed
+        self._work.compute_inv_kernel()
+
+    def __call__(self, params, compute_grad: bool):
+        gp = self._work
+        gp.mean_function().set_h_params(np.asarray(params, dtype=np.float64))
+        gp.recompute(True, False)
+        lik = gp.compute_log_lik()
+        if not compute_grad:
+            return _opt.no_grad(lik)
+        return lik, gp.compute_mean_grad_log_lik()

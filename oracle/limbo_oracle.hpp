@@ -444,6 +444,57 @@ struct GP {
             }
         return tot;
     }
+
+    // gp.hpp:353-399 compute_kernel_grad_log_loo_cv: for every h-param j, Zeta_j = K^-1 dK/dtheta_j and
+    // grads(j,p) = sum_i (alpha_ip (Zeta_j alpha)_ip - 0.5 (1 + alpha_ip^2 / Kinv_ii) (Zeta_j K^-1)_ii) / Kinv_ii
+    void kernel_grad_log_loo_cv(T* grad, bool optimize_noise)
+    {
+        if (!inv_updated) compute_inv_kernel();
+        const int np = kern.n_params();
+        const int nh = np + (optimize_noise ? 1 : 0);
+        std::vector<T> dk((size_t)N * N * nh), g(nh);
+        for (long i = 0; i < N; ++i)
+            for (long j = 0; j <= i; ++j) { // gp.hpp:367-376: lower part from the functor, mirrored
+                kern.gradient(&X[i * D], &X[j * D], g.data());
+                if (optimize_noise) g[np] = (i == j) ? T(2) * kern.noise : T(0);
+                for (int q = 0; q < nh; ++q) dk[(size_t)q * N * N + i + j * N] = dk[(size_t)q * N * N + j + i * N] = g[q];
+            }
+        std::vector<T> Z((size_t)N * N);
+        for (int q = 0; q < nh; ++q) {
+            const T* dK = &dk[(size_t)q * N * N];
+            for (long i = 0; i < N; ++i)
+                for (long l = 0; l < N; ++l) {
+                    T s = 0;
+                    for (long k = 0; k < N; ++k) s += Kinv[i + k * N] * dK[k + l * N];
+                    Z[i + l * N] = s;
+                }
+            T tot = 0;
+            for (int p = 0; p < P; ++p)
+                for (long i = 0; i < N; ++i) {
+                    T za = 0, zk = 0;
+                    for (long l = 0; l < N; ++l) {
+                        za += Z[i + l * N] * alpha[l + (size_t)p * N];
+                        zk += Z[i + l * N] * Kinv[l + i * N];
+                    }
+                    const T inv_diag = T(1) / Kinv[i + i * N];
+                    const T a = alpha[i + (size_t)p * N];
+                    tot += (a * za - T(0.5) * (T(1) + a * a * inv_diag) * zk) * inv_diag;
+                }
+            grad[q] = tot;
+        }
+    }
+
+    // the data-dependent factor of gp.hpp:325-327 (compute_mean_grad_log_lik): w(n, p) = obs_mean.col(p)^T * Kinv.col(n)
+    void kinv_obs(T* out)
+    {
+        if (!inv_updated) compute_inv_kernel();
+        for (int p = 0; p < P; ++p)
+            for (long n = 0; n < N; ++n) {
+                T s = 0;
+                for (long r = 0; r < N; ++r) s += obs_mean[r + (size_t)p * N] * Kinv[r + n * N];
+                out[n + (size_t)p * N] = s;
+            }
+    }
 };
 
 // ---------------------------------------------------------------------------

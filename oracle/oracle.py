@@ -36,7 +36,8 @@ def load() -> C.CDLL:
             "lbo_set_data": ([vp, lg, i, i, vp, vp], None), "lbo_set_kernel": ([vp, i, vp, i, d], None),
             "lbo_fit": ([vp], lg), "lbo_refit_alpha": ([vp, vp], None), "lbo_append": ([vp, vp, vp], None),
             "lbo_query": ([vp, lg, vp, vp, vp, i], None), "lbo_log_lik": ([vp], d), "lbo_grad": ([vp, vp, i], None),
-            "lbo_loo_cv": ([vp], d), "lbo_get": ([vp, i, vp], None), "lbo_n": ([vp], lg),
+            "lbo_loo_cv": ([vp], d), "lbo_loo_grad": ([vp, vp, i], None), "lbo_kinv_obs": ([vp, vp], None),
+            "lbo_get": ([vp, i, vp], None), "lbo_n": ([vp], lg),
             "lbo_kernel_eval": ([i, i, vp, d, vp, vp, i], d), "lbo_kernel_grad": ([i, i, vp, vp, vp, vp], None),
             "lbo_ucb": ([lg, vp, vp, d, vp], None), "lbo_ei": ([lg, vp, vp, d, d, vp], None),
             "lbo_gp_ucb_beta": ([i, i, d], d),
@@ -116,6 +117,18 @@ class OracleGP:
 
     def loo_cv(self) -> float:
         return float(self.lib.lbo_loo_cv(self.h))
+
+    def loo_grad(self, optimize_noise: bool = False):
+        nh = self.hp.size + (1 if optimize_noise else 0)
+        g = np.empty(nh)
+        self.lib.lbo_loo_grad(self.h, _p(g), int(optimize_noise))
+        return g
+
+    def kinv_obs(self):
+        n = int(self.lib.lbo_n(self.h))
+        out = np.empty((n, self.P), order="F")
+        self.lib.lbo_kinv_obs(self.h, _p(out))
+        return out
 
     def get(self, what: int):
         n = int(self.lib.lbo_n(self.h))

@@ -19,6 +19,8 @@ struct IGP {
     virtual double log_lik() const = 0;
     virtual void grad(double* g, int optimize_noise) = 0;
     virtual double loo_cv() = 0;
+    virtual void loo_grad(double* g, int optimize_noise) = 0;
+    virtual void kinv_obs(double* out) = 0;
     virtual void get(int what, double* dst) = 0;
     virtual long n() const = 0;
     virtual IGP* clone() const = 0;
@@ -78,6 +80,19 @@ struct GPImpl : IGP {
         for (int i = 0; i < nh; ++i) g[i] = (double)gg[i];
     }
     double loo_cv() override { return (double)gp.log_loo_cv(); }
+    void loo_grad(double* g, int on) override
+    {
+        int nh = gp.kern.n_params() + (on ? 1 : 0);
+        std::vector<T> gg(nh);
+        gp.kernel_grad_log_loo_cv(gg.data(), on != 0);
+        for (int i = 0; i < nh; ++i) g[i] = (double)gg[i];
+    }
+    void kinv_obs(double* out) override
+    {
+        std::vector<T> w((size_t)gp.N * gp.P);
+        gp.kinv_obs(w.data());
+        for (size_t i = 0; i < w.size(); ++i) out[i] = (double)w[i];
+    }
     void get(int what, double* dst) override
     {
         const std::vector<T>* src = nullptr;
@@ -117,6 +132,8 @@ void lbo_query(void* h, long M, const double* Xq, double* mu, double* s2, int nt
 double lbo_log_lik(void* h) { return ((IGP*)h)->log_lik(); }
 void lbo_grad(void* h, double* g, int optimize_noise) { ((IGP*)h)->grad(g, optimize_noise); }
 double lbo_loo_cv(void* h) { return ((IGP*)h)->loo_cv(); }
+void lbo_loo_grad(void* h, double* g, int optimize_noise) { ((IGP*)h)->loo_grad(g, optimize_noise); }
+void lbo_kinv_obs(void* h, double* out) { ((IGP*)h)->kinv_obs(out); }
 void lbo_get(void* h, int what, double* dst) { ((IGP*)h)->get(what, dst); }
 long lbo_n(void* h) { return ((IGP*)h)->n(); }
 

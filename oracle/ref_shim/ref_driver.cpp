@@ -14,7 +14,9 @@
 #include <limbo/kernel/matern_five_halves.hpp>
 #include <limbo/kernel/matern_three_halves.hpp>
 #include <limbo/kernel/squared_exp_ard.hpp>
+#include <limbo/mean/constant.hpp>
 #include <limbo/mean/data.hpp>
+#include <limbo/mean/function_ard.hpp>
 #include <limbo/model/gp.hpp>
 #include <limbo/model/gp/kernel_lf_opt.hpp>
 #include <limbo/opt/rprop.hpp>
@@ -38,6 +40,9 @@ struct Params {
     };
     struct acqui_ucb : public defaults::acqui_ucb {};
     struct acqui_ei : public defaults::acqui_ei {};
+    struct mean_constant {
+        BO_PARAM(double, constant, 0.25);
+    };
 };
 BO_DECLARE_DYN_PARAM(double, Params::kernel, noise);
 BO_DECLARE_DYN_PARAM(int, Params::opt_rprop, iterations);
@@ -130,9 +135,96 @@ int run(long N, int D, int Pout, const double* X, const double* Y, double noise,
     return 0;
 }
 
+// LOO-CV objective and its gradient (gp.hpp:339-399), kernel gradient of the likelihood for comparison
+template <typename P, typename Kernel>
+int run_loo(long N, int D, int Pout, const double* X, const double* Y, double noise, const double* hp, int nh, double* loo, double* loo_grad)
+{
+    P::kernel::set_noise(noise);
+    using GP_t = model::GP<P, Kernel, mean::Data<P>, model::gp::KernelLFOpt<P, opt::Rprop<P>>>;
+    auto samples = rows_of(X, N, D);
+    auto obs = rows_of(Y, N, Pout);
+    GP_t gp(D, Pout);
+    if (hp) {
+        Eigen::VectorXd h((Eigen::Index)nh);
+        for (int i = 0; i < nh; ++i) h(i) = hp[i];
+        gp.kernel_function().set_h_params(h);
+    }
+    gp.compute(samples, obs);
+    *loo = gp.compute_log_loo_cv();
+    if (loo_grad) {
+        Eigen::VectorXd g = gp.compute_kernel_grad_log_loo_cv();
+        for (Eigen::Index i = 0; i < g.size(); ++i) loo_grad[i] = g(i);
+    }
+    return 0;
+}
+
+// mean-parameter gradient of the likelihood (gp.hpp:313-330) with mean::FunctionARD<mean::Constant> (tunable affine map of
+// a tunable constant): h-params = [tr (P x (P+1), row-major), constant]
+template <typename P, typename Kernel>
+int run_mean_grad(long N, int D, int Pout, const double* X, const double* Y, double noise, const double* hp, int nh, const double* mean_hp,
+    int n_mean_hp, double* loglik, double* mean_grad, double* mu_at_x0)
+{
+    P::kernel::set_noise(noise);
+    using Mean_t = mean::FunctionARD<P, mean::Constant<P>>;
+    using GP_t = model::GP<P, Kernel, Mean_t, model::gp::KernelLFOpt<P, opt::Rprop<P>>>;
+    auto samples = rows_of(X, N, D);
+    auto obs = rows_of(Y, N, Pout);
+    GP_t gp(D, Pout);
+    if (hp) {
+        Eigen::VectorXd h((Eigen::Index)nh);
+        for (int i = 0; i < nh; ++i) h(i) = hp[i];
+        gp.kernel_function().set_h_params(h);
+    }
+    if ((int)gp.mean_function().h_params_size() != n_mean_hp) return 3;
+    Eigen::VectorXd mh((Eigen::Index)n_mean_hp);
+    for (int i = 0; i < n_mean_hp; ++i) mh(i) = mean_hp[i];
+    gp.mean_function().set_h_params(mh);
+    gp.compute(samples, obs);
+    *loglik = gp.compute_log_lik();
+    Eigen::VectorXd g = gp.compute_mean_grad_log_lik();
+    for (Eigen::Index i = 0; i < g.size(); ++i) mean_grad[i] = g(i);
+    Eigen::VectorXd m = gp.mu(samples[0]);
+    for (int p = 0; p < Pout; ++p) mu_at_x0[p] = m(p);
+    return 0;
+}
+
 } // namespace
 
 extern "C" {
+
+int ref_gp_mean_grad(int kernel_id, long N, int D, int P, const double* X, const double* Y, double noise, const double* hp, int nh,
+    const double* mean_hp, int n_mean_hp, double* loglik, double* mean_grad, double* mu_at_x0)
+{
+#define RUN(KK) return run_mean_grad<Params, kernel::KK<Params>>(N, D, P, X, Y, noise, hp, nh, mean_hp, n_mean_hp, loglik, mean_grad, mu_at_x0)
+    switch (kernel_id) {
+    case 0: RUN(SquaredExpARD);
+    case 1: RUN(MaternFiveHalves);
+    case 2: RUN(MaternThreeHalves);
+    default: RUN(Exp);
+    }
+#undef RUN
+}
+
+int ref_gp_loo(int kernel_id, int optimize_noise, long N, int D, int P, const double* X, const double* Y, double noise,
+    const double* hp, int nh, double* loo, double* loo_grad)
+{
+#define RUN(PP, KK) return run_loo<PP, kernel::KK<PP>>(N, D, P, X, Y, noise, hp, nh, loo, loo_grad)
+    if (optimize_noise) {
+        switch (kernel_id) {
+        case 0: RUN(ParamsNoise, SquaredExpARD);
+        case 1: RUN(ParamsNoise, MaternFiveHalves);
+        case 2: RUN(ParamsNoise, MaternThreeHalves);
+        default: RUN(ParamsNoise, Exp);
+        }
+    }
+    switch (kernel_id) {
+    case 0: RUN(Params, SquaredExpARD);
+    case 1: RUN(Params, MaternFiveHalves);
+    case 2: RUN(Params, MaternThreeHalves);
+    default: RUN(Params, Exp);
+    }
+#undef RUN
+}
 
 // kernel_id: 0 SquaredExpARD, 1 MaternFiveHalves, 2 MaternThreeHalves, 3 Exp.  Y is N x P row-major observations
 // (NOT mean-subtracted: mean::Data is the reference's own).  optimize_noise selects ParamsNoise (grad gets +1 entry).

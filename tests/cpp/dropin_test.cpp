@@ -1,5 +1,5 @@
 // tests/cpp/dropin_test.cpp — the drop-in claim, compiled: the reference's OWN policy templates
-// (acqui::UCB, acqui::EI, model::gp::KernelLFOpt<Params, opt::Rprop>, kernel::*, mean::Data from
+// (acqui::UCB, acqui::EI, model::gp::KernelLFOpt / KernelLooOpt / KernelMeanLFOpt<Params, opt::Rprop>, kernel::*, mean::* from
 // /root/reference/src/limbo) instantiated over limbo_b200::model::GP and, side by side, over the
 // reference's limbo::model::GP; results must agree to the fp64 bar.  Needs a GPU to run.
 // (Eigen is the stand-in from oracle/ref_shim because the image has no Eigen.)
@@ -8,9 +8,13 @@
 #include <limbo/acqui/ucb.hpp>
 #include <limbo/kernel/matern_five_halves.hpp>
 #include <limbo/kernel/squared_exp_ard.hpp>
+#include <limbo/mean/constant.hpp>
 #include <limbo/mean/data.hpp>
+#include <limbo/mean/function_ard.hpp>
 #include <limbo/model/gp.hpp>
 #include <limbo/model/gp/kernel_lf_opt.hpp>
+#include <limbo/model/gp/kernel_loo_opt.hpp>
+#include <limbo/model/gp/kernel_mean_lf_opt.hpp>
 #include <limbo/opt/rprop.hpp>
 
 #include <limbo_b200/model/gp.hpp>
@@ -27,6 +31,9 @@ struct Params {
     };
     struct acqui_ucb : public defaults::acqui_ucb {};
     struct acqui_ei : public defaults::acqui_ei {};
+    struct mean_constant {
+        BO_PARAM(double, constant, 0.5);
+    };
 };
 
 struct FirstElem {
@@ -99,9 +106,47 @@ int run_case(const char* name, int N, int D)
     return ok ? 0 : 1;
 }
 
+// The reference's KernelLooOpt<Rprop> (model/gp/kernel_loo_opt.hpp) and KernelMeanLFOpt<Rprop> with
+// mean::FunctionARD<mean::Constant> (kernel_mean_lf_opt.hpp, mean/function_ard.hpp) driving both model types.
+template <typename HP, typename Mean>
+int run_hp_case(const char* name, int N, int D, bool loo)
+{
+    using Kernel = kernel::SquaredExpARD<Params>;
+    using RefGP = model::GP<Params, Kernel, Mean, HP>;
+    using NewGP = limbo_b200::model::GP<Params, Kernel, Mean, HP>;
+    unsigned long long seed = 77;
+    std::vector<Eigen::VectorXd> X, Y;
+    for (int i = 0; i < N; ++i) {
+        Eigen::VectorXd x((Eigen::Index)D), y((Eigen::Index)1);
+        double s = 1.5;
+        for (int d = 0; d < D; ++d) { x(d) = u01(seed); s += std::cos(3.0 * x(d)); }
+        y(0) = s;
+        X.push_back(x);
+        Y.push_back(y);
+    }
+    RefGP ref(D, 1);
+    NewGP gpu(D, 1);
+    ref.compute(X, Y);
+    gpu.compute(X, Y);
+    double dg;
+    if (loo) dg = (ref.compute_kernel_grad_log_loo_cv() - gpu.compute_kernel_grad_log_loo_cv()).norm() / ref.compute_kernel_grad_log_loo_cv().norm();
+    else dg = (ref.compute_mean_grad_log_lik() - gpu.compute_mean_grad_log_lik()).norm() / ref.compute_mean_grad_log_lik().norm();
+    ref.optimize_hyperparams();
+    gpu.optimize_hyperparams();
+    double dh = (ref.kernel_function().h_params() - gpu.kernel_function().h_params()).norm();
+    double dm = (ref.mean_function().h_params() - gpu.mean_function().h_params()).norm();
+    double v1 = loo ? ref.get_log_loo_cv() : ref.get_log_lik(), v2 = loo ? gpu.get_log_loo_cv() : gpu.get_log_lik();
+    double dv = std::fabs(v1 - v2) / std::fabs(v1);
+    std::printf("%s N=%d D=%d dgrad_rel=%.3e |dh|=%.3e |dmean_h|=%.3e dobjective_rel=%.3e\n", name, N, D, dg, dh, dm, dv);
+    return (dg < 1e-9 && dh < 1e-7 && dm < 1e-7 && dv < 1e-9) ? 0 : 1;
+}
+
 int main()
 {
     int bad = 0;
+    bad += run_hp_case<model::gp::KernelLooOpt<Params, opt::Rprop<Params>>, mean::Data<Params>>("KernelLooOpt", 70, 2, true);
+    bad += run_hp_case<model::gp::KernelMeanLFOpt<Params, opt::Rprop<Params>>, mean::FunctionARD<Params, mean::Constant<Params>>>(
+        "KernelMeanLFOpt", 70, 2, false);
     bad += run_case<kernel::SquaredExpARD<Params>>("SquaredExpARD", 60, 3);
     bad += run_case<kernel::MaternFiveHalves<Params>>("MaternFiveHalves", 150, 2);
     std::printf(bad ? "DROPIN FAIL\n" : "DROPIN OK\n");

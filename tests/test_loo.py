@@ -1,0 +1,226 @@
+"""the leave-one-out objective (GP::compute_log_loo_cv / compute_kernel_grad_log_loo_cv,
+gp.hpp:339-399; KernelLooOpt, model/gp/kernel_loo_opt.hpp) and the mean-parameter gradient (compute_mean_grad_log_lik,
+gp.hpp:313-330; MeanLFOpt / KernelMeanLFOpt; mean::FunctionARD / mean::Constant).
+Fixtures in tests/golden/loo/ come from the reference's own code (tests/golden/make_golden_loo.py).
+Tolerances: LOO value and log-lik 1e-10 relative; gradients 1e-9 relative to the largest entry (they are sums of N
+terms that scale with cond(K); the reference's own test for them is a finite-difference check, test_gp.cpp:273-380)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LOO = sorted(glob.glob(os.path.join(HERE, "golden", "loo", "loo_*.npz")))
+MG = sorted(glob.glob(os.path.join(HERE, "golden", "loo", "meangrad_*.npz")))
+KNAMES = {0: "SquaredExpARD", 1: "MaternFiveHalves", 2: "MaternThreeHalves", 3: "Exp"}
+
+
+def _ids(paths):
+    return [os.path.basename(p)[:-4] for p in paths]
+
+
+def _split_hp(g):
+    hp = np.asarray(g["hp_in"], dtype=float)
+    on = bool(g["optimize_noise"]) if "optimize_noise" in g else False
+    noise = float(np.exp(2 * hp[-1])) if on else float(g["noise"])  # kernel.hpp:116-123
+    return (hp[:-1] if on else hp), hp, noise, on
+
+
+def test_fixtures_present():
+    assert len(LOO) >= 7 and len(MG) >= 2
+
+
+@pytest.mark.parametrize("path", LOO, ids=_ids(LOO))
+def test_oracle_loo_reproduces_reference(path, oracle_mod):
+    g = np.load(path)
+    hp_own, _, noise, on = _split_hp(g)
+    og = oracle_mod.OracleGP()
+    og.set_data(g["X"], g["Y"] - g["Y"].mean(axis=0))
+    og.set_kernel(int(g["kernel_id"]), hp_own, noise)
+    assert og.fit() == -1  # Eigen convention of the restatement: -1 = success
+    assert abs(og.loo_cv() - float(g["loo"])) <= 1e-12 * abs(float(g["loo"]))
+    assert np.abs(og.loo_grad(on) - g["loo_grad"]).max() <= 1e-11 * np.abs(g["loo_grad"]).max()
+
+
+def _mean_policy(params_cls):
+    from limbo_b200 import mean
+    return mean.function_ard(mean.Constant)
+
+
+class _MeanParams:
+    class mean_constant:
+        constant = 0.25  # the value compiled into oracle/ref_shim/ref_driver.cpp (overwritten by the fixture's h-params)
+
+
+@pytest.mark.parametrize("path", MG, ids=_ids(MG))
+def test_oracle_mean_grad_reproduces_reference(path, oracle_mod):
+    """Python mirrors of mean::FunctionARD / mean::Constant + the oracle's K^-1 obs_mean against the reference."""
+    from limbo_b200 import mean
+    g = np.load(path)
+    X, Y, P = g["X"], g["Y"], int(g["P"])
+    mf = mean.function_ard(mean.Constant)(_MeanParams, P)
+    assert mf.h_params_size() == g["mean_hp"].size
+    mf.set_h_params(g["mean_hp"])
+    assert np.array_equal(mf.h_params(), g["mean_hp"])
+    M = np.stack([mf(x, None) for x in X])
+    og = oracle_mod.OracleGP()
+    og.set_data(X, Y - M)
+    og.set_kernel(int(g["kernel_id"]), g["hp_in"], float(g["noise"]))
+    assert og.fit() == -1  # Eigen convention of the restatement: -1 = success
+    assert abs(og.log_lik() - float(g["loglik"])) <= 1e-12 * abs(float(g["loglik"]))
+    w = og.kinv_obs()
+    grad = np.zeros(mf.h_params_size())
+    for n in range(X.shape[0]):
+        mg = mf.grad(X[n], None)
+        for p in range(P):
+            grad += w[n, p] * mg[p]
+    assert np.abs(grad - g["mean_grad"]).max() <= 1e-11 * np.abs(g["mean_grad"]).max()
+    mu, _ = og.query(X[:1])
+    assert np.abs(mu[0] + mf(X[0], None) - g["mu_at_x0"]).max() <= 1e-11
+
+
+# ------------------------------------------------------------------ GPU ----
+def _gp_for(g, hp_own, noise, on, **kw):
+    from limbo_b200 import kernel, mean, model
+
+    class P_:
+        class kernel:
+            pass
+    P_.kernel.noise = noise
+    P_.kernel.optimize_noise = on
+    gp = model.GP(int(g["D"]), int(g["P"]), params=P_, kernel=getattr(kernel, KNAMES[int(g["kernel_id"])]), mean=mean.Data, **kw)
+    return gp
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", LOO, ids=_ids(LOO))
+def test_cuda_loo_reproduces_reference(path):
+    g = np.load(path)
+    hp_own, hp_full, noise, on = _split_hp(g)
+    gp = _gp_for(g, hp_own, noise, on)
+    gp.kernel_function().set_h_params(hp_full)
+    gp.compute(list(g["X"]), list(g["Y"]))
+    v = gp.compute_log_loo_cv()
+    assert abs(v - float(g["loo"])) <= 1e-10 * abs(float(g["loo"]))
+    assert gp.get_log_loo_cv() == v
+    gr = gp.compute_kernel_grad_log_loo_cv()
+    assert gr.shape == g["loo_grad"].shape
+    assert np.abs(gr - g["loo_grad"]).max() <= 1e-9 * np.abs(g["loo_grad"]).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", MG, ids=_ids(MG))
+def test_cuda_mean_grad_reproduces_reference(path):
+    from limbo_b200 import kernel, mean, model
+    g = np.load(path)
+    X, Y, P = g["X"], g["Y"], int(g["P"])
+
+    class P_(_MeanParams):
+        class kernel:
+            noise = float(g["noise"])
+            optimize_noise = False
+    gp = model.GP(int(g["D"]), P, params=P_, kernel=getattr(kernel, KNAMES[int(g["kernel_id"])]), mean=mean.function_ard(mean.Constant))
+    gp.kernel_function().set_h_params(g["hp_in"])
+    gp.mean_function().set_h_params(g["mean_hp"])
+    gp.compute(list(X), list(Y))
+    assert abs(gp.compute_log_lik() - float(g["loglik"])) <= 1e-10 * abs(float(g["loglik"]))
+    gr = gp.compute_mean_grad_log_lik()
+    assert np.abs(gr - g["mean_grad"]).max() <= 1e-9 * np.abs(g["mean_grad"]).max()
+    assert np.abs(gp.mu(X[0]) - g["mu_at_x0"]).max() <= 1e-10
+
+
+@pytest.mark.gpu
+def test_cuda_loo_many_tiles_against_oracle(oracle_mod):
+    """N = 700 (6 tiles of 128, ragged last tile), P = 2, SE-ARD with noise optimised: every tile pair of Z = K^-1 dK."""
+    from limbo_b200 import kernel, mean, model, synth
+    N, D = 700, 3
+    X = synth.points(99, N, D)
+    y = synth.targets(X)
+    Y = np.stack([y, 0.5 * y + np.sin(3 * X[:, 0])], axis=1)
+    hp = np.array([-0.9, -0.7, -0.8, 0.1, np.log(np.sqrt(0.03))])
+
+    class P_:
+        class kernel:
+            noise = 0.03
+            optimize_noise = True
+    gp = model.GP(D, 2, params=P_, kernel=kernel.SquaredExpARD, mean=mean.Data)
+    gp.kernel_function().set_h_params(hp)
+    gp.compute(list(X), list(Y))
+    og = oracle_mod.OracleGP()
+    og.set_data(X, Y - Y.mean(axis=0))
+    og.set_kernel(0, hp[:-1], 0.03)
+    assert og.fit() == -1  # Eigen convention of the restatement: -1 = success
+    ref_v, ref_g = og.loo_cv(), og.loo_grad(True)
+    assert abs(gp.compute_log_loo_cv() - ref_v) <= 1e-10 * abs(ref_v)
+    gr = gp.compute_kernel_grad_log_loo_cv()
+    assert np.abs(gr - ref_g).max() <= 1e-9 * np.abs(ref_g).max()
+    # K^-1 obs_mean (mean-gradient factor) on the same model
+    import ctypes as C
+    from limbo_b200 import _lib
+    w = np.empty((N, 2), order="F")
+    _lib.check(_lib.load().lb_kinv_obs_mean(gp._h, w.ctypes.data), "lb_kinv_obs_mean")
+    wr = og.kinv_obs()
+    assert np.abs(w - wr).max() <= 1e-9 * np.abs(wr).max()
+
+
+@pytest.mark.gpu
+def test_kernel_loo_opt_follows_the_oracle_trajectory(oracle_mod):
+    """KernelLooOpt (kernel_loo_opt.hpp:57-97) with 6 Rprop iterations: same host optimiser, device objective vs the oracle's."""
+    from limbo_b200 import kernel, mean, model, opt, synth
+    N, D = 90, 2
+    X = synth.points(5, N, D)
+    y = synth.targets(X)
+
+    class P_:
+        class opt_rprop:
+            iterations = 6
+            eps_stop = 0.0
+    gp = model.GP(D, 1, params=P_, kernel=kernel.SquaredExpARD, mean=mean.Data, hp_opt=model.KernelLooOpt(P_))
+    gp.compute(list(X), list(y[:, None]))
+    gp.optimize_hyperparams()
+    og = oracle_mod.OracleGP()
+    og.set_data(X, (y - y.mean())[:, None])
+
+    def objective(p, compute_grad):
+        og.set_kernel(0, np.asarray(p, dtype=float), 0.01)
+        assert og.fit() == -1  # Eigen convention of the restatement: -1 = success
+        return (og.loo_cv(), og.loo_grad(False)) if compute_grad else opt.no_grad(og.loo_cv())
+    best = opt.Rprop(P_)(objective, np.zeros(D + 1), False)
+    assert np.abs(gp.kernel_function().h_params() - best).max() <= 1e-8
+    objective(best, False)
+    assert abs(gp.get_log_loo_cv() - og.loo_cv()) <= 1e-9 * abs(og.loo_cv())
+
+
+@pytest.mark.gpu
+def test_mean_lf_opt_and_kernel_mean_lf_opt_improve_the_likelihood():
+    """MeanLFOpt (mean_lf_opt.hpp) keeps the factor and tunes the mean; KernelMeanLFOpt (kernel_mean_lf_opt.hpp) tunes both.
+    As in test_gp.cpp:131-380 the analytic gradients are checked against central finite differences of the objective."""
+    from limbo_b200 import kernel, mean, model, synth
+    from limbo_b200.model import hp_opt
+    N, D = 120, 2
+    X = synth.points(11, N, D)
+    y = synth.targets(X) + 2.0
+
+    class P_(_MeanParams):
+        class opt_rprop:
+            iterations = 25
+            eps_stop = 0.0
+    for policy in (model.MeanLFOpt, model.KernelMeanLFOpt):
+        gp = model.GP(D, 1, params=P_, kernel=kernel.SquaredExpARD, mean=mean.function_ard(mean.Constant), hp_opt=policy(P_))
+        gp.compute(list(X), list(y[:, None]))
+        before = gp.compute_log_lik()
+        # finite differences of the functor the policy optimises
+        fun = hp_opt._MeanLFOptimization(gp) if policy is model.MeanLFOpt else hp_opt._KernelMeanLFOptimization(gp)
+        x0 = gp.mean_function().h_params() if policy is model.MeanLFOpt else np.concatenate(
+            [gp.kernel_function().h_params(), gp.mean_function().h_params()])
+        _, ga = fun(x0, True)
+        for i in range(x0.size):
+            e = np.zeros_like(x0)
+            e[i] = 1e-5
+            fd = (fun(x0 + e, False)[0] - fun(x0 - e, False)[0]) / 2e-5
+            assert abs(fd - ga[i]) <= 1e-5 * max(1.0, abs(ga[i])), (policy.__name__, i, fd, ga[i])
+        gp.optimize_hyperparams()
+        after = gp.get_log_lik()
+        assert after > before + 1e-3, (policy.__name__, before, after)  # Rprop keeps the best-seen point (rprop.hpp:104-110)
+        assert abs(gp.compute_log_lik() - after) <= 1e-9 * abs(after)
