@@ -44,7 +44,8 @@ typedef struct lb_gp lb_gp;
 #define LB_ERR_TIMEOUT (-6)
 
 /* kernel ids (src/limbo/kernel/*.hpp) */
-#define LB_KERNEL_SQUARED_EXP_ARD 0 /* kernel/squared_exp_ard.hpp (k = 0)   h-params [log l_1..log l_D, log sigma_f] */
+#define LB_KERNEL_SQUARED_EXP_ARD 0 /* kernel/squared_exp_ard.hpp   h-params [log l_1..log l_D, (A(:,0) .. A(:,k-1): D each, k <= 4), log sigma_f];
+                                       k = Params::kernel_squared_exp_ard::k() is inferred from n_hparams = D + D k + 1 */
 #define LB_KERNEL_MATERN_FIVE_HALVES 1 /* kernel/matern_five_halves.hpp      h-params [log l, log sigma_f] */
 #define LB_KERNEL_MATERN_THREE_HALVES 2 /* kernel/matern_three_halves.hpp */
 #define LB_KERNEL_EXP 3 /* kernel/exp.hpp */

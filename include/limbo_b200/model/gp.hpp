@@ -46,7 +46,8 @@ namespace limbo_b200 {
         template <typename K> struct kernel_traits; // no definition: unsupported kernels do not compile
         template <typename P> struct kernel_traits<limbo::kernel::SquaredExpARD<P>> {
             static constexpr int id = LB_KERNEL_SQUARED_EXP_ARD;
-            static void check() { assert(P::kernel_squared_exp_ard::k() == 0 && "SquaredExpARD with k > 0 is not supported by the B200 backend"); }
+            // k > 0 (Lambda columns, squared_exp_ard.hpp:109-126): the h-params carry the D x k matrix, lb_set_kernel reads k from their count
+            static void check() { assert(P::kernel_squared_exp_ard::k() >= 0 && P::kernel_squared_exp_ard::k() <= 4 && "SquaredExpARD: 0 <= k <= 4"); }
         };
         template <typename P> struct kernel_traits<limbo::kernel::MaternFiveHalves<P>> {
             static constexpr int id = LB_KERNEL_MATERN_FIVE_HALVES;

@@ -126,8 +126,9 @@ __global__ void pack_soa_kernel(const double* __restrict__ src, int64_t n, int D
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int d = blockIdx.y;
     if (i >= np) return;
-    double v = (i < n) ? src[i * D + d] : 0.0;
-    if (scaled && kp.id == LB_K_SE_ARD) v *= kp.inv_ell[d];
+    // D = row length of src; grid.y = D (raw copy) or kp.D (staged for the kernel: x/ell and the Lambda projections)
+    double v = 0.0;
+    if (i < n) v = scaled ? lb_staged_coord(kp, d, [&](int r) { return src[i * D + r]; }) : src[i * D + d];
     dst[(int64_t)d * np + i] = v;
 }
 
@@ -237,7 +238,7 @@ int alloc_model(lb_gp* h, int64_t Np, int D, int P)
 {
     const int64_t T = Np / LB_TILE;
     LB_CUDA(cudaMalloc(&h->dX, sizeof(double) * D * Np));
-    LB_CUDA(cudaMalloc(&h->dXs, sizeof(double) * D * Np));
+    LB_CUDA(cudaMalloc(&h->dXs, sizeof(double) * (D + LB_MAX_LAMBDA) * Np));
     LB_CUDA(cudaMalloc(&h->dY, sizeof(double) * P * Np));
     LB_CUDA(cudaMalloc(&h->dAlpha, sizeof(double) * P * Np));
     LB_CUDA(cudaMalloc(&h->dL, sizeof(double) * Np * Np));
@@ -319,6 +320,7 @@ int lb_destroy(lb_gp* hh)
     free_ws(h->ex.ws);
     cudaFree(h->dInfo);
     cudaFree(h->dScratch);
+    cudaFree(h->dLambda);
     cudaFree(h->ex.dMisc);
     if (h->ex.own) cudaStreamDestroy(h->ex.own);
     if (h->side) cudaStreamDestroy(h->side);
@@ -358,8 +360,10 @@ static int set_data_common(lb_gp* h, int64_t N, int D, int P, const double* X, c
         int rc = alloc_model(h, Np, D, P);
         if (rc) return rc;
     }
+    if (D != h->D) h->kp.klam = 0; // the Lambda matrix belongs to the previous input dimension
     h->N = N; h->D = D; h->P = P;
-    h->kp.D = D;
+    h->kp.Draw = D;
+    h->kp.D = D + h->kp.klam;
     h->fitted = false; h->linv_valid = false; h->kinv_valid = false; h->linv32_valid = false;
     const double* dXr = X;
     const double* dYr = Y;
@@ -393,16 +397,33 @@ int lb_set_kernel(lb_gp* h, int kernel_id, const double* p, int n_hparams, doubl
     if (!h || !p) return LB_ERR_ARG;
     if (kernel_id < 0 || kernel_id > 3) return LB_ERR_UNSUPPORTED;
     if (h->D <= 0) return LB_ERR_STATE; // need the input dimension first (lb_set_data)
-    const int want = (kernel_id == LB_K_SE_ARD) ? h->D + 1 : 2;
-    if (n_hparams != want) return LB_ERR_ARG;
+    int klam = 0;
+    if (kernel_id == LB_K_SE_ARD) { // [log ell (D), A columns (D each, k of them), log sigma_f]  squared_exp_ard.hpp:91,96-105
+        const int rest = n_hparams - 1 - h->D;
+        if (rest < 0 || rest % h->D != 0) return LB_ERR_ARG;
+        klam = rest / h->D;
+        if (klam > LB_MAX_LAMBDA || h->D + klam > LB_MAX_D) return LB_ERR_UNSUPPORTED;
+    }
+    else if (n_hparams != 2)
+        return LB_ERR_ARG;
     KernParams& kp = h->kp;
     kp.id = kernel_id;
-    kp.D = h->D;
+    kp.Draw = h->D;
+    kp.klam = klam;
+    kp.D = h->D + klam;
+    kp.lambda = nullptr;
     kp.noise = noise;
-    if (kernel_id == LB_K_SE_ARD) { // squared_exp_ard.hpp:96-105
+    if (kernel_id == LB_K_SE_ARD) {
         for (int d = 0; d < h->D; ++d) kp.inv_ell[d] = 1.0 / std::exp(p[d]);
-        kp.sf2 = std::exp(2.0 * p[h->D]);
+        kp.sf2 = std::exp(2.0 * p[n_hparams - 1]);
         kp.l = 1.0;
+        if (klam > 0) { // _A(i, j) = p((j + 1) * D + i): already column-major
+            LB_CUDA(cudaSetDevice(h->device));
+            if (!h->dLambda) LB_CUDA(cudaMalloc(&h->dLambda, sizeof(double) * LB_MAX_D * LB_MAX_LAMBDA));
+            LB_CUDA(cudaMemcpyAsync(h->dLambda, p + h->D, sizeof(double) * h->D * klam, cudaMemcpyHostToDevice, h->stream));
+            LB_CUDA(cudaStreamSynchronize(h->stream));
+            kp.lambda = h->dLambda;
+        }
     }
     else { // matern_five_halves.hpp:97-102 and siblings
         kp.l = std::exp(p[0]);
@@ -524,7 +545,7 @@ int lb_append(lb_gp* h, const double* x, const double* Yall)
         double *nX, *nXs, *nY, *nA, *nL, *nI; int* nF;
         LB_CUDA(cudaStreamSynchronize(h->stream));
         LB_CUDA(cudaMalloc(&nX, sizeof(double) * D * newNp));
-        LB_CUDA(cudaMalloc(&nXs, sizeof(double) * D * newNp));
+        LB_CUDA(cudaMalloc(&nXs, sizeof(double) * (D + LB_MAX_LAMBDA) * newNp));
         LB_CUDA(cudaMalloc(&nY, sizeof(double) * P * newNp));
         LB_CUDA(cudaMalloc(&nA, sizeof(double) * P * newNp));
         LB_CUDA(cudaMalloc(&nL, sizeof(double) * newNp * newNp));
@@ -586,7 +607,7 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
     std::lock_guard<std::mutex> lock(h->ex.qmutex);
     QueryWs& w = h->ex.ws;
     cudaStream_t st = h->stream;
-    const int D = h->D, P = h->P > 0 ? h->P : 1;
+    const int D = h->D, De = h->kp.D, P = h->P > 0 ? h->P : 1; // raw / staged input dimension
     const int64_t Mp = (M + LB_TILE - 1) / LB_TILE * LB_TILE;
     int rc;
     if ((rc = ensure(&w.dMu, &w.mu_bytes, sizeof(double) * M * P))) return rc;
@@ -610,7 +631,7 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
             if ((rc = lb_tf32_prepare(h))) return rc;
             const int64_t cap = std::max<int64_t>(LB_TILE, ((int64_t)4 << 30) / (4 * h->Np) / LB_TILE * LB_TILE);
             const int64_t Mc = std::min(Mp, cap);
-            if ((rc = ensure(&w.dQs, &w.qs_bytes, sizeof(double) * D * Mc))) return rc;
+            if ((rc = ensure(&w.dQs, &w.qs_bytes, sizeof(double) * De * Mc))) return rc;
             if ((rc = ensure(&w.dKt, &w.kt_bytes, sizeof(float) * (size_t)Mc * h->Np))) return rc;
             if ((rc = ensure(&w.dNorm2, &w.norm2_bytes, sizeof(float) * (size_t)Mc * 4))) return rc; // up to 4 cluster partials
             if ((rc = ensure(&w.dV, &w.v_bytes, sizeof(double) * (size_t)P * (h->Np / LB_TILE) * Mc))) return rc; // mean partials per training tile
@@ -619,7 +640,7 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
             for (int64_t m0 = 0; m0 < M; m0 += Mc) {
                 const int64_t mc = std::min(Mc, M - m0);
                 const int64_t mcp = (mc + LB_TILE - 1) / LB_TILE * LB_TILE;
-                dim3 g1((unsigned)((mcp + 255) / 256), (unsigned)D);
+                dim3 g1((unsigned)((mcp + 255) / 256), (unsigned)De);
                 pack_soa_kernel<<<g1, 256, 0, st>>>(dQraw + m0 * D, mc, D, w.dQs, mcp, h->kp, 1);
                 h->launches++;
                 if ((rc = lb_launch_query_tf32(h, st, mc, w.dQs, mcp, w.dKt, w.dNorm2, w.dErr, w.dV, w.dMu + m0 * P, w.dS2 + m0, &h->launches)))
@@ -638,9 +659,9 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
             LB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
             const int64_t ntiles = (M + 7) / 8;
             const int grid = (int)std::min<int64_t>(sms, ntiles);
-            if ((rc = ensure(&w.dQs, &w.qs_bytes, sizeof(double) * D * Mp))) return rc;
+            if ((rc = ensure(&w.dQs, &w.qs_bytes, sizeof(double) * De * Mp))) return rc;
             if ((rc = ensure(&w.dV, &w.v_bytes, sizeof(double) * lb_query_fused_scratch_doubles(h, grid)))) return rc;
-            dim3 g1((unsigned)((Mp + 255) / 256), (unsigned)D);
+            dim3 g1((unsigned)((Mp + 255) / 256), (unsigned)De);
             pack_soa_kernel<<<g1, 256, 0, st>>>(dQraw, M, D, w.dQs, Mp, h->kp, 1);
             h->launches++;
             if ((rc = lb_launch_query_fused(h, st, M, w.dQs, Mp, w.dV, grid, w.dMu, w.dS2, &h->launches))) return rc;
@@ -650,12 +671,12 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
         int64_t Mc = Mp;
         const int64_t maxcols = std::max<int64_t>(LB_TILE, ((int64_t)4 << 30) / (8 * h->Np) / LB_TILE * LB_TILE);
         if (Mc > maxcols) Mc = maxcols;
-        if ((rc = ensure(&w.dQs, &w.qs_bytes, sizeof(double) * D * Mc))) return rc;
+        if ((rc = ensure(&w.dQs, &w.qs_bytes, sizeof(double) * De * Mc))) return rc;
         if ((rc = ensure(&w.dV, &w.v_bytes, sizeof(double) * h->Np * Mc))) return rc;
         for (int64_t m0 = 0; m0 < M; m0 += Mc) {
             const int64_t mc = std::min(Mc, M - m0);
             const int64_t mcp = (mc + LB_TILE - 1) / LB_TILE * LB_TILE;
-            dim3 g1((unsigned)((mcp + 255) / 256), (unsigned)D);
+            dim3 g1((unsigned)((mcp + 255) / 256), (unsigned)De);
             pack_soa_kernel<<<g1, 256, 0, st>>>(dQraw + m0 * D, mc, D, w.dQs, mcp, h->kp, 1);
             h->launches++;
             if ((rc = lb_launch_query(h, st, mc, w.dQs, mcp, w.dV, w.dMu + m0 * P, w.dS2 + m0, &h->launches))) return rc;
@@ -879,11 +900,20 @@ int lb_clone(const lb_gp* src, lb_gp** out)
     cudaStream_t st = src->stream;
     h->kp = src->kp; h->kernel_set = src->kernel_set; h->n_hparams = src->n_hparams;
     h->N = src->N; h->D = src->D; h->P = src->P;
+    h->kp.lambda = nullptr;
+    if (src->kp.klam > 0) { // own copy of the Lambda matrix
+        if (cudaMalloc(&h->dLambda, sizeof(double) * LB_MAX_D * LB_MAX_LAMBDA) != cudaSuccess
+            || cudaMemcpyAsync(h->dLambda, src->dLambda, sizeof(double) * LB_MAX_D * LB_MAX_LAMBDA, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+            lb_destroy(h);
+            return LB_ERR_CUDA;
+        }
+        h->kp.lambda = h->dLambda;
+    }
     if (src->Np > 0) {
         if ((rc = alloc_model(h, src->Np, src->D, src->P))) { lb_destroy(h); return rc; }
         const int64_t Np = src->Np, T = Np / LB_TILE;
         cudaMemcpyAsync(h->dX, src->dX, sizeof(double) * src->D * Np, cudaMemcpyDeviceToDevice, st);
-        cudaMemcpyAsync(h->dXs, src->dXs, sizeof(double) * src->D * Np, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(h->dXs, src->dXs, sizeof(double) * src->kp.D * Np, cudaMemcpyDeviceToDevice, st);
         cudaMemcpyAsync(h->dY, src->dY, sizeof(double) * src->P * Np, cudaMemcpyDeviceToDevice, st);
         if (src->fitted) {
             cudaMemcpyAsync(h->dAlpha, src->dAlpha, sizeof(double) * src->P * Np, cudaMemcpyDeviceToDevice, st);

@@ -41,6 +41,7 @@ void lb_set_last_cuda_error(cudaError_t e, const char* file, int line);
 
 enum { LB_K_SE_ARD = 0, LB_K_MATERN52 = 1, LB_K_MATERN32 = 2, LB_K_EXP = 3 };
 #define LB_MAX_D 64
+#define LB_MAX_LAMBDA 4 // columns of the SE-ARD Lambda matrix (Params::kernel_squared_exp_ard::k)
 
 // Kernel parameters passed by value to device code.
 struct KernParams {
@@ -52,6 +53,12 @@ struct KernParams {
     double inv_ell[LB_MAX_D]; // SE-ARD: 1/exp(p_d)
     double c1;       // Matern: sqrt(5)/l resp. sqrt(3)/l ; Exp: 1/l^2   (host-precomputed, saves a divide per pair)
     double c2;       // Matern-5/2: 5/(3 l^2)
+    // SE-ARD with k > 0 (squared_exp_ard.hpp:109-126,142-146): z = d^T (A A^T + diag(ell^-2)) d = |W^T d|^2 with
+    // W = [diag(1/ell) | A].  The staged samples carry D = Draw + klam coordinates (x/ell, A^T x), so every kernel that
+    // consumes the staged tiles is unchanged; only the staging and the gradient wrt A know about A.
+    int Draw;        // input dimension of the caller's points
+    int klam;        // number of columns of A
+    const double* lambda; // device, Draw x klam column-major (nullptr when klam == 0)
 };
 
 // ---------------------------------------------------------------------------
@@ -167,6 +174,18 @@ __device__ __forceinline__ double lb_unit_kernel_from_z(double z, const KernPara
     return lb_exp_nonpos(-0.5 * (z * kp.c1));
 }
 
+// staged coordinate d (0 <= d < kp.D) of a raw point given by x(r), r < kp.Draw
+template <typename F>
+__device__ __forceinline__ double lb_staged_coord(const KernParams& kp, int d, F&& x)
+{
+    if (kp.id != LB_K_SE_ARD) return x(d);
+    if (d < kp.Draw) return x(d) * kp.inv_ell[d]; // squared_exp_ard.hpp:148: cwiseQuotient(_ell), applied once per point
+    double s = 0.0;
+    const double* a = kp.lambda + (int64_t)(d - kp.Draw) * kp.Draw;
+    for (int r = 0; r < kp.Draw; ++r) s = fma(a[r], x(r), s);
+    return s;
+}
+
 // ---------------------------------------------------------------------------
 // PTX helpers
 // ---------------------------------------------------------------------------
@@ -274,7 +293,8 @@ struct lb_gp {
     int n_hparams = 0;
 
     double* dX = nullptr;    // D x Np raw samples (SoA)
-    double* dXs = nullptr;   // D x Np samples scaled for the kernel (SE-ARD: /ell)
+    double* dXs = nullptr;   // (D + LB_MAX_LAMBDA) x Np samples staged for the kernel (SE-ARD: x/ell, then A^T x)
+    double* dLambda = nullptr; // D x LB_MAX_LAMBDA (SE-ARD A matrix)
     double* dY = nullptr;    // Np x P  obs_mean (col-major), zero padded
     double* dL = nullptr;    // Np x Np K then L (col-major)
     double* dInvD = nullptr; // T x 128 x 128

@@ -22,10 +22,9 @@ __global__ void scale_x_kernel(const double* __restrict__ X, double* __restrict_
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int d = blockIdx.y;
     if (i >= Np) return;
-    double v = X[d * Np + i];
     // squared_exp_ard.hpp:148: (x1 - x2).cwiseQuotient(_ell); we scale x once
-    // by 1/ell_d instead (<= 2 ulp difference on z).
-    Xs[d * Np + i] = (kp.id == LB_K_SE_ARD) ? v * kp.inv_ell[d] : v;
+    // by 1/ell_d instead (<= 2 ulp difference on z); Lambda columns: common.cuh lb_staged_coord
+    Xs[d * Np + i] = lb_staged_coord(kp, d, [&](int r) { return X[r * Np + i]; });
 }
 
 __device__ __forceinline__ void tile_from_index(int t, int& bi, int& bj)
@@ -140,7 +139,7 @@ kbuild_kernel(const double* __restrict__ Xs, double* __restrict__ K, int64_t N, 
 
 int lb_launch_scale_x(lb_gp* h)
 {
-    dim3 grid((unsigned)((h->Np + 255) / 256), (unsigned)h->D);
+    dim3 grid((unsigned)((h->Np + 255) / 256), (unsigned)h->kp.D);
     scale_x_kernel<<<grid, 256, 0, h->stream>>>(h->dX, h->dXs, h->Np, h->kp);
     h->launches++;
     LB_CUDA(cudaGetLastError());

@@ -11,6 +11,7 @@
 #include "gemm.cuh"
 
 int lb_launch_trsm_lower(const lb_gp* h, cudaStream_t st, double* dV, int64_t Mp, int i_begin, long long* launches);
+int lb_launch_grad_lambda(lb_gp* h, double* dGrad); // loo.cu
 
 namespace {
 
@@ -326,10 +327,12 @@ grad_kernel(const double* __restrict__ Xs, const double* __restrict__ Kinv, cons
         double a = 0, b = 0, c = 0;
         for (int w = 0; w < 8; ++w) { a += sred[w][0]; b += sred[w][1]; c += sred[w][2]; }
         double* out = part + (int64_t)blockIdx.x * nh;
-        if (ard) {
-            for (int d = 0; d < D; ++d) out[d] = stot[d];
-            out[D] = a;
-            if (optimize_noise) out[D + 1] = c;
+        if (ard) { // [ell (Draw), Lambda entries (filled by lb_launch_grad_lambda), sigma_f, (noise)]
+            const int nk = nh - (optimize_noise ? 1 : 0);
+            for (int d = 0; d < kp.Draw; ++d) out[d] = stot[d];
+            for (int d = kp.Draw; d < nk - 1; ++d) out[d] = 0.0;
+            out[nk - 1] = a;
+            if (optimize_noise) out[nk] = c;
         }
         else {
             out[0] = b;
@@ -445,5 +448,6 @@ int lb_launch_grad(lb_gp* h, int optimize_noise, double* dGrad)
     grad_reduce_kernel<<<nh, 256, 0, h->stream>>>(h->dScratch, ntiles, nh, dGrad);
     h->launches += 2;
     LB_CUDA(cudaGetLastError());
+    if (h->kp.id == LB_K_SE_ARD && h->kp.klam > 0) return lb_launch_grad_lambda(h, dGrad);
     return LB_OK;
 }

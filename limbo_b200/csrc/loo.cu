@@ -21,7 +21,8 @@ namespace {
 using Cfg = lbg::CfgWide;
 
 // dK[i + j*ld] = d k(x_i, x_j) / d theta_q for i, j < N, 0 in the padding.
-//   SE-ARD   (squared_exp_ard.hpp:127-135): q < D: k * ((x_q - y_q)/ell_q)^2 ; q == D: 2k
+//   SE-ARD   (squared_exp_ard.hpp:107-136): q < D: k * ((x_q - y_q)/ell_q)^2 ; Lambda entry A(i,j): -k (d^T A(:,j)) d_i ;
+//            last: 2k
 //   Matern52 (matern_five_halves.hpp:115-133), Matern32 (matern_three_halves.hpp:110-124), Exp (exp.hpp:101-110):
 //            q == 0: d/d log l ; q == 1: 2k
 //   q == n_hparams (optimize_noise): 2 * noise on the diagonal (kernel.hpp:90-93)
@@ -36,15 +37,22 @@ dk_build_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, KernParams
         if (q >= n_hparams)
             out = (i == j) ? 2.0 * kp.noise : 0.0;
         else {
-            double z = 0.0, qd2 = 0.0;
+            // SE-ARD parameter layout: [ell (Draw), A(:,0) .. A(:,klam-1) (Draw each), sigma_f]
+            const bool is_lam = (kp.id == LB_K_SE_ARD) && q >= kp.Draw && q < n_hparams - 1;
+            const int lam_j = is_lam ? (q - kp.Draw) / kp.Draw : 0, lam_i = is_lam ? (q - kp.Draw) % kp.Draw : 0;
+            double z = 0.0, qd2 = 0.0, proj = 0.0, raw = 0.0;
             for (int d = 0; d < kp.D; ++d) {
                 const double df = Xs[(int64_t)d * Np + i] - Xs[(int64_t)d * Np + j];
                 z = fma(df, df, z);
                 if (d == q) qd2 = df * df;
+                if (is_lam && d == kp.Draw + lam_j) proj = df;          // (x1 - x2)^T A(:,j)
+                if (is_lam && d == lam_i) raw = df / kp.inv_ell[lam_i];  // (x1 - x2)_i (the staged one is divided by ell_i)
             }
             if (kp.id == LB_K_SE_ARD) {
                 const double k = kp.sf2 * exp(-0.5 * z);
-                out = (q < kp.D) ? k * qd2 : 2.0 * k;
+                if (q < kp.Draw) out = k * qd2;             // squared_exp_ard.hpp:117 / :131
+                else if (is_lam) out = -proj * raw * k;     // squared_exp_ard.hpp:119-122
+                else out = 2.0 * k;
             }
             else if (kp.id == LB_K_MATERN52) {
                 const double d = sqrt(z), d_sq = d * d, l_sq = kp.l * kp.l;
@@ -204,6 +212,45 @@ kinv_obs_reduce_kernel(const double* __restrict__ part, int64_t ld, int64_t N, i
     }
 }
 
+// part[b] = sum over a fixed slice of the elements (i, j < N) of (sum_p alpha_ip alpha_jp - Kinv_ij) dK_ij
+constexpr int WDOT_BLOCKS = 1024;
+__global__ void __launch_bounds__(256)
+wdot_kernel(const double* __restrict__ Kinv, const double* __restrict__ dK, int64_t ld, int64_t N, const double* __restrict__ alpha, int P,
+    double* __restrict__ part)
+{
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int64_t j = blockIdx.x; j < N; j += WDOT_BLOCKS)
+        for (int64_t i = threadIdx.x; i < N; i += 256) {
+            double w = -Kinv[i + j * ld];
+            for (int p = 0; p < P; ++p) w = fma(alpha[i + (int64_t)p * ld], alpha[j + (int64_t)p * ld], w);
+            s = fma(w, dK[i + j * ld], s);
+        }
+    s = lb_warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        part[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(256)
+wdot_reduce_kernel(const double* __restrict__ part, double* __restrict__ out)
+{
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int b = threadIdx.x; b < WDOT_BLOCKS; b += 256) s += part[b];
+    s = lb_warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        *out = 0.5 * t;
+    }
+}
+
 int ensure_sym_kinv(lb_gp* h)
 {
     int rc;
@@ -250,6 +297,34 @@ int lb_launch_loo_grad(lb_gp* h, int optimize_noise, double* dGrad)
         dk_build_kernel<<<g1, 256, 0, h->stream>>>(h->dXs, Np, h->N, h->kp, q, h->n_hparams, h->dWork);
         loo_zeta_kernel<<<T * T, Cfg::THREADS, Cfg::PIPE_BYTES, h->stream>>>(h->dKinv, h->dWork, Np, h->dAlpha, h->P, T, part_zk, part_za);
         loo_grad_reduce_kernel<<<1, 1024, 0, h->stream>>>(h->dKinv, Np, h->N, h->dAlpha, h->P, T, part_zk, part_za, dGrad + q);
+        h->launches += 3;
+    }
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+// Likelihood gradient wrt the entries of the SE-ARD Lambda matrix (squared_exp_ard.hpp:119-122; gp.hpp:299-308):
+//   g_q = sum_{i >= j} w_ij dK_q,ij (1/2 on the diagonal) = 1/2 sum_{all i,j} (alpha alpha^T - K^-1)_ij dK_q,ij
+// one dK build + one weighted reduction per entry (k > 0 is a rarely used option; the ell / sigma_f / noise entries come
+// from the fused grad_kernel).
+int lb_launch_grad_lambda(lb_gp* h, double* dGrad)
+{
+    int rc = ensure_sym_kinv(h);
+    if (rc) return rc;
+    const int64_t Np = h->Np;
+    if (!h->dWork || h->work_np != Np) {
+        if (h->dWork) cudaFree(h->dWork);
+        h->dWork = nullptr;
+        LB_CUDA(cudaMalloc(&h->dWork, sizeof(double) * Np * Np));
+        h->work_np = Np;
+    }
+    if ((rc = lb_ensure_scratch(h, sizeof(double) * WDOT_BLOCKS))) return rc;
+    const int Dr = h->kp.Draw;
+    for (int q = Dr; q < Dr + Dr * h->kp.klam; ++q) {
+        dim3 g1((unsigned)((Np + 255) / 256), (unsigned)Np);
+        dk_build_kernel<<<g1, 256, 0, h->stream>>>(h->dXs, Np, h->N, h->kp, q, h->n_hparams, h->dWork);
+        wdot_kernel<<<WDOT_BLOCKS, 256, 0, h->stream>>>(h->dKinv, h->dWork, Np, h->N, h->dAlpha, h->P, h->dScratch);
+        wdot_reduce_kernel<<<1, 256, 0, h->stream>>>(h->dScratch, dGrad + q);
         h->launches += 3;
     }
     LB_CUDA(cudaGetLastError());

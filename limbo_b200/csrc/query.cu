@@ -693,7 +693,7 @@ bool g_attr = false;
 
 } // namespace slab
 
-int lb_query_fused_supported(const lb_gp* h) { return h->D <= slab::DMAXF && h->P <= slab::PMAXF; }
+int lb_query_fused_supported(const lb_gp* h) { return h->kp.D <= slab::DMAXF && h->P <= slab::PMAXF; }
 size_t lb_query_fused_scratch_doubles(const lb_gp* h, int grid) { return (size_t)grid * h->Np * slab::SLAB; }
 
 int lb_launch_query_fused(const lb_gp* h, cudaStream_t st, int64_t M, const double* dQs, int64_t Mp, double* dVscratch,

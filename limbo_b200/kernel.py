@@ -59,19 +59,22 @@ class BaseKernel:
 
 
 class SquaredExpARD(BaseKernel):
-    """kernel/squared_exp_ard.hpp:83-151 (k = 0 only; k > 0 raises)."""
+    """kernel/squared_exp_ard.hpp:83-151.  h-params (log space): [ell_1..ell_D, A(:,0), .., A(:,k-1), sigma_f]; with
+    k = Params.kernel_squared_exp_ard.k > 0 the squared distance is d^T (A A^T + diag(ell^-2)) d (:109-126, :142-146),
+    which the device evaluates on the staged coordinates (x / ell, A^T x)."""
     kernel_id = _lib.KERNEL_SQUARED_EXP_ARD
 
     def __init__(self, params=None, dim: int = 1):
         super().__init__(params, dim)
-        if int(get(params, "kernel_squared_exp_ard", "k")) != 0:
-            raise NotImplementedError("SquaredExpARD with k > 0 (Lambda columns) is not supported by the B200 backend")
-        p = np.zeros(dim + 1)
+        self._k = int(get(params, "kernel_squared_exp_ard", "k"))
+        if self._k < 0 or self._k > 4:
+            raise NotImplementedError("SquaredExpARD: the B200 backend supports 0 <= k <= 4 Lambda columns")
+        p = np.zeros(dim + dim * self._k + 1)  # squared_exp_ard.hpp:85-87
         p[-1] = math.log(math.sqrt(float(get(params, "kernel_squared_exp_ard", "sigma_sq"))))
         self.set_params(p)
 
     def params_size(self) -> int:
-        return self._dim + 1
+        return self._dim + self._dim * self._k + 1
 
     def ell(self) -> np.ndarray:
         return np.exp(self._h_params[: self._dim])

@@ -61,15 +61,20 @@ struct Kernel {
     T l = 1;            // isotropic kernels      matern_five_halves.hpp:97-102
     T sf2 = 1;          // exp(2 p_last)
     T noise = T(0.01);  // kernel/kernel.hpp:57,76-79
+    int klam = 0;       // Params::kernel_squared_exp_ard::k(): columns of the Lambda matrix _A (squared_exp_ard.hpp:83,91)
+    std::vector<T> A;   // D x klam column-major
 
-    int n_params() const { return id == K_SE_ARD ? D + 1 : 2; }
+    int n_params() const { return id == K_SE_ARD ? D + D * klam + 1 : 2; }
 
     void set_params(const double* p)
     {
-        if (id == K_SE_ARD) {
+        if (id == K_SE_ARD) { // squared_exp_ard.hpp:96-105
             ell.resize(D);
             for (int d = 0; d < D; ++d) ell[d] = t_exp(T(p[d]));
-            sf2 = t_exp(T(2.0) * T(p[D]));
+            A.resize((size_t)D * klam);
+            for (int j = 0; j < klam; ++j)
+                for (int i = 0; i < D; ++i) A[i + (size_t)j * D] = T(p[(j + 1) * D + i]);
+            sf2 = t_exp(T(2.0) * T(p[n_params() - 1]));
         }
         else {
             l = t_exp(T(p[0]));
@@ -81,7 +86,8 @@ struct Kernel {
     T pure(const T* x1, const T* x2) const
     {
         switch (id) {
-        case K_SE_ARD: { // squared_exp_ard.hpp:138-151 (k == 0 branch)
+        case K_SE_ARD: { // squared_exp_ard.hpp:138-151
+            if (klam > 0) return sf2 * t_exp(T(-0.5) * lambda_z(x1, x2));
             T z = 0;
             for (int d = 0; d < D; ++d) {
                 T q = (x1[d] - x2[d]) / ell[d];
@@ -115,6 +121,30 @@ struct Kernel {
         }
     }
 
+    // squared_exp_ard.hpp:112-114 / :142-146: K = A A^T, K.diagonal() += ell^-2, z = (d^T K) d
+    T lambda_z(const T* x1, const T* x2) const
+    {
+        std::vector<T> Km((size_t)D * D), t(D);
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j) {
+                T s = 0;
+                for (int c = 0; c < klam; ++c) s += A[i + (size_t)c * D] * A[j + (size_t)c * D];
+                Km[i + (size_t)j * D] = s;
+            }
+        for (int i = 0; i < D; ++i) {
+            T inv = T(1) / ell[i];
+            Km[i + (size_t)i * D] += inv * inv;
+        }
+        for (int j = 0; j < D; ++j) {
+            T s = 0;
+            for (int i = 0; i < D; ++i) s += (x1[i] - x2[i]) * Km[i + (size_t)j * D];
+            t[j] = s;
+        }
+        T z = 0;
+        for (int j = 0; j < D; ++j) z += t[j] * (x1[j] - x2[j]);
+        return z;
+    }
+
     // BaseKernel::operator()  kernel/kernel.hpp:81-84
     T operator()(const T* x1, const T* x2, long i = -1, long j = -2) const
     {
@@ -125,7 +155,21 @@ struct Kernel {
     void gradient(const T* x1, const T* x2, T* g) const
     {
         switch (id) {
-        case K_SE_ARD: { // squared_exp_ard.hpp:127-135
+        case K_SE_ARD: { // squared_exp_ard.hpp:107-136
+            if (klam > 0) {
+                T k = sf2 * t_exp(T(-0.5) * lambda_z(x1, x2));
+                for (int d = 0; d < D; ++d) {
+                    T q = (x1[d] - x2[d]) / ell[d];
+                    g[d] = q * q * k;
+                }
+                for (int j = 0; j < klam; ++j) { // :119-122  G = -((x1-x2)^T A.col(j)) * (x1-x2) * k
+                    T s = 0;
+                    for (int i = 0; i < D; ++i) s += (x1[i] - x2[i]) * A[i + (size_t)j * D];
+                    for (int i = 0; i < D; ++i) g[(j + 1) * D + i] = (-s) * (x1[i] - x2[i]) * k;
+                }
+                g[n_params() - 1] = T(2) * k;
+                return;
+            }
             T zs = 0;
             for (int d = 0; d < D; ++d) {
                 T q = (x1[d] - x2[d]) / ell[d];

@@ -39,7 +39,7 @@ struct GPImpl : IGP {
         gp.kern.id = id;
         gp.kern.D = gp.D;
         gp.kern.noise = T(noise);
-        (void)nh;
+        gp.kern.klam = (id == lbo::K_SE_ARD && gp.D > 0) ? (nh - 1 - gp.D) / gp.D : 0; // Params::kernel_squared_exp_ard::k()
         gp.kern.set_params(hp);
     }
     long fit() override { gp.compute_full_kernel(); return gp.chol_info; }

@@ -55,7 +55,7 @@ def run(kernel_id: int, X, Y, noise=0.01, hp=None, Xq=None, n0=0, rprop_iters=0,
     P = Y.shape[1]
     Xq = np.zeros((0, D)) if Xq is None else np.ascontiguousarray(Xq, dtype=np.float64)
     M = Xq.shape[0]
-    nh_own = D + 1 if kernel_id == 0 else 2
+    nh_own = D + 1 if kernel_id == 0 else (3 * D + 1 if kernel_id == 4 else 2)  # 4 = SE-ARD with k = 2 Lambda columns
     nh = nh_own + (1 if optimize_noise else 0)
     hpa = None if hp is None else np.ascontiguousarray(hp, dtype=np.float64)
     K = np.empty((N, N), order="F"); L = np.empty((N, N), order="F"); A = np.empty((N, P), order="F")
@@ -78,7 +78,7 @@ def loo(kernel_id: int, X, Y, noise=0.01, hp=None, optimize_noise=False, want_gr
     if Y.ndim == 1:
         Y = Y[:, None]
     N, D = X.shape
-    nh = (D + 1 if kernel_id == 0 else 2) + (1 if optimize_noise else 0)
+    nh = (D + 1 if kernel_id == 0 else (3 * D + 1 if kernel_id == 4 else 2)) + (1 if optimize_noise else 0)
     hpa = None if hp is None else np.ascontiguousarray(hp, dtype=np.float64)
     v = C.c_double()
     g = np.empty(nh)

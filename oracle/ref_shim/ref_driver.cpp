@@ -47,6 +47,14 @@ struct Params {
 BO_DECLARE_DYN_PARAM(double, Params::kernel, noise);
 BO_DECLARE_DYN_PARAM(int, Params::opt_rprop, iterations);
 
+// Params::kernel_squared_exp_ard::k() = 2: SE-ARD with two Lambda columns (squared_exp_ard.hpp:109-126,142-146)
+struct ParamsLambda : Params {
+    struct kernel_squared_exp_ard {
+        BO_PARAM(int, k, 2);
+        BO_PARAM(double, sigma_sq, 1);
+    };
+};
+
 struct ParamsNoise : Params {
     struct kernel {
         BO_DYN_PARAM(double, noise);
@@ -221,6 +229,7 @@ int ref_gp_loo(int kernel_id, int optimize_noise, long N, int D, int P, const do
     case 0: RUN(Params, SquaredExpARD);
     case 1: RUN(Params, MaternFiveHalves);
     case 2: RUN(Params, MaternThreeHalves);
+    case 4: RUN(ParamsLambda, SquaredExpARD); // k = 2
     default: RUN(Params, Exp);
     }
 #undef RUN
@@ -245,6 +254,7 @@ int ref_gp_run(int kernel_id, int optimize_noise, long N, int D, int P, const do
     case 0: RUN(Params, SquaredExpARD);
     case 1: RUN(Params, MaternFiveHalves);
     case 2: RUN(Params, MaternThreeHalves);
+    case 4: RUN(ParamsLambda, SquaredExpARD); // k = 2
     default: RUN(Params, Exp);
     }
 #undef RUN

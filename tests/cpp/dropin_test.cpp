@@ -50,7 +50,15 @@ static double u01(unsigned long long& s)
     return (double)(z >> 11) * (1.0 / 9007199254740992.0);
 }
 
-template <typename Kernel>
+// SquaredExpARD with two Lambda columns (squared_exp_ard.hpp:109-126,142-146)
+struct ParamsLambda : Params {
+    struct kernel_squared_exp_ard {
+        BO_PARAM(int, k, 2);
+        BO_PARAM(double, sigma_sq, 1);
+    };
+};
+
+template <typename Kernel, typename Params = ::Params>
 int run_case(const char* name, int N, int D)
 {
     using HP = model::gp::KernelLFOpt<Params, opt::Rprop<Params>>;
@@ -149,6 +157,7 @@ int main()
         "KernelMeanLFOpt", 70, 2, false);
     bad += run_case<kernel::SquaredExpARD<Params>>("SquaredExpARD", 60, 3);
     bad += run_case<kernel::MaternFiveHalves<Params>>("MaternFiveHalves", 150, 2);
+    bad += run_case<kernel::SquaredExpARD<ParamsLambda>, ParamsLambda>("SquaredExpARD_k2", 70, 3);
     std::printf(bad ? "DROPIN FAIL\n" : "DROPIN OK\n");
     return bad;
 }

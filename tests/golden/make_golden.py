@@ -30,9 +30,16 @@ CASES = [
     ("matern52_incremental_n100_d1", 1, 100, 1, 1, 30, 0.01, None, 60, False, 0),
     ("se_ard_incremental_cross128_d3", 0, 140, 3, 1, 30, 0.01, None, 120, False, 0),
     ("se_ard_rprop8_n60_d2", 0, 60, 2, 1, 10, 0.01, None, 0, False, 8),
+    # kernel_id 4 = SquaredExpARD with Params::kernel_squared_exp_ard::k() = 2 (Lambda columns): hp = [ell (D), A(:,0), A(:,1), sigma_f]
+    ("se_ard_lambda2_n90_d3", 4, 90, 3, 1, 24, 0.01, [-0.3, -0.5, -0.2, 0.5, -0.4, 0.3, 0.1, 0.7, -0.6, 0.2], 0, False, 0),
+    ("se_ard_lambda2_incremental_n140_d2_p2", 4, 140, 2, 2, 16, 0.02, [-0.4, -0.1, 0.6, -0.3, -0.2, 0.5, 0.1], 126, False, 0),
+    ("se_ard_lambda2_rprop5_n50_d2", 4, 50, 2, 1, 8, 0.01, None, 0, False, 5),
 ]
 
+ONLY = sys.argv[1:]  # optional: regenerate only the named fixtures
 for name, kid, N, D, P, M, noise, hp, n0, on, iters in CASES:
+    if ONLY and name not in ONLY:
+        continue
     X = synth.points(1234, N, D)
     y = synth.targets(X)
     Y = np.stack([y * (p + 1) + 0.1 * p for p in range(P)], axis=1)

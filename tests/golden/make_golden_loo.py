@@ -24,8 +24,12 @@ LOO_CASES = [
     ("loo_matern32_n70_d3_noiseopt", 2, 70, 3, 1, 0.05, [0.2, -0.1, float(np.log(np.sqrt(0.05)))], True),
     ("loo_exp_n70_d3", 3, 70, 3, 1, 0.01, [-0.3, 0.1], False),
     ("loo_se_ard_n260_d4", 0, 260, 4, 1, 0.01, [-0.7, -0.5, -0.6, -0.8, 0.0], False),
+    ("loo_se_ard_lambda2_n80_d2", 4, 80, 2, 1, 0.01, [-0.4, -0.1, 0.6, -0.3, -0.2, 0.5, 0.1], False),  # kernel_id 4: k = 2
 ]
+ONLY = sys.argv[1:]
 for name, kid, N, D, P, noise, hp, on in LOO_CASES:
+    if ONLY and name not in ONLY:
+        continue
     X = synth.points(4321, N, D)
     y = synth.targets(X)
     Y = np.stack([y * (p + 1) + 0.1 * p for p in range(P)], axis=1)
@@ -40,6 +44,8 @@ MEAN_CASES = [
     ("meangrad_matern52_n140_d3_p2", 1, 140, 3, 2, 0.01, [-0.4, 0.2], [1.1, 0.2, -0.1, -0.3, 0.9, 0.4, 0.7]),
 ]
 for name, kid, N, D, P, noise, hp, mh in MEAN_CASES:
+    if ONLY and name not in ONLY:
+        continue
     X = synth.points(4322, N, D)
     y = synth.targets(X)
     Y = np.stack([y * (p + 1) + 0.1 * p for p in range(P)], axis=1)

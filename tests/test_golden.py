@@ -12,7 +12,13 @@ import pytest
 
 GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
 IDS = [os.path.basename(p)[:-4] for p in GOLD]
-KNAMES = {0: "SquaredExpARD", 1: "MaternFiveHalves", 2: "MaternThreeHalves", 3: "Exp"}
+KNAMES = {0: "SquaredExpARD", 1: "MaternFiveHalves", 2: "MaternThreeHalves", 3: "Exp", 4: "SquaredExpARD"}
+# fixture kernel_id 4 = SquaredExpARD with Params::kernel_squared_exp_ard::k() = 2 (Lambda columns); the ABI / oracle id stays 0
+
+
+def _kid(g):
+    kid = int(g["kernel_id"])
+    return (0, 2) if kid == 4 else (kid, 0)
 
 
 def test_fixtures_present():
@@ -20,8 +26,9 @@ def test_fixtures_present():
 
 
 def _hp_own(g):
-    D, kid = int(g["D"]), int(g["kernel_id"])
-    nh = D + 1 if kid == 0 else 2
+    D = int(g["D"])
+    kid, klam = _kid(g)
+    nh = D + D * klam + 1 if kid == 0 else 2
     hp = np.asarray(g["hp"], dtype=float)  # final h-params the reference reports (incl. noise entry if optimised)
     return hp[:nh], hp
 
@@ -31,12 +38,13 @@ def test_oracle_reproduces_reference(path, oracle_mod):
     O = oracle_mod
     g = np.load(path)
     X, Y, Xq = g["X"], g["Y"], g["Xq"]
-    kid, noise, n0, on, iters = int(g["kernel_id"]), float(g["noise"]), int(g["n0"]), bool(g["optimize_noise"]), int(g["rprop_iters"])
+    noise, n0, on, iters = float(g["noise"]), int(g["n0"]), bool(g["optimize_noise"]), int(g["rprop_iters"])
+    kid, klam = _kid(g)
     hp_own, hp_full = _hp_own(g)
     og = O.OracleGP()
     if iters > 0:
         hp0 = np.asarray(g["hp_in"], dtype=float)
-        nh = X.shape[1] + 1 if kid == 0 else 2
+        nh = X.shape[1] * (1 + klam) + 1 if kid == 0 else 2
         hp0 = hp0 if hp0.size else np.zeros(nh)
         og.set_data(X, Y - Y.mean(axis=0))
         og.set_kernel(kid, hp0, noise)
@@ -75,12 +83,17 @@ def test_cuda_path_reproduces_reference(path):
     from limbo_b200 import acqui, kernel, mean, model, opt
     g = np.load(path)
     X, Y, Xq = g["X"], g["Y"], g["Xq"]
-    kid, noise, n0, on, iters = int(g["kernel_id"]), float(g["noise"]), int(g["n0"]), bool(g["optimize_noise"]), int(g["rprop_iters"])
+    noise, n0, on, iters = float(g["noise"]), int(g["n0"]), bool(g["optimize_noise"]), int(g["rprop_iters"])
+    kid, klam = _kid(g)
     hp_own, hp_full = _hp_own(g)
 
     class Prm:
         class kernel:
             pass
+
+        class kernel_squared_exp_ard:
+            k = klam
+            sigma_sq = 1.0
 
         class opt_rprop:
             iterations = max(iters, 1)
