@@ -98,8 +98,14 @@ def test_kernel_param_plumbing():
     class P2:
         class kernel_squared_exp_ard:
             k = 2
+    k2 = kernel.SquaredExpARD(P2, 3)  # squared_exp_ard.hpp:83-92: D + D k + 1 parameters, Lambda zero-initialised
+    assert k2.params_size() == 3 + 3 * 2 + 1 and np.array_equal(k2.h_params(), np.zeros(10))
+
+    class P3:
+        class kernel_squared_exp_ard:
+            k = 5
     with pytest.raises(NotImplementedError):
-        kernel.SquaredExpARD(P2, 3)
+        kernel.SquaredExpARD(P3, 3)
 
 
 def test_rprop_on_quadratic_and_call_count():
@@ -157,3 +163,25 @@ def test_mean_policies():
     assert np.array_equal(mean.NullFunction(None, 2)(xs[0], FakeGP()), [0.0, 0.0])
     c = mean.Constant(None, 2)
     assert np.array_equal(c(xs[0], FakeGP()), [1.0, 1.0]) and c.h_params_size() == 1
+
+
+def test_archives_write_the_reference_formats(tmp_path):
+    """serialize/text_archive.hpp:69-112 and binary_archive.hpp:68-160: byte-level layout of both archive kinds."""
+    import struct
+    from limbo_b200 import serialize
+    M = np.array([[1.5, -2.0, 3.25], [0.1, 1e-17, 7.0]])
+    vecs = [np.array([1.0, 2.0]), np.array([-3.5, 4.0])]
+    t = serialize.TextArchive(str(tmp_path / "t"))
+    t.save(M, "m"); t.save(vecs, "v"); t.save(np.array([1.0, 2.0, 3.0]), "col")
+    assert open(t.fname("m")).read().splitlines()[0].split(" ") == [repr(1.5), repr(-2.0), repr(3.25)]
+    assert len(open(t.fname("col")).read().splitlines()) == 3  # an Eigen vector is written as a column
+    assert np.array_equal(t.load_matrix("m"), M) and np.array_equal(t.load_vector("col"), [1.0, 2.0, 3.0])
+    assert all(np.array_equal(a, b) for a, b in zip(t.load_vector_list("v"), vecs))
+    b = serialize.BinaryArchive(str(tmp_path / "b"))
+    b.save(M, "m"); b.save(vecs, "v"); b.save(np.array([1.0, 2.0, 3.0]), "col")
+    raw = open(b.fname("m"), "rb").read()
+    assert raw == struct.pack("<qq", 2, 3) + struct.pack("<6d", 1.5, 0.1, -2.0, 1e-17, 3.25, 7.0)  # Index rows, cols; column-major
+    rawv = open(b.fname("v"), "rb").read()
+    assert rawv == struct.pack("<i", 2) + struct.pack("<qq2d", 2, 1, 1.0, 2.0) + struct.pack("<qq2d", 2, 1, -3.5, 4.0)
+    assert np.array_equal(b.load_matrix("m"), M) and np.array_equal(b.load_vector("col"), [1.0, 2.0, 3.0])
+    assert all(np.array_equal(x, y) for x, y in zip(b.load_vector_list("v"), vecs))

@@ -21,13 +21,17 @@ def test_save_load_roundtrip(tmp_path):
         assert (tmp_path / "gp_text" / (name + ".dat")).exists()
     Xq = synth.points(2, 1000, 4)
     mu, s2 = gp.query_batch(Xq)
-    for recompute in (True, False):
-        g2 = model.GP(-1, -1, kernel=kernel.SquaredExpARD, mean=mean.Data)
-        g2.load(serialize.TextArchive(d), recompute=recompute)
-        assert g2.nb_samples() == 300 and g2.dim_in() == 4 and g2.dim_out() == 2
-        m2, v2 = g2.query_batch(Xq)
-        assert np.abs(mu - m2).max() <= 1e-10 and np.abs(s2 - v2).max() <= 1e-10
-        assert abs(g2.compute_log_lik() - gp.compute_log_lik()) <= 1e-10 * abs(gp.compute_log_lik())
+    db = str(tmp_path / "gp_bin")
+    gp.save(serialize.BinaryArchive(db))  # binary_archive.hpp: same six objects, .bin files
+    assert (tmp_path / "gp_bin" / "matrixL.bin").stat().st_size == 16 + 8 * 300 * 300
+    for archive in (serialize.TextArchive(d), serialize.BinaryArchive(db)):
+        for recompute in (True, False):
+            g2 = model.GP(-1, -1, kernel=kernel.SquaredExpARD, mean=mean.Data)
+            g2.load(archive, recompute=recompute)
+            assert g2.nb_samples() == 300 and g2.dim_in() == 4 and g2.dim_out() == 2
+            m2, v2 = g2.query_batch(Xq)
+            assert np.abs(mu - m2).max() <= 1e-10 and np.abs(s2 - v2).max() <= 1e-10
+            assert abs(g2.compute_log_lik() - gp.compute_log_lik()) <= 1e-10 * abs(gp.compute_log_lik())
 
 
 def test_multi_gp_matches_plain_gps():
