@@ -383,6 +383,34 @@ static int set_data_common(lb_gp* h, int64_t N, int D, int P, const double* X, c
     return LB_OK;
 }
 
+// Samples only (multi-GPU Cholesky, potrf.cu lb_dchol_*): stages X without allocating the N x N factor storage of
+// this handle; the handle can then only serve lb_set_kernel and the lb_dchol_* calls.
+int lb_dchol_set_points(lb_gp* h, int64_t N, int D, const double* X)
+{
+    if (!h || N <= 0 || D < 1 || D > LB_MAX_D || !X) return LB_ERR_ARG;
+    LB_CUDA(cudaSetDevice(h->device));
+    LB_CUDA(cudaStreamSynchronize(h->stream));
+    free_model(h);
+    const int64_t Np = (N + LB_TILE - 1) / LB_TILE * LB_TILE;
+    LB_CUDA(cudaMalloc(&h->dX, sizeof(double) * D * Np));
+    LB_CUDA(cudaMalloc(&h->dXs, sizeof(double) * (D + LB_MAX_LAMBDA) * Np));
+    h->Np = Np;
+    if (D != h->D) h->kp.klam = 0;
+    h->N = N; h->D = D; h->P = 0;
+    h->kp.Draw = D;
+    h->kp.D = D + h->kp.klam;
+    h->fitted = false; h->linv_valid = false; h->kinv_valid = false; h->linv32_valid = false;
+    int rc = lb_ensure_scratch(h, sizeof(double) * (size_t)N * D);
+    if (rc) return rc;
+    LB_CUDA(cudaMemcpyAsync(h->dScratch, X, sizeof(double) * N * D, cudaMemcpyHostToDevice, h->stream));
+    dim3 g1((unsigned)((Np + 255) / 256), (unsigned)D);
+    pack_soa_kernel<<<g1, 256, 0, h->stream>>>(h->dScratch, N, D, h->dX, Np, h->kp, 0);
+    h->launches++;
+    LB_CUDA(cudaStreamSynchronize(h->stream));
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
 int lb_set_data(lb_gp* h, int64_t N, int D, int P, const double* X, const double* Y)
 {
     return set_data_common(h, N, D, P, X, Y, false);
@@ -442,7 +470,7 @@ int lb_set_kernel(lb_gp* h, int kernel_id, const double* p, int n_hparams, doubl
 int lb_fit(lb_gp* h)
 {
     if (!h) return LB_ERR_ARG;
-    if (!h->kernel_set || h->Np == 0) return LB_ERR_STATE;
+    if (!h->kernel_set || h->Np == 0 || !h->dL) return LB_ERR_STATE;
     LB_CUDA(cudaSetDevice(h->device));
     if (h->N == 0) return LB_ERR_STATE; // gp.hpp:90 assert(samples.size() != 0)
     int rc;
@@ -457,7 +485,7 @@ int lb_fit(lb_gp* h)
 int lb_fit_async(lb_gp* h) // same as lb_fit without the final host sync / info read (bench "value" leg)
 {
     if (!h) return LB_ERR_ARG;
-    if (!h->kernel_set || h->Np == 0 || h->N == 0) return LB_ERR_STATE;
+    if (!h->kernel_set || h->Np == 0 || h->N == 0 || !h->dL) return LB_ERR_STATE;
     int rc;
     if ((rc = lb_launch_scale_x(h))) return rc;
     if ((rc = lb_launch_kbuild(h, h->dL))) return rc;

@@ -396,3 +396,198 @@ int lb_launch_potrf(lb_gp* h)
     LB_CUDA(cudaGetLastError());
     return LB_OK;
 }
+
+// =====================================================================================================================
+// Multi-GPU Cholesky (BASELINE.json config 5, SURVEY.md §8e "stretch"): building blocks for a 1-D block-cyclic
+// right-looking factorisation over 256-column panels ("pairs" of 128-blocks, the same pair structure as lb_launch_potrf).
+// Pair p (global 128-block columns 2p, 2p+1) lives on rank p mod G; a rank stores its pairs side by side, full height:
+//   local 128-block column l  <->  global block column  j(l) = 2 * (G * (l / 2) + rank) + (l & 1)
+// One step = owner factors its pair (potf2, trsm, K=128 column update, potf2, trsm: the kernels above on its local
+// columns), packs the rows below the pair into a contiguous panel, the host broadcasts the panel (NCCL, the only
+// exchange step of the path), and every rank applies the K = 256 update to the local columns right of the pair.  The host
+// side (limbo_b200/dist_chol.py) owns the streams, the double-buffered panel and the look-ahead.
+// =====================================================================================================================
+namespace {
+
+__device__ __forceinline__ int dchol_global_block(int l, int rank, int G) { return 2 * (G * (l >> 1) + rank) + (l & 1); }
+
+// K[:, local columns] for this rank: dLoc[i + c*ld], c = local column; noise + 1e-8 on the diagonal (kernel.hpp:83);
+// identity in the padding (i or global column >= N).
+__global__ void __launch_bounds__(256)
+dchol_build_kernel(const double* __restrict__ Xs, int64_t xs_ld, int64_t N, int64_t Nd, KernParams kp, int rank, int G, int64_t ncols_local,
+    double* __restrict__ dLoc)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t c = blockIdx.y;
+    if (i >= Nd || c >= ncols_local) return;
+    const int64_t j = (int64_t)dchol_global_block((int)(c / LB_TILE), rank, G) * LB_TILE + (c % LB_TILE);
+    double v;
+    if (i >= N || j >= N) v = (i == j) ? 1.0 : 0.0;
+    else {
+        double z = 0.0;
+        for (int d = 0; d < kp.D; ++d) {
+            const double q = Xs[(int64_t)d * xs_ld + i] - Xs[(int64_t)d * xs_ld + j];
+            z = fma(q, q, z);
+        }
+        v = lb_kernel_from_z(kp.id, z, kp) + ((i == j) ? kp.noise + 1e-8 : 0.0);
+    }
+    dLoc[i + c * Nd] = v;
+}
+
+// panel[r + c*ldp] = cols[(row0 + r) + c*ld], r < ldp, c < 256
+__global__ void __launch_bounds__(256)
+dchol_pack_kernel(const double* __restrict__ cols, int64_t ld, int64_t row0, double* __restrict__ panel, int64_t ldp)
+{
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int c = blockIdx.y;
+    if (r < ldp) panel[r + c * ldp] = cols[row0 + r + c * ld];
+}
+
+// C[i, j(l)] -= P[i,:] P[j(l),:]^T for the local block columns l in [l0, l1) whose global index j(l) > kpair+1, i >= j(l).
+// P is the packed panel: row block b of the global matrix sits at panel row (b - (kpair + 2)) * 128, ld = ldp, K = 256.
+template <typename C>
+__global__ void __launch_bounds__(C::THREADS, (C::THREADS == 256) ? 2 : 1)
+dchol_update_kernel(double* __restrict__ Lloc, int64_t ld, const double* __restrict__ P, int64_t ldp, int kpair, int l0, int l1, int rank,
+    int G, int T)
+{
+    extern __shared__ __align__(16) double smem[];
+    constexpr int SPLIT = LB_TILE / C::BN;
+    int idx = blockIdx.x / SPLIT;
+    const int h = blockIdx.x - idx * SPLIT;
+    int l = l0;
+    for (; l < l1; ++l) {
+        const int nt = T - dchol_global_block(l, rank, G);
+        if (idx < nt) break;
+        idx -= nt;
+    }
+    if (l >= l1) return;
+    const int j = dchol_global_block(l, rank, G), i = j + idx;
+    const int b0 = kpair + 2;
+    const double* A = P + (int64_t)(i - b0) * LB_TILE;
+    const double* B = P + (int64_t)(j - b0) * LB_TILE + h * C::BN;
+    double* Cg = Lloc + (int64_t)i * LB_TILE + ((int64_t)l * LB_TILE + h * C::BN) * ld;
+    lbg::Acc<C> acc;
+    lbg::load_acc<C>(acc, Cg, ld);
+    lbg::mainloop<C, false, false, true>(acc, A, ldp, B, ldp, 2 * LB_TILE, smem);
+    lbg::store_acc<C>(acc, Cg, ld);
+}
+
+// zero the strictly upper part of the local columns (matrixL has a zero upper triangle, gp.hpp:565) and return
+// sum log L_jj over the local columns with global index < N in out[0]
+__global__ void __launch_bounds__(256)
+dchol_finish_kernel(double* __restrict__ Lloc, int64_t ld, int64_t N, int rank, int G, int64_t ncols_local, double* __restrict__ part)
+{
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int64_t c = blockIdx.x; c < ncols_local; c += gridDim.x) {
+        const int64_t j = (int64_t)dchol_global_block((int)(c / LB_TILE), rank, G) * LB_TILE + (c % LB_TILE);
+        double* col = Lloc + c * ld;
+        for (int64_t i = threadIdx.x; i < j && i < ld; i += 256) col[i] = 0.0;
+        if (threadIdx.x == 0 && j < N) s += log(col[j]);
+    }
+    s = lb_warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        part[blockIdx.x] = t;
+    }
+}
+__global__ void dchol_sum_kernel(const double* __restrict__ part, int n, double* __restrict__ out)
+{
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += part[i];
+    *out = s;
+}
+
+bool g_dchol_attr = false;
+
+} // namespace
+
+extern "C" {
+
+// K columns of this rank.  h supplies the staged samples and the kernel (lb_set_data + lb_set_kernel, no fit needed);
+// Nd = padded order (multiple of 256), dLoc = Nd x ncols_local, column-major.
+int lb_dchol_build(lb_gp* h, int64_t Nd, int rank, int G, int64_t ncols_local, double* dLoc)
+{
+    if (!h || !dLoc || Nd % (2 * LB_TILE) || !h->kernel_set || h->N <= 0) return LB_ERR_ARG;
+    int rc = lb_launch_scale_x(h);
+    if (rc) return rc;
+    dim3 grid((unsigned)((Nd + 255) / 256), (unsigned)ncols_local);
+    dchol_build_kernel<<<grid, 256, 0, h->stream>>>(h->dXs, h->Np, h->N, Nd, h->kp, rank, G, ncols_local, dLoc);
+    h->launches++;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+// Owner step for pair `kpair` (global 128-block index of its first column, even): dCols = the pair's 256 local columns
+// (Nd x 256, ld = Nd).  Factors them in place and packs rows [(kpair+2)*128, Nd) into dPanel (ld = Nd - (kpair+2)*128).
+// dInvD: 2 x 128 x 128 scratch; dInfo: 2 ints (first failing pivot, 1-based local to the pair's diagonal block, or 0).
+int lb_dchol_panel(lb_gp* h, double* dCols, int64_t Nd, int kpair, double* dInvD, int* dInfo, double* dPanel)
+{
+    if (!h || !dCols || !dInvD || !dInfo) return LB_ERR_ARG;
+    int rc = set_attrs();
+    if (rc) return rc;
+    const int T = (int)(Nd / LB_TILE);
+    cudaStream_t st = h->stream;
+    // the kernels above address block (i, k) as L + i*128 + k*128*ld: shift the bases so that block column kpair is dCols
+    double* Lb = dCols - (int64_t)kpair * LB_TILE * Nd;
+    double* Ib = dInvD - (int64_t)kpair * LB_TILE * LB_TILE;
+    potf2_inv_kernel<<<1, 256, POTF2_SMEM, st>>>(Lb, Nd, kpair, Ib, dInfo, 1);
+    trsm_panel_kernel<<<T - kpair - 1, lbg::CfgWide::THREADS, lbg::CfgWide::PIPE_BYTES, st>>>(Lb, Nd, kpair, Ib);
+    syrk_kernel<SyrkCfg><<<(T - kpair - 1) * SYRK_SPLIT, SyrkCfg::THREADS, SyrkCfg::PIPE_BYTES, st>>>(Lb, Nd, kpair, 1, kpair + 1, 1, T);
+    potf2_inv_kernel<<<1, 256, POTF2_SMEM, st>>>(Lb, Nd, kpair + 1, Ib, dInfo, 1);
+    h->launches += 4;
+    if (kpair + 2 < T) {
+        trsm_panel_kernel<<<T - kpair - 2, lbg::CfgWide::THREADS, lbg::CfgWide::PIPE_BYTES, st>>>(Lb, Nd, kpair + 1, Ib);
+        const int64_t ldp = Nd - (int64_t)(kpair + 2) * LB_TILE;
+        dim3 grid((unsigned)((ldp + 255) / 256), 2 * LB_TILE);
+        dchol_pack_kernel<<<grid, 256, 0, st>>>(dCols, Nd, (int64_t)(kpair + 2) * LB_TILE, dPanel, ldp);
+        h->launches += 2;
+    }
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+// Trailing update of the local block columns [l0, l1) with the packed panel of pair kpair (on h's stream).
+int lb_dchol_update(lb_gp* h, double* dLoc, int64_t Nd, const double* dPanel, int kpair, int l0, int l1, int rank, int G)
+{
+    if (!h || !dLoc || !dPanel) return LB_ERR_ARG;
+    if (!g_dchol_attr) {
+        LB_CUDA(cudaFuncSetAttribute(dchol_update_kernel<SyrkCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg::PIPE_BYTES));
+        g_dchol_attr = true;
+    }
+    const int T = (int)(Nd / LB_TILE);
+    int64_t tiles = 0;
+    int lfirst = l1;
+    for (int l = l0; l < l1; ++l) {
+        const int j = 2 * (G * (l >> 1) + rank) + (l & 1);
+        if (j <= kpair + 1) continue; // left of / inside the panel: nothing to update
+        if (l < lfirst) lfirst = l;
+        tiles += T - j;
+    }
+    if (tiles == 0) return LB_OK;
+    const int64_t ldp = Nd - (int64_t)(kpair + 2) * LB_TILE;
+    LbProfScope ps(h, h->stream, LB_PC_SYRK);
+    dchol_update_kernel<SyrkCfg><<<(unsigned)(tiles * SYRK_SPLIT), SyrkCfg::THREADS, SyrkCfg::PIPE_BYTES, h->stream>>>(dLoc, Nd, dPanel, ldp, kpair,
+        lfirst, l1, rank, G, T);
+    h->launches++;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+// zero the upper triangle of the local columns; *dLogdetPart (device) = sum over local columns of log L_jj
+int lb_dchol_finish(lb_gp* h, double* dLoc, int64_t Nd, int64_t N, int rank, int G, int64_t ncols_local, double* dLogdetPart)
+{
+    if (!h || !dLoc || !dLogdetPart) return LB_ERR_ARG;
+    int rc = lb_ensure_scratch(h, sizeof(double) * 1024);
+    if (rc) return rc;
+    dchol_finish_kernel<<<1024, 256, 0, h->stream>>>(dLoc, Nd, N, rank, G, ncols_local, h->dScratch);
+    dchol_sum_kernel<<<1, 1, 0, h->stream>>>(h->dScratch, 1024, dLogdetPart);
+    h->launches += 2;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+} // extern "C"

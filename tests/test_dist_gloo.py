@@ -133,3 +133,102 @@ def test_sharded_restarts_world2_equals_world1(tmp_path):
     recs = [json.loads(o.strip().splitlines()[-1]) for o, _ in outs]
     assert np.allclose(recs[0]["best"], recs[1]["best"], rtol=0, atol=0)
     assert np.allclose(recs[0]["best"], single, rtol=0, atol=1e-15)
+
+
+# ---- multi-GPU Cholesky schedule (limbo_b200/dist_chol.py), executed with NumPy over gloo ---------------------------
+WORKER_DCHOL = r"""
+import sys, json
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from limbo_b200 import dist_chol as dc
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=int(sys.argv[4]))
+rank, world = dist.get_rank(), dist.get_world_size()
+N = int(sys.argv[5])
+Nd = dc.padded_order(N); T = Nd // dc.TILE; npairs = T // 2
+rng = np.random.default_rng(3)
+B = rng.standard_normal((N, N + 5))
+K = np.eye(Nd); K[:N, :N] = B @ B.T / N + 0.5 * np.eye(N)          # SPD, identity in the padding (as the device build)
+pairs = dc.local_pairs(npairs, rank, world)
+cols = np.concatenate([np.arange(dc.global_block(l, rank, world) * dc.TILE, (dc.global_block(l, rank, world) + 1) * dc.TILE)
+                       for l in range(2 * len(pairs))]) if pairs else np.zeros(0, dtype=int)
+L = K[:, cols].copy()                                               # this rank's columns, full height
+panels = [None, None]
+log = []
+for act in dc.schedule(npairs, rank, world):
+    kind, p = act[0], act[1]
+    r0 = (2 * p + 2) * dc.TILE
+    if kind == "panel":
+        lp = p // world
+        c = slice(lp * dc.PAIR, (lp + 1) * dc.PAIR)
+        d0 = 2 * p * dc.TILE
+        Ld = np.linalg.cholesky(L[d0:d0 + dc.PAIR, c])
+        L[d0:d0 + dc.PAIR, c] = Ld
+        L[r0:, c] = np.linalg.solve(Ld, L[r0:, c].T).T
+        panels[p % 2] = L[r0:, c].copy()
+    elif kind == "bcast":
+        t = torch.from_numpy(panels[p % 2] if act[2] == rank else np.empty((Nd - r0, dc.PAIR)))
+        dist.broadcast(t, src=act[2])
+        panels[p % 2] = t.numpy()
+    else:
+        _, _, l0, l1, tag = act
+        P = panels[p % 2]
+        for l in range(l0, l1):
+            j = dc.global_block(l, rank, world)
+            assert j > 2 * p + 1
+            rows = slice(j * dc.TILE, Nd)
+            L[rows, l * dc.TILE:(l + 1) * dc.TILE] -= P[j * dc.TILE - r0:, :] @ P[j * dc.TILE - r0:(j + 1) * dc.TILE - r0, :].T
+    log.append(act[0])
+ref = np.linalg.cholesky(K)
+err = 0.0
+for ci, j in enumerate(cols):
+    err = max(err, float(np.abs(L[j:, ci] - ref[j:, j]).max()))
+print(json.dumps({"rank": rank, "err": err, "ncols": int(cols.size), "n_panel": log.count("panel"), "n_bcast": log.count("bcast")}))
+dist.destroy_process_group()
+"""
+
+
+def test_dist_cholesky_schedule_structure():
+    """Every pair is factored exactly once by its owner, every panel but the last is broadcast once per rank, and every
+    local block column right of a panel is updated exactly once by it (a and b parts are disjoint)."""
+    sys.path.insert(0, ROOT)
+    from limbo_b200 import dist_chol as dc
+    for world in (1, 2, 3, 8):
+        for npairs in (1, 2, 5, 16):
+            panels = []
+            for rank in range(world):
+                acts = list(dc.schedule(npairs, rank, world))
+                panels += [a[1] for a in acts if a[0] == "panel"]
+                assert [a[1] for a in acts if a[0] == "bcast"] == list(range(npairs - 1))
+                nlb = 2 * len(dc.local_pairs(npairs, rank, world))
+                for p in range(npairs - 1):
+                    upd = [a for a in acts if a[0] == "update" and a[1] == p]
+                    touched = [l for a in upd for l in range(a[2], a[3])]
+                    want = [l for l in range(nlb) if dc.global_block(l, rank, world) > 2 * p + 1]
+                    assert sorted(touched) == want and len(set(touched)) == len(touched)
+                    # look-ahead: the a part (columns of pair p + 1) comes first on its owner
+                    if (p + 1) % world == rank:
+                        assert upd[0][4] == "a" and [dc.global_block(l, rank, world) for l in range(upd[0][2], upd[0][3])] == [2 * p + 2, 2 * p + 3]
+                # a panel is issued only after the a-part update of the previous step
+                order = [(a[0], a[1]) for a in acts]
+                for p in [a[1] for a in acts if a[0] == "panel" and a[1] > 0]:
+                    assert order.index(("update", p - 1)) < order.index(("panel", p))
+            assert sorted(panels) == list(range(npairs))
+
+
+def test_dist_cholesky_world2_gloo(tmp_path):
+    """The schedule executed with NumPy on 2 gloo ranks (ragged N: 700 -> 3 pairs) reproduces numpy.linalg.cholesky."""
+    import json
+    port = _free_port()
+    script = tmp_path / "worker_dchol.py"
+    script.write_text(WORKER_DCHOL)
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r), "2", "700"], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True, env=env) for r in range(2)]
+    outs = [p.communicate(timeout=180) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e[-2000:]
+    recs = [json.loads(o.strip().splitlines()[-1]) for o, _ in outs]
+    assert all(r["err"] < 1e-11 for r in recs), recs
+    assert sum(r["ncols"] for r in recs) == 768 and sum(r["n_panel"] for r in recs) == 3
+    assert all(r["n_bcast"] == 2 for r in recs)
