@@ -1,5 +1,6 @@
 """Small end-to-end case for compute-sanitizer (memcheck / racecheck / synccheck): fit, append, query (fused and
-multi-launch), acquisition, log-lik, gradient, TF32 query."""
+multi-launch), acquisition, log-lik, gradient, LOO value / gradient, K^-1 obs_mean, SE-ARD with Lambda columns, tf32 and fp16
+queries, and the multi-GPU Cholesky blocks at world = 1."""
 import ctypes as C
 import os
 import sys
@@ -13,7 +14,7 @@ N, D, M = 300, 6, 700
 X = synth.points(1, N + 2, D)
 y = synth.targets(X)
 Xq = synth.points(2, M, D)
-for prec in ("fp64", "tf32"):
+for prec in ("fp64", "tf32", "fp16"):
     gp = model.GP(D, 1, kernel=kernel.SquaredExpARD, mean=mean.Data, precision=prec)
     gp.compute(X[:N], y[:N, None])
     gp.add_sample(X[N], y[N:N + 1])
@@ -28,4 +29,27 @@ for prec in ("fp64", "tf32"):
         mu2, s22 = gp.query_batch(Xq)
         assert np.abs(mu - mu2).max() < 1e-10 and np.abs(s2 - s22).max() < 1e-10
         print(gp.compute_log_lik(), gp.compute_kernel_grad_log_lik())
+        print(gp.compute_log_loo_cv(), gp.compute_kernel_grad_log_loo_cv())
+        w = np.empty((N + 2, 1), order="F")
+        _lib.check(lib.lb_kinv_obs_mean(gp._h, w.ctypes.data), "kinv_obs")
+
+
+class PL:
+    class kernel_squared_exp_ard:
+        k = 2
+        sigma_sq = 1.0
+
+
+gl = model.GP(D, 1, params=PL, kernel=kernel.SquaredExpARD, mean=mean.Data)
+hp = gl.kernel_function().h_params()
+hp[D:3 * D] = np.linspace(-0.5, 0.5, 2 * D)
+gl.kernel_function().set_h_params(hp)
+gl.compute(X[:N], y[:N, None])
+print("lambda", gl.compute_log_lik(), gl.compute_kernel_grad_log_lik()[:3], gl.query_batch(Xq[:50])[1].sum())
+
+from limbo_b200 import dist_chol  # noqa: E402
+dc = dist_chol.DistCholesky(X[:N], gp.kernel_function(), 0, 1, "cuda:0")
+dc.build()
+print("dchol", dc.factor())
+dc.close()
 print("SANITIZE CASE DONE")
