@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdio>
 #include <mutex>
 #include <new>
 #include <string>
@@ -657,8 +658,14 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
         if (h->precision == LB_PREC_TF32 || h->precision == LB_PREC_FP16) {
             // reduced-precision variance on tcgen05 (tf32_query.cu); mu is accumulated in fp64 from the fp64 kernel values
             if ((rc = lb_tf32_prepare(h))) return rc;
-            const int64_t cap = std::max<int64_t>(LB_TILE, ((int64_t)4 << 30) / (4 * h->Np) / LB_TILE * LB_TILE);
-            const int64_t Mc = std::min(Mp, cap);
+            // Candidate chunks of k x (SMs / 2 CTA pairs x 256 candidates): whole waves of the persistent tcgen05 GEMM (a 65536
+            // chunk = 3.46 waves cost 15 %); K*^T chunk <= 4 GiB.
+            int sms = 148;
+            LB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+            const int64_t CH = 2 * LB_TILE, wave = (int64_t)(sms / 2) * CH;
+            const int64_t cap = std::max<int64_t>(CH, ((int64_t)4 << 30) / (4 * h->Np) / CH * CH);
+            int64_t Mc = (cap >= wave) ? cap / wave * wave : cap;
+            Mc = std::min((M + CH - 1) / CH * CH, Mc);
             if ((rc = ensure(&w.dQs, &w.qs_bytes, sizeof(double) * De * Mc))) return rc;
             if ((rc = ensure(&w.dKt, &w.kt_bytes, sizeof(float) * (size_t)Mc * h->Np))) return rc;
             if ((rc = ensure(&w.dNorm2, &w.norm2_bytes, sizeof(float) * (size_t)Mc * 4))) return rc; // up to 4 cluster partials
@@ -667,12 +674,12 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
             LB_CUDA(cudaMemsetAsync(w.dErr, 0, sizeof(int), st));
             for (int64_t m0 = 0; m0 < M; m0 += Mc) {
                 const int64_t mc = std::min(Mc, M - m0);
-                const int64_t mcp = (mc + LB_TILE - 1) / LB_TILE * LB_TILE;
+                const int64_t mcp = (mc + CH - 1) / CH * CH;
                 dim3 g1((unsigned)((mcp + 255) / 256), (unsigned)De);
                 pack_soa_kernel<<<g1, 256, 0, st>>>(dQraw + m0 * D, mc, D, w.dQs, mcp, h->kp, 1);
                 h->launches++;
-                if ((rc = lb_launch_query_tf32(h, st, mc, w.dQs, mcp, w.dKt, w.dNorm2, w.dErr, w.dV, w.dMu + m0 * P, w.dS2 + m0, &h->launches)))
-                    return rc;
+                if ((rc = lb_launch_kstar_tf32(h, st, mc, w.dQs, mcp, w.dKt, w.dV, w.dMu + m0 * P, &h->launches))) return rc;
+                if ((rc = lb_launch_sigma_tf32(h, st, mc, mcp, w.dKt, w.dNorm2, w.dErr, w.dS2 + m0, &h->launches))) return rc;
             }
             if (!out_dev) {
                 int herr = 0;
@@ -977,8 +984,14 @@ int lb_profile_read(lb_gp* h, double* ms_out, long long* count_out, int reset)
     Profiler* p = (Profiler*)h->prof;
     LB_CUDA(cudaStreamSynchronize(h->stream));
     std::lock_guard<std::mutex> lk(p->mu);
+    const bool dump = getenv("LB_PROF_TIMELINE") != nullptr; // debug: per-launch (class, start, end) in ms from the first record
     for (auto& r : p->recs) {
         float ms = 0.f;
+        if (dump && !p->recs.empty()) {
+            float t0 = 0.f, t1 = 0.f;
+            if (cudaEventElapsedTime(&t0, p->recs[0].a, r.a) == cudaSuccess && cudaEventElapsedTime(&t1, p->recs[0].a, r.b) == cudaSuccess)
+                fprintf(stderr, "LBTL %d %.3f %.3f\n", r.cls, t0, t1);
+        }
         if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { p->ms[r.cls] += ms; p->n[r.cls]++; }
         p->pool.push_back(r.a); p->pool.push_back(r.b);
     }

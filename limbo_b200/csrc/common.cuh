@@ -349,5 +349,7 @@ int lb_launch_tf32_gemm_norm(cudaStream_t st, const void* dA, int64_t lda, const
 int lb_launch_tf32_gemm_norm_cluster(cudaStream_t st, const void* dA, int64_t lda, const void* dB, int64_t ldb, int64_t M, int64_t N,
     int64_t K, int tri, float* dNorm2, int* dErr, int sms, int cl, int f16);
 int lb_tf32_cluster_size();
-int lb_launch_query_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const double* dQs, int64_t Mcp, float* dKt, float* dNorm2,
-    int* dErr, double* dMuPart, double* dMu, double* dS2, long long* launches);
+int lb_launch_kstar_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const double* dQs, int64_t Mcp, float* dKt, double* dMuPart,
+    double* dMu, long long* launches);
+int lb_launch_sigma_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, int64_t Mcp, const float* dKt, float* dNorm2, int* dErr, double* dS2,
+    long long* launches);

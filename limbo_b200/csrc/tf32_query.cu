@@ -63,16 +63,37 @@ __device__ __forceinline__ bool mbar_try(uint64_t* b, uint32_t parity)
     return ok != 0;
 }
 // bounded wait: returns false (and raises *err) instead of spinning forever
+// The error flag (global memory) is polled only every 1024 attempts: a volatile load per spin from six spinning warps
+// would saturate the SM's load/store path (and starve any kernel sharing the SM).
 __device__ __forceinline__ bool mbar_wait(uint64_t* b, uint32_t parity, int* err)
 {
     long long spins = 0;
     while (!mbar_try(b, parity)) {
-        if (++spins > SPIN_LIMIT || *(volatile int*)err) {
+        if ((++spins & 1023) == 0 && (spins > SPIN_LIMIT || *(volatile int*)err)) {
             atomicExch(err, 1);
             return false;
         }
     }
     return true;
+}
+// Long waits of a whole warp (epilogue waiting for ~100 us of MMAs): one lane polls with a back-off, the other 31 lanes
+// sleep at the warp barrier instead of issuing try_wait / branch instructions.
+__device__ __forceinline__ bool mbar_wait_warp(uint64_t* b, uint32_t parity, int* err)
+{
+    int ok = 1;
+    if ((threadIdx.x & 31) == 0) {
+        long long spins = 0;
+        while (!mbar_try(b, parity)) {
+            __nanosleep(128);
+            if ((++spins & 255) == 0 && (spins > (SPIN_LIMIT >> 4) || *(volatile int*)err)) {
+                atomicExch(err, 1);
+                ok = 0;
+                break;
+            }
+        }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    return ok != 0;
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
 {
@@ -222,7 +243,7 @@ tf32_gemm_norm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         for (int mt = blockIdx.x; mt < m_tiles && ok; mt += gridDim.x) {
             float acc = 0.f;
             for (int nt = 0; nt < n_tiles && ok; ++nt) {
-                if (!mbar_wait(&tfull[buf], tph[buf], err)) { ok = false; break; }
+                if (!mbar_wait_warp(&tfull[buf], tph[buf], err)) { ok = false; break; }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll 1
@@ -377,7 +398,7 @@ tf32_gemm_norm_cluster_kernel(const __grid_constant__ CUtensorMap mapA, const __
         for (int mt = cluster_id; mt < m_tiles && ok; mt += nclusters) {
             float acc = 0.f;
             for (int grp = 0; grp < n_groups && ok; ++grp) {
-                if (!mbar_wait(&tfull[buf], tph[buf], err)) { ok = false; break; }
+                if (!mbar_wait_warp(&tfull[buf], tph[buf], err)) { ok = false; break; }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll 1
@@ -406,6 +427,201 @@ tf32_gemm_norm_cluster_kernel(const __grid_constant__ CUtensorMap mapA, const __
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): the GEMM above is bound by operand delivery from L2 (11.2 TB/s measured at
+// 128 x 256 tiles, the LTS cap of the chip is ~12 TB/s), so the lever is bytes per MAC.  Two CTAs of a cluster form one
+// MMA pair: UMMA M = 256 (each CTA owns 128 candidates = its own A rows and its own TMEM lanes) and every B tile is split
+// between the two CTAs (128 of the 256 rows of L^-1 each), so B is fetched once per 256 candidates.  Each A slab is used
+// for TWO n-tiles (two 256-column accumulators = all 512 TMEM columns): per 128 x 256 x 64-MAC unit a CTA pulls
+// 8 KB (A) + 16 KB (B) instead of 8 + 32 KB.  Only the leader CTA issues MMAs; both CTAs run a TMA producer whose
+// transactions complete on the LEADER's "full" barrier; commits are multicast to both CTAs ("slot free", "accumulators
+// full"); both epilogues report "accumulators drained" to the leader.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int HB_BYTES = (BN / 2) * 128;                    // half of a B tile: 128 rows x 128 B
+constexpr int PAIR_STAGE_BYTES = A_BYTES + 2 * HB_BYTES;    // A + B(n0) half + B(n1) half = 48 KB
+constexpr size_t PAIR_SMEM_BYTES = (size_t)STAGES * PAIR_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta));
+    return r;
+}
+// TMA load whose bytes complete on a barrier given by its shared::cluster address (the leader's)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     lb_smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
+                 : "memory");
+}
+template <bool F16>
+__host__ __device__ constexpr uint32_t idesc_pair()
+{
+    return (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+}
+template <bool F16>
+__device__ __forceinline__ void umma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
+{
+    if (F16)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc_pair<true>()), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc_pair<false>()), "r"(accumulate)
+            : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(lb_smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+// M % 256 == 0, N % 512 == 0.  norm2[c] = sum_n D[c, n]^2 (one partial per candidate).
+template <bool F16>
+__global__ void __launch_bounds__(THREADS, 1)
+pair_gemm_norm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int64_t M, int64_t N, int64_t K,
+    int tri, float* __restrict__ norm2, int* __restrict__ err)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + (size_t)STAGES * PAIR_STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 1;
+    uint32_t* tmem_base_s = (uint32_t*)(tempty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int m_pairs = (int)(M / (2 * BM)), n_groups = (int)(N / (2 * BN));
+    constexpr int BKE = bke<F16>();
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 8); // 4 epilogue warps of each CTA of the pair (leader's copy is the one waited on)
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) { // the same warp of BOTH CTAs performs the pair-wide allocation (all 512 columns)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(lb_smem_u32(tmem_base_s)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_base_s;
+
+    auto kblocks_of = [&](int nt) {
+        const int64_t kend = tri ? (int64_t)(nt + 1) * BN : K;
+        return (int)((kend < K ? kend : K) / BKE);
+    };
+
+    if (warp == 0) {
+        if (lane == 0) { // ===== TMA producer (both CTAs): own A rows, own half of both B tiles; bytes land on the leader's barrier =====
+            int s = 0; uint32_t ph = 0; bool ok = true;
+            for (int mt = pair_id; mt < m_pairs && ok; mt += npairs) {
+                for (int grp = 0; grp < n_groups && ok; ++grp) {
+                    const int n0 = 2 * grp, n1 = n0 + 1;
+                    const int kb0 = kblocks_of(n0), kb1 = kblocks_of(n1);
+                    for (int kb = 0; kb < kb1; ++kb) {
+                        if (!mbar_wait(&empty[s], ph ^ 1, err)) { ok = false; break; }
+                        const bool has0 = kb < kb0;
+                        uint8_t* sa = smem + (size_t)s * PAIR_STAGE_BYTES;
+                        const uint32_t lfull = mapa_u32(lb_smem_u32(&full[s]), 0);
+                        if (rank == 0) mbar_expect_tx(&full[s], 2u * (uint32_t)(A_BYTES + HB_BYTES + (has0 ? HB_BYTES : 0)));
+                        tma_load_2d_pair(sa, &mapA, kb * BKE, mt * 2 * BM + rank * BM, lfull);
+                        if (has0) tma_load_2d_pair(sa + A_BYTES, &mapB, kb * BKE, n0 * BN + rank * (BN / 2), lfull);
+                        tma_load_2d_pair(sa + A_BYTES + HB_BYTES, &mapB, kb * BKE, n1 * BN + rank * (BN / 2), lfull);
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    }
+    else if (warp == 1) {
+        if (lane == 0 && rank == 0) { // ===== MMA issuer: leader CTA only =====
+            int s = 0; uint32_t ph = 0; bool ok = true;
+            uint32_t tph = 0;
+            for (int mt = pair_id; mt < m_pairs && ok; mt += npairs) {
+                for (int grp = 0; grp < n_groups && ok; ++grp) {
+                    const int kb0 = kblocks_of(2 * grp), kb1 = kblocks_of(2 * grp + 1);
+                    if (!mbar_wait(tempty, tph ^ 1, err)) { ok = false; break; }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int kb = 0; kb < kb1; ++kb) {
+                        if (!mbar_wait(&full[s], ph, err)) { ok = false; break; }
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sa = lb_smem_u32(smem + (size_t)s * PAIR_STAGE_BYTES);
+                        const uint64_t adesc = make_desc(sa), b0desc = make_desc(sa + A_BYTES), b1desc = make_desc(sa + A_BYTES + HB_BYTES);
+                        if (kb < kb0) {
+#pragma unroll
+                            for (int k = 0; k < MMAS_PER_STAGE; ++k)
+                                umma_pair<F16>(tmem_base, adesc + (uint64_t)(2 * k), b0desc + (uint64_t)(2 * k), (kb | k) != 0);
+                        }
+#pragma unroll
+                        for (int k = 0; k < MMAS_PER_STAGE; ++k)
+                            umma_pair<F16>(tmem_base + (uint32_t)BN, adesc + (uint64_t)(2 * k), b1desc + (uint64_t)(2 * k), (kb | k) != 0);
+                        umma_commit_pair(&empty[s]); // slot s is free in both CTAs
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                    umma_commit_pair(tfull); // both accumulators complete, in both CTAs
+                    tph ^= 1;
+                }
+            }
+        }
+    }
+    else { // ===== epilogue (both CTAs): each thread owns one candidate = one TMEM lane of its CTA =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t ltempty = mapa_u32(lb_smem_u32(tempty), 0);
+        uint32_t tph = 0; bool ok = true;
+        for (int mt = pair_id; mt < m_pairs && ok; mt += npairs) {
+            float acc = 0.f;
+            for (int grp = 0; grp < n_groups && ok; ++grp) {
+                if (!mbar_wait_warp(tfull, tph, err)) { ok = false; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+                for (int c = 0; c < 2 * BN; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float d = __uint_as_float(v[j]);
+                        acc = fmaf(d, d, acc);
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(ltempty);
+                tph ^= 1;
+            }
+            if (ok) norm2[(int64_t)mt * 2 * BM + rank * BM + row] = acc;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all(); // neither CTA leaves (or frees TMEM) while the pair may still be using its memory
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -490,6 +706,9 @@ static int launch_cluster(cudaStream_t st, const CUtensorMap& mapA, const CUtens
     return LB_OK;
 }
 
+int lb_launch_pair_gemm_norm(cudaStream_t st, const void* dA, int64_t lda, const void* dB, int64_t ldb, int64_t M, int64_t N, int64_t K,
+    int tri, float* dNorm2, int* dErr, int sms, int f16);
+
 int lb_launch_tf32_gemm_norm_cluster(cudaStream_t st, const void* dA, int64_t lda, const void* dB, int64_t ldb, int64_t M, int64_t N,
     int64_t K, int tri, float* dNorm2, int* dErr, int sms, int cl, int f16)
 {
@@ -508,6 +727,60 @@ int lb_launch_tf32_gemm_norm_cluster(cudaStream_t st, const void* dA, int64_t ld
                        : launch_cluster<4, true>(st, mapA, mapB, M, N, K, tri, dNorm2, dErr, grid);
     return cl == 2 ? launch_cluster<2, false>(st, mapA, mapB, M, N, K, tri, dNorm2, dErr, grid)
                    : launch_cluster<4, false>(st, mapA, mapB, M, N, K, tri, dNorm2, dErr, grid);
+}
+
+template <bool F16>
+static int launch_pair(cudaStream_t st, const CUtensorMap& mapA, const CUtensorMap& mapB, int64_t M, int64_t N, int64_t K, int tri,
+    float* dNorm2, int* dErr, int grid)
+{
+    using namespace tf32q;
+    static bool attr_done = false;
+    if (!attr_done) {
+        LB_CUDA(cudaFuncSetAttribute(pair_gemm_norm_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM_BYTES));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = PAIR_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    LB_CUDA(cudaLaunchKernelEx(&cfg, pair_gemm_norm_kernel<F16>, mapA, mapB, M, N, K, tri, dNorm2, dErr));
+    return LB_OK;
+}
+
+// CTA-pair (cta_group::2) launch: M % 256 == 0, N % 512 == 0; dNorm2 holds M floats.
+int lb_launch_pair_gemm_norm(cudaStream_t st, const void* dA, int64_t lda, const void* dB, int64_t ldb, int64_t M, int64_t N, int64_t K,
+    int tri, float* dNorm2, int* dErr, int sms, int f16)
+{
+    using namespace tf32q;
+    if (M % (2 * BM) || N % (2 * BN) || K % 64) return LB_ERR_ARG;
+    alignas(64) CUtensorMap mapA, mapB;
+    int rc;
+    if ((rc = make_map(&mapA, dA, M, K, lda, BM, f16 != 0))) return rc;
+    if ((rc = make_map(&mapB, dB, N, K, ldb, BN / 2, f16 != 0))) return rc;
+    int npairs = sms / 2;
+    if (npairs > M / (2 * BM)) npairs = (int)(M / (2 * BM));
+    return f16 ? launch_pair<true>(st, mapA, mapB, M, N, K, tri, dNorm2, dErr, 2 * npairs)
+               : launch_pair<false>(st, mapA, mapB, M, N, K, tri, dNorm2, dErr, 2 * npairs);
+}
+
+extern "C" int lb_debug_pair_gemm(const void* dA, const void* dB, long long M, long long N, long long K, int tri, float* dNorm2, int f16)
+{
+    int* dErr = nullptr;
+    LB_CUDA(cudaMalloc(&dErr, sizeof(int)));
+    LB_CUDA(cudaMemset(dErr, 0, sizeof(int)));
+    int rc = lb_launch_pair_gemm_norm(0, dA, K, dB, K, M, N, K, tri, dNorm2, dErr, 148, f16);
+    if (rc) { cudaFree(dErr); return rc; }
+    LB_CUDA(cudaDeviceSynchronize());
+    int herr = 0;
+    LB_CUDA(cudaMemcpy(&herr, dErr, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(dErr);
+    return herr ? LB_ERR_TIMEOUT : LB_OK;
 }
 
 __global__ void debug_exp_kernel(const double* in, double* out, long long n)
@@ -560,17 +833,18 @@ extern "C" int lb_debug_tf32_gemm(const void* dA, const void* dB, long long M, l
 // ===========================================================================
 namespace tf32q {
 
-constexpr int DCH = 16;
+constexpr int DCH_WIDE = 16; // input dimensions staged per pass
 
 // Kt[c * ldk + n] = (float) k(x_n, q_c)  for one tile of 128 candidates x 128 training points; zero for n >= N.
 // grid: (Np/128, Mc/128).  Same thread mapping as kbuild_kernel: the two consecutive "rows" of a thread are two
 // consecutive n, stored as one float2 (n is the contiguous, K-major index of the GEMM's A operand).
 // F16: the stored values are k / sigma_f^2 (in (0, 1]) as half.  EDGE: the tile crosses N or M (zero beyond).
-template <int KID, bool F16, bool EDGE>
-__global__ void __launch_bounds__(256, 2)
-kstar_t32_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, const double* __restrict__ Qs, int64_t Mp, int64_t M,
-    void* __restrict__ Kt_, int64_t ldk, KernParams kp, const double* __restrict__ alpha, int P,
-    double* __restrict__ mu_part, int64_t i_first, int64_t j_first)
+// Tiles [i_first, i_first + ni) x [j_first, j_first + nj) are walked with a grid-stride loop (training index fastest), so the
+// same kernel runs one tile per CTA or as a small persistent grid.
+template <int KID, bool F16, bool EDGE, int DCH>
+__device__ __forceinline__ void kstar_t32_body(const double* __restrict__ Xs, int64_t Np, int64_t N, const double* __restrict__ Qs, int64_t Mp,
+    int64_t M, void* __restrict__ Kt_, int64_t ldk, const KernParams& kp, const double* __restrict__ alpha, int P,
+    double* __restrict__ mu_part, int64_t i_first, int64_t j_first, int64_t ni, int64_t nj)
 {
     __shared__ __align__(128) double sxi[DCH][LB_TILE];
     __shared__ __align__(128) double sxj[DCH][LB_TILE];
@@ -579,8 +853,6 @@ kstar_t32_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, const dou
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int li = lane & 7, lj = lane >> 3;
     const int D = kp.D;
-    const int64_t ti = i_first + blockIdx.x; // training tile index (also the slot of the mean partial)
-    const int64_t i0 = ti * LB_TILE, j0 = (j_first + blockIdx.y) * LB_TILE; // i: training, j: candidates
     const int r0 = warp * 16 + 2 * li;
     if (tid == 0) {
         lb_mbar_init(&bar, 1);
@@ -589,6 +861,9 @@ kstar_t32_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, const dou
     __syncthreads();
     uint32_t phase = 0;
     const int npass = (D + DCH - 1) / DCH;
+    for (int64_t tile = blockIdx.x; tile < ni * nj; tile += gridDim.x) {
+    const int64_t ti = i_first + tile % ni; // training tile index (also the slot of the mean partial)
+    const int64_t i0 = ti * LB_TILE, j0 = (j_first + tile / ni) * LB_TILE; // i: training, j: candidates
     for (int h = 0; h < 2; ++h) {
         double z[8][4];
 #pragma unroll
@@ -678,8 +953,18 @@ kstar_t32_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, const dou
             __syncthreads();
         }
     }
+    } // tile loop
 }
 
+// one tile per CTA (or any grid): two CTAs per SM by registers
+template <int KID, bool F16, bool EDGE, int DCH>
+__global__ void __launch_bounds__(256, 2)
+kstar_t32_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, const double* __restrict__ Qs, int64_t Mp, int64_t M,
+    void* __restrict__ Kt_, int64_t ldk, KernParams kp, const double* __restrict__ alpha, int P,
+    double* __restrict__ mu_part, int64_t i_first, int64_t j_first, int64_t ni, int64_t nj)
+{
+    kstar_t32_body<KID, F16, EDGE, DCH>(Xs, Np, N, Qs, Mp, M, Kt_, ldk, kp, alpha, P, mu_part, i_first, j_first, ni, nj);
+}
 // mu[c*P + p] = sum over the training tiles of the partials written by kstar_t32_kernel (fixed order)
 __global__ void __launch_bounds__(256)
 mu_reduce_kernel(const double* __restrict__ part, int ntiles, int64_t Mp, int P, int64_t M, double* __restrict__ mu)
@@ -759,6 +1044,17 @@ int lb_tf32_cluster_size()
     return cl;
 }
 
+// CTA-pair kernel (cta_group::2, pair_gemm_norm_kernel) unless LB_TF32_PAIR=0: config 4 fp16 GEMM 229 -> see DESIGN.md §4.5
+int lb_tf32_pair_mode()
+{
+    static int pm = -1;
+    if (pm < 0) {
+        const char* e = getenv("LB_TF32_PAIR");
+        pm = e ? (atoi(e) != 0) : 1;
+    }
+    return pm;
+}
+
 // Prepare the row-major reduced-precision copy of L^-1 (rows padded with zeros to a multiple of 256 * cluster size).
 // fp32 (tf32 MMA) stores L^-1 as is; fp16 stores L^-1 * 2^e with e chosen so that max |.| <= 2^14.
 int lb_tf32_prepare(lb_gp* h)
@@ -768,7 +1064,7 @@ int lb_tf32_prepare(lb_gp* h)
     const bool f16 = (h->precision == 2);
     int rc;
     if (!h->linv_valid && (rc = lb_launch_linv(h))) return rc;
-    const int cl = lb_tf32_cluster_size();
+    const int cl = lb_tf32_pair_mode() ? 2 : lb_tf32_cluster_size(); // the pair kernel walks two 256-row n-tiles per group
     const int64_t Np = h->Np, Nr = (Np + BN * cl - 1) / (BN * cl) * (BN * cl);
     const size_t esz = f16 ? 2 : 4;
     if (!h->dLinv32 || h->linv32_rows != Nr) {
@@ -802,14 +1098,17 @@ int lb_tf32_prepare(lb_gp* h)
     return LB_OK;
 }
 
-// mu (M x P, fp64) and sigma2 (M, fp64 container of a reduced-precision value) for one chunk of Mc <= capacity candidates.
-int lb_launch_query_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const double* dQs, int64_t Mcp, float* dKt, float* dNorm2,
-    int* dErr, double* dMuPart, double* dMu, double* dS2, long long* launches)
+// K*^T chunk (reduced precision, K-major) and mu (M x P, fp64) for Mc candidates.
+// (Tried and dropped: running this build for chunk i+1 on a second stream under the tcgen05 GEMM of chunk i.  Even with a
+// 13 KB / 104-register variant, cp.async staging, dynamic tile hand-out, polite mbarrier waits and the full 228 KB carve-out on
+// the GEMM, the fp64 CTAs made almost no progress while the GEMM CTA was resident and slowed it by 15 %: 272-285 ms per 1M
+// candidates against 256 ms for plain back-to-back launches, profiles/r01_config4_notes.txt.)
+int lb_launch_kstar_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const double* dQs, int64_t Mcp, float* dKt, double* dMuPart,
+    double* dMu, long long* launches)
 {
     using namespace tf32q;
     const bool f16 = (h->precision == 2);
     const int64_t Np = h->Np;
-    const double kscale = f16 ? 1.0 / h->kp.sf2 : 1.0;
     {
         LbProfScope ps(h, st, LB_PC_KSTAR);
         // interior tiles without bounds checks; the last tile row / column (when N or Mc is not a multiple of 128) with
@@ -817,9 +1116,9 @@ int lb_launch_query_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const doub
         const int64_t fi = h->N / LB_TILE, fj = Mc / LB_TILE; // number of full tiles
         auto go = [&](auto kid, auto f16c, auto edgec, int64_t ia, int64_t ib, int64_t ja, int64_t jb) {
             if (ib <= ia || jb <= ja) return;
-            dim3 g((unsigned)(ib - ia), (unsigned)(jb - ja));
-            kstar_t32_kernel<decltype(kid)::value, decltype(f16c)::value, decltype(edgec)::value><<<g, 256, 0, st>>>(h->dXs, Np, h->N, dQs, Mcp, Mc,
-                dKt, Np, h->kp, h->dAlpha, h->P, dMuPart, ia, ja);
+            const int64_t tiles = (ib - ia) * (jb - ja);
+            kstar_t32_kernel<decltype(kid)::value, decltype(f16c)::value, decltype(edgec)::value, DCH_WIDE><<<(unsigned)tiles, 256, 0, st>>>(h->dXs, Np,
+                h->N, dQs, Mcp, Mc, dKt, Np, h->kp, h->dAlpha, h->P, dMuPart, ia, ja, ib - ia, jb - ja);
             if (launches) ++*launches;
         };
         auto go_prec = [&](auto kid) {
@@ -842,20 +1141,35 @@ int lb_launch_query_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const doub
         LbProfScope ps(h, st, LB_PC_QREDUCE);
         mu_reduce_kernel<<<(unsigned)((Mc + 255) / 256), 256, 0, st>>>(dMuPart, (int)(Np / LB_TILE), Mcp, h->P, Mc, dMu);
     }
+    if (launches) ++*launches;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+// sigma2 (M, fp64 container of a reduced-precision value) from a K*^T chunk: tcgen05 GEMM + row norms, then the clamp / noise of gp.hpp:618-624
+int lb_launch_sigma_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, int64_t Mcp, const float* dKt, float* dNorm2, int* dErr, double* dS2,
+    long long* launches)
+{
+    using namespace tf32q;
+    const bool f16 = (h->precision == 2);
+    const int64_t Np = h->Np;
+    const double kscale = f16 ? 1.0 / h->kp.sf2 : 1.0;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     int rc;
-    const int cl = lb_tf32_cluster_size();
+    const bool pair = lb_tf32_pair_mode() && (Mcp % (2 * BM) == 0) && (h->linv32_rows % (2 * BN) == 0);
+    const int cl = pair ? 1 : lb_tf32_cluster_size(); // number of partial norms per candidate
     {
         LbProfScope ps(h, st, LB_PC_QSTEP);
-        if (cl == 1) rc = lb_launch_tf32_gemm_norm(st, dKt, Np, h->dLinv32, Np, Mcp, h->linv32_rows, Np, 1, dNorm2, nullptr, dErr, sms, f16);
+        if (pair) rc = lb_launch_pair_gemm_norm(st, dKt, Np, h->dLinv32, Np, Mcp, h->linv32_rows, Np, 1, dNorm2, dErr, sms, f16);
+        else if (cl == 1) rc = lb_launch_tf32_gemm_norm(st, dKt, Np, h->dLinv32, Np, Mcp, h->linv32_rows, Np, 1, dNorm2, nullptr, dErr, sms, f16);
         else rc = lb_launch_tf32_gemm_norm_cluster(st, dKt, Np, h->dLinv32, Np, Mcp, h->linv32_rows, Np, 1, dNorm2, dErr, sms, cl, f16);
     }
     if (rc) return rc;
     // D was computed from (K* kscale) and (L^-1 scale): |V|^2 = norm / (kscale scale)^2
     const double unscale = 1.0 / ((kscale * h->linv32_scale) * (kscale * h->linv32_scale));
     sigma2_t32_kernel<<<(unsigned)((Mc + 255) / 256), 256, 0, st>>>(dNorm2, cl, Mcp, Mc, h->kp.sf2, h->kp.noise, unscale, dS2);
-    if (launches) *launches += 3;
+    if (launches) *launches += 2;
     LB_CUDA(cudaGetLastError());
     return LB_OK;
 }

@@ -49,4 +49,20 @@ for cl in (2, 4):
             nerr = ((nrm - (ref ** 2).sum(1)).abs() / (ref ** 2).sum(1)).max().item()
             print(f"cluster={cl} tri={tri} f16={f16} rc={rc} norm rel err {nerr:.2e} time {dt * 1e3:.1f} ms")
             assert rc == 0 and nerr < 5e-3
+# CTA-pair (cta_group::2) kernel: M % 256 == 0, N % 512 == 0
+lib.lb_debug_pair_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_int]
+if M % 256 == 0 and N % 512 == 0:
+    for tri in (0, 1):
+        Bt = torch.tril(B) if tri else B
+        for f16 in (0, 1):
+            Ah, Bh = (A.half(), Bt.half()) if f16 else (A, Bt)
+            nrm = torch.zeros(M, device="cuda", dtype=torch.float32)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            rc = lib.lb_debug_pair_gemm(Ah.data_ptr(), Bh.data_ptr(), M, N, K, tri, nrm.data_ptr(), f16)
+            dt = time.time() - t0
+            ref = (Ah.double() @ Bh.double().T)
+            nerr = ((nrm.double() - (ref ** 2).sum(1)).abs() / (ref ** 2).sum(1)).max().item()
+            print(f"pair tri={tri} f16={f16} rc={rc} norm rel err {nerr:.2e} time {dt * 1e3:.1f} ms", flush=True)
+            assert rc == 0 and nerr < 5e-3
 print("TF32 GEMM OK")
