@@ -43,7 +43,7 @@ typedef struct lb_gp lb_gp;
 #define LB_ERR_UNSUPPORTED (-5)
 #define LB_ERR_TIMEOUT (-6)
 
-/* kernel ids (src/limbo/kernel/*.hpp) */
+/* kernel ids (the functors under src/limbo/kernel/) */
 #define LB_KERNEL_SQUARED_EXP_ARD 0 /* kernel/squared_exp_ard.hpp   h-params [log l_1..log l_D, (A(:,0) .. A(:,k-1): D each, k <= 4), log sigma_f];
                                        k = Params::kernel_squared_exp_ard::k() is inferred from n_hparams = D + D k + 1 */
 #define LB_KERNEL_MATERN_FIVE_HALVES 1 /* kernel/matern_five_halves.hpp      h-params [log l, log sigma_f] */

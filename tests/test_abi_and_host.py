@@ -20,6 +20,22 @@ def test_library_exports_every_declared_symbol(lib):
     assert sorted(_lib.DECLARED_SYMBOLS) == declared
     for name in declared:
         assert hasattr(lib, name), name
+    # the multi-GPU building blocks (include/limbo_b200_dist.h)
+    hdr2 = open(os.path.join(ROOT, "include", "limbo_b200_dist.h")).read()
+    declared2 = sorted(set(re.findall(r"\b(lb_dchol_[a-z_0-9]+)\s*\(", hdr2)))
+    assert declared2 == ["lb_dchol_build", "lb_dchol_finish", "lb_dchol_panel", "lb_dchol_set_points", "lb_dchol_update"]
+    for name in declared2:
+        assert hasattr(lib, name), name
+
+
+def test_headers_compile_as_c(tmp_path):
+    """include/*.h are plain C (extern "C", pointers and sizes only)."""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "limbo_b200.h"\n#include "limbo_b200_dist.h"\nint main(void) { return LB_OK; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
 
 
 def test_strerror_without_gpu(lib):
