@@ -833,6 +833,15 @@ extern "C" int lb_debug_tf32_gemm(const void* dA, const void* dB, long long M, l
 // ===========================================================================
 namespace tf32q {
 
+// fp32 -> tf32 with round-to-nearest: tcgen05.mma.kind::tf32 ignores the low 13 mantissa bits of its operands, i.e. truncates;
+// a truncated operand is biased low, and the bias of |L^-1 k*|^2 does not average out over the N terms of the sum.
+__device__ __forceinline__ float tf32_rna(float v)
+{
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return __uint_as_float(u);
+}
+
 constexpr int DCH_WIDE = 16; // input dimensions staged per pass
 
 // Kt[c * ldk + n] = (float) k(x_n, q_c)  for one tile of 128 candidates x 128 training points; zero for n >= N.
@@ -922,8 +931,8 @@ __device__ __forceinline__ void kstar_t32_body(const double* __restrict__ Xs, in
             }
             else {
                 float* Kt = reinterpret_cast<float*>(Kt_);
-                *reinterpret_cast<float2*>(&Kt[gj * ldk + gi]) = make_float2(v[0], v[1]);
-                *reinterpret_cast<float2*>(&Kt[(gj + 1) * ldk + gi]) = make_float2(v[2], v[3]);
+                *reinterpret_cast<float2*>(&Kt[gj * ldk + gi]) = make_float2(tf32_rna(v[0]), tf32_rna(v[1]));
+                *reinterpret_cast<float2*>(&Kt[(gj + 1) * ldk + gi]) = make_float2(tf32_rna(v[2]), tf32_rna(v[3]));
             }
         }
         // mean partials from the fp64 kernel values: mu_part[(p * ntiles + tile) * Mp + candidate] = sum over this tile's
@@ -1008,7 +1017,7 @@ linv_to_rowmajor_kernel(const double* __restrict__ Linv, int64_t ld, void* __res
     __syncthreads();
     for (int nn = ty; nn < 32; nn += 8) {
         if (F16) reinterpret_cast<__half*>(R_)[(n0 + nn) * ldr + k0 + tx] = __float2half_rn(tile[tx][nn]);
-        else reinterpret_cast<float*>(R_)[(n0 + nn) * ldr + k0 + tx] = tile[tx][nn];
+        else reinterpret_cast<float*>(R_)[(n0 + nn) * ldr + k0 + tx] = tf32_rna(tile[tx][nn]);
     }
 }
 
