@@ -93,42 +93,11 @@ __device__ __forceinline__ double lb_kernel_from_z(int id, double z, double sf2,
     }
 }
 
-// Same functors with the per-pair divisions and the square root replaced by host-precomputed reciprocals and a
-// branch-free rsqrt (<= a few ulp from the reference's operation order; K stays within 1e-15 of the Eigen path).
-__device__ __forceinline__ double lb_rsqrt_nr(double x)
-{
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    const double h = 0.5 * x;
-    r = fma(r, fma(-h * r, r, 0.5), r);
-    r = fma(r, fma(-h * r, r, 0.5), r);
-    return r;
-}
-__device__ __forceinline__ double lb_kernel_from_z(int id, double z, const KernParams& kp)
-{
-    switch (id) {
-    case LB_K_SE_ARD:
-        return kp.sf2 * exp(-0.5 * z);
-    case LB_K_MATERN52: {
-        const double d = (z > 0.0) ? z * lb_rsqrt_nr(z) : 0.0;
-        const double term1 = kp.c1 * d;
-        const double term2 = kp.c2 * (d * d);
-        return kp.sf2 * (1 + term1 + term2) * exp(-term1);
-    }
-    case LB_K_MATERN32: {
-        const double d = (z > 0.0) ? z * lb_rsqrt_nr(z) : 0.0;
-        const double term = kp.c1 * d;
-        return kp.sf2 * (1 + term) * exp(-term);
-    }
-    default:
-        return kp.sf2 * exp(-0.5 * (z * kp.c1));
-    }
-}
-
 // exp(t) for t <= 0, branch-free: n = rint(t log2 e), r = t - n ln 2 (two-term), degree-13 Taylor in |r| <= 0.347
-// (truncation < 5e-18), 2^n by an exponent-field add.  Relative error < 3e-16 for t >= -708, exactly 0 below (where
-// the reference's std::exp returns a denormal < 2.3e-308).  Used by the reduced-precision K* build, which is bound by
-// the fp64 pipe: ~18 fp64 instructions and no slow-path branch, so the 32 evaluations of a thread interleave.
+// (truncation < 5e-18), 2^n by an exponent-field add.  Relative error < 3e-16 for t >= -708 (tests/test_gpu_tf32.py),
+// exactly 0 below (where the reference's std::exp returns a denormal < 2.3e-308).  ~18 fp64 instructions and no slow-path
+// branch, so the 32 evaluations a thread holds interleave: the kernel-evaluation loops (K build, K*, gradient) are bound
+// by the fp64 pipe whenever they are not bound by HBM.
 __device__ __forceinline__ double lb_exp_nonpos(double t)
 {
     const double MAGIC = 6755399441055744.0; // 1.5 * 2^52
@@ -154,6 +123,38 @@ __device__ __forceinline__ double lb_exp_nonpos(double t)
     const int hi = __double2hiint(p) + (n << 20);
     const double e = __hiloint2double(hi, __double2loint(p));
     return t < -708.0 ? 0.0 : e;
+}
+
+// Same functors with the per-pair divisions and the square root replaced by host-precomputed reciprocals and a
+// branch-free rsqrt (<= a few ulp from the reference's operation order; K stays within 1e-15 of the Eigen path).
+__device__ __forceinline__ double lb_rsqrt_nr(double x)
+{
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double h = 0.5 * x;
+    r = fma(r, fma(-h * r, r, 0.5), r);
+    r = fma(r, fma(-h * r, r, 0.5), r);
+    return r;
+}
+__device__ __forceinline__ double lb_kernel_from_z(int id, double z, const KernParams& kp)
+{
+    switch (id) {
+    case LB_K_SE_ARD:
+        return kp.sf2 * exp(-0.5 * z); // libm here: the SE-ARD K build is HBM bound with it (0.85 of peak) and compute bound (0.67) with lb_exp_nonpos
+    case LB_K_MATERN52: {
+        const double d = (z > 0.0) ? z * lb_rsqrt_nr(z) : 0.0;
+        const double term1 = kp.c1 * d;
+        const double term2 = kp.c2 * (d * d);
+        return kp.sf2 * (1 + term1 + term2) * lb_exp_nonpos(-term1);
+    }
+    case LB_K_MATERN32: {
+        const double d = (z > 0.0) ? z * lb_rsqrt_nr(z) : 0.0;
+        const double term = kp.c1 * d;
+        return kp.sf2 * (1 + term) * lb_exp_nonpos(-term);
+    }
+    default:
+        return kp.sf2 * exp(-0.5 * (z * kp.c1));
+    }
 }
 
 // Normalised kernel value (sigma_f^2 = 1) from the (scaled) squared distance, kernel id as a template parameter.

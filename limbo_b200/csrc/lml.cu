@@ -251,14 +251,14 @@ grad_kernel(const double* __restrict__ Xs, const double* __restrict__ Kinv, cons
                         double d = sqrt(zz), d_sq = d * d, l_sq = kp.l * kp.l;
                         double term1 = sqrt(5.0) * d / kp.l;
                         double term2 = 5. * d_sq / (3. * l_sq);
-                        double r = exp(-term1);
+                        double r = lb_exp_nonpos(-term1);
                         g0 = kp.sf2 * (r * term1 * (1 + term1 + term2) + (-term1 - 2. * term2) * r);
                         g1 = 2 * kp.sf2 * (1 + term1 + term2) * r;
                     }
                     else if (kp.id == LB_K_MATERN32) { // matern_three_halves.hpp:110-124
                         double d = sqrt(zz);
                         double term = sqrt(3.0) * d / kp.l;
-                        double r = exp(-term);
+                        double r = lb_exp_nonpos(-term);
                         g0 = kp.sf2 * (-term * r + (1 + term) * term * r);
                         g1 = 2 * kp.sf2 * (1 + term) * r;
                     }
