@@ -43,6 +43,30 @@ def test_oracle_loo_reproduces_reference(path, oracle_mod):
     assert np.abs(og.loo_grad(on) - g["loo_grad"]).max() <= 1e-11 * np.abs(g["loo_grad"]).max()
 
 
+def test_oracle_loo_gradient_vs_finite_differences(oracle_mod):
+    """src/tests/test_gp.cpp:273-380 (LOO-CV gradient against central differences; same shape of check, tighter bar)."""
+    rng = np.random.default_rng(3)
+    N, D = 40, 4
+    X = rng.uniform(-1.0, 1.0, (N, D))
+    Y = np.stack([np.cos(X.sum(1)), np.sin(X[:, 0] * 2)], axis=1)
+    og = oracle_mod.OracleGP()
+    og.set_data(X, Y - Y.mean(axis=0))
+
+    def f(hp):
+        og.set_kernel(0, hp, 0.05)
+        og.fit()
+        return og.loo_cv()
+    for trial in range(5):
+        hp = rng.uniform(-1.0, 1.0, D + 1)
+        f(hp)
+        g = og.loo_grad(False)
+        for i in range(D + 1):
+            e = np.zeros(D + 1)
+            e[i] = 1e-5
+            fd = (f(hp + e) - f(hp - e)) / 2e-5
+            assert abs(fd - g[i]) <= 1e-5 * max(1.0, abs(g[i])), (trial, i, fd, g[i])
+
+
 def _mean_policy(params_cls):
     from limbo_b200 import mean
     return mean.function_ard(mean.Constant)
