@@ -83,6 +83,7 @@ struct QueryWs { // per-handle query workspace (guarded by qmutex)
     double* dMean = nullptr; size_t mean_bytes = 0;
     float* dKt = nullptr; size_t kt_bytes = 0;         // TF32 path: K*^T chunk (Mc x Np fp32)
     float* dNorm2 = nullptr; size_t norm2_bytes = 0;
+    double* dBias = nullptr; size_t bias_bytes = 0;    // reduced-precision path: rounding-bias weight per candidate
     int* dErr = nullptr;
 };
 
@@ -220,15 +221,15 @@ void free_ws(QueryWs& w)
 {
     cudaFree(w.dQraw); cudaFree(w.dQs); cudaFree(w.dV); cudaFree(w.dMu); cudaFree(w.dS2); cudaFree(w.dAcq);
     cudaFree(w.dBlkVal); cudaFree(w.dBlkIdx); cudaFree(w.dBest); cudaFree(w.dBestIdx); cudaFree(w.dMean);
-    cudaFree(w.dKt); cudaFree(w.dNorm2); cudaFree(w.dErr);
+    cudaFree(w.dKt); cudaFree(w.dNorm2); cudaFree(w.dErr); cudaFree(w.dBias);
     w = QueryWs();
 }
 
 void free_model(lb_gp* h)
 {
     cudaFree(h->dX); cudaFree(h->dXs); cudaFree(h->dY); cudaFree(h->dL); cudaFree(h->dInvD); cudaFree(h->dAlpha);
-    cudaFree(h->dLinv); cudaFree(h->dKinv); cudaFree(h->dFlags); cudaFree(h->dLinv32); cudaFree(h->dWork);
-    h->dWork = nullptr; h->work_np = 0;
+    cudaFree(h->dLinv); cudaFree(h->dKinv); cudaFree(h->dFlags); cudaFree(h->dLinv32); cudaFree(h->dWork); cudaFree(h->dLinvW);
+    h->dWork = nullptr; h->work_np = 0; h->dLinvW = nullptr; h->linvw_np = 0;
     h->dLinv32 = nullptr; h->linv32_valid = false; h->linv32_rows = 0;
     h->dX = h->dXs = h->dY = h->dL = h->dInvD = h->dAlpha = h->dLinv = h->dKinv = nullptr;
     h->dFlags = nullptr;
@@ -669,7 +670,8 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
             if ((rc = ensure(&w.dQs, &w.qs_bytes, sizeof(double) * De * Mc))) return rc;
             if ((rc = ensure(&w.dKt, &w.kt_bytes, sizeof(float) * (size_t)Mc * h->Np))) return rc;
             if ((rc = ensure(&w.dNorm2, &w.norm2_bytes, sizeof(float) * (size_t)Mc * 4))) return rc; // up to 4 cluster partials
-            if ((rc = ensure(&w.dV, &w.v_bytes, sizeof(double) * (size_t)P * (h->Np / LB_TILE) * Mc))) return rc; // mean partials per training tile
+            if ((rc = ensure(&w.dV, &w.v_bytes, sizeof(double) * (size_t)(P + 1) * (h->Np / LB_TILE) * Mc))) return rc; // mean (+ bias) partials per training tile
+            if ((rc = ensure(&w.dBias, &w.bias_bytes, sizeof(double) * Mc))) return rc;
             if (!w.dErr) LB_CUDA(cudaMalloc(&w.dErr, sizeof(int)));
             LB_CUDA(cudaMemsetAsync(w.dErr, 0, sizeof(int), st));
             for (int64_t m0 = 0; m0 < M; m0 += Mc) {
@@ -678,8 +680,8 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
                 dim3 g1((unsigned)((mcp + 255) / 256), (unsigned)De);
                 pack_soa_kernel<<<g1, 256, 0, st>>>(dQraw + m0 * D, mc, D, w.dQs, mcp, h->kp, 1);
                 h->launches++;
-                if ((rc = lb_launch_kstar_tf32(h, st, mc, w.dQs, mcp, w.dKt, w.dV, w.dMu + m0 * P, &h->launches))) return rc;
-                if ((rc = lb_launch_sigma_tf32(h, st, mc, mcp, w.dKt, w.dNorm2, w.dErr, w.dS2 + m0, &h->launches))) return rc;
+                if ((rc = lb_launch_kstar_tf32(h, st, mc, w.dQs, mcp, w.dKt, w.dV, w.dMu + m0 * P, w.dBias, &h->launches))) return rc;
+                if ((rc = lb_launch_sigma_tf32(h, st, mc, mcp, w.dKt, w.dNorm2, w.dErr, w.dBias, w.dS2 + m0, &h->launches))) return rc;
             }
             if (!out_dev) {
                 int herr = 0;

@@ -296,6 +296,7 @@ struct lb_gp {
     double* dX = nullptr;    // D x Np raw samples (SoA)
     double* dXs = nullptr;   // (D + LB_MAX_LAMBDA) x Np samples staged for the kernel (SE-ARD: x/ell, then A^T x)
     double* dLambda = nullptr; // D x LB_MAX_LAMBDA (SE-ARD A matrix)
+    double* dLinvW = nullptr; int64_t linvw_np = 0; // reduced-precision path: |L^-1 e_k|^2 per column (rounding-bias weights)
     double* dY = nullptr;    // Np x P  obs_mean (col-major), zero padded
     double* dL = nullptr;    // Np x Np K then L (col-major)
     double* dInvD = nullptr; // T x 128 x 128
@@ -351,6 +352,6 @@ int lb_launch_tf32_gemm_norm_cluster(cudaStream_t st, const void* dA, int64_t ld
     int64_t K, int tri, float* dNorm2, int* dErr, int sms, int cl, int f16);
 int lb_tf32_cluster_size();
 int lb_launch_kstar_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const double* dQs, int64_t Mcp, float* dKt, double* dMuPart,
-    double* dMu, long long* launches);
-int lb_launch_sigma_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, int64_t Mcp, const float* dKt, float* dNorm2, int* dErr, double* dS2,
-    long long* launches);
+    double* dMu, double* dBias, long long* launches);
+int lb_launch_sigma_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, int64_t Mcp, const float* dKt, float* dNorm2, int* dErr,
+    const double* dBias, double* dS2, long long* launches);

@@ -853,7 +853,7 @@ constexpr int DCH_WIDE = 16; // input dimensions staged per pass
 template <int KID, bool F16, bool EDGE, int DCH>
 __device__ __forceinline__ void kstar_t32_body(const double* __restrict__ Xs, int64_t Np, int64_t N, const double* __restrict__ Qs, int64_t Mp,
     int64_t M, void* __restrict__ Kt_, int64_t ldk, const KernParams& kp, const double* __restrict__ alpha, int P,
-    double* __restrict__ mu_part, int64_t i_first, int64_t j_first, int64_t ni, int64_t nj)
+    double* __restrict__ mu_part, int64_t i_first, int64_t j_first, int64_t ni, int64_t nj, const double* __restrict__ colw)
 {
     __shared__ __align__(128) double sxi[DCH][LB_TILE];
     __shared__ __align__(128) double sxj[DCH][LB_TILE];
@@ -937,11 +937,23 @@ __device__ __forceinline__ void kstar_t32_body(const double* __restrict__ Xs, in
         }
         // mean partials from the fp64 kernel values: mu_part[(p * ntiles + tile) * Mp + candidate] = sum over this tile's
         // 128 training points (lanes -> warps in a fixed order; the tiles are summed in order by mu_reduce_kernel)
-        for (int p = 0; p < P; ++p) {
-            const double a0 = alpha[(int64_t)p * Np + gi], a1 = alpha[(int64_t)p * Np + gi + 1];
+        // Pass p == P (when colw != nullptr): sum_k k*_k^2 |L^-1 e_k|^2, the weight of the rounding-noise bias of |L^-1 k*|^2
+        // (sigma2_t32_kernel subtracts its expectation).
+        for (int p = 0; p < P + (colw ? 1 : 0); ++p) {
+            const bool bias = (p == P);
+            const double* wv = bias ? colw : alpha + (int64_t)p * Np;
+            const double a0 = wv[gi], a1 = wv[gi + 1];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                double s0 = fma(z[c][1], a1, z[c][0] * a0), s1 = fma(z[c][3], a1, z[c][2] * a0);
+                double s0, s1;
+                if (bias) {
+                    s0 = fma(z[c][1] * z[c][1], a1, z[c][0] * z[c][0] * a0);
+                    s1 = fma(z[c][3] * z[c][3], a1, z[c][2] * z[c][2] * a0);
+                }
+                else {
+                    s0 = fma(z[c][1], a1, z[c][0] * a0);
+                    s1 = fma(z[c][3], a1, z[c][2] * a0);
+                }
 #pragma unroll
                 for (int o = 1; o < 8; o <<= 1) {
                     s0 += __shfl_xor_sync(0xffffffffu, s0, o);
@@ -970,21 +982,42 @@ template <int KID, bool F16, bool EDGE, int DCH>
 __global__ void __launch_bounds__(256, 2)
 kstar_t32_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, const double* __restrict__ Qs, int64_t Mp, int64_t M,
     void* __restrict__ Kt_, int64_t ldk, KernParams kp, const double* __restrict__ alpha, int P,
-    double* __restrict__ mu_part, int64_t i_first, int64_t j_first, int64_t ni, int64_t nj)
+    double* __restrict__ mu_part, int64_t i_first, int64_t j_first, int64_t ni, int64_t nj, const double* __restrict__ colw)
 {
-    kstar_t32_body<KID, F16, EDGE, DCH>(Xs, Np, N, Qs, Mp, M, Kt_, ldk, kp, alpha, P, mu_part, i_first, j_first, ni, nj);
+    kstar_t32_body<KID, F16, EDGE, DCH>(Xs, Np, N, Qs, Mp, M, Kt_, ldk, kp, alpha, P, mu_part, i_first, j_first, ni, nj, colw);
 }
 // mu[c*P + p] = sum over the training tiles of the partials written by kstar_t32_kernel (fixed order)
 __global__ void __launch_bounds__(256)
-mu_reduce_kernel(const double* __restrict__ part, int ntiles, int64_t Mp, int P, int64_t M, double* __restrict__ mu)
+mu_reduce_kernel(const double* __restrict__ part, int ntiles, int64_t Mp, int P, int64_t M, double* __restrict__ mu,
+    double* __restrict__ bias)
 {
     const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (c >= M) return;
-    for (int p = 0; p < P; ++p) {
+    for (int p = 0; p < P + (bias ? 1 : 0); ++p) {
         const double* q = part + (int64_t)p * ntiles * Mp + c;
         double s = 0.0;
         for (int t = 0; t < ntiles; ++t) s += q[(int64_t)t * Mp];
-        mu[c * P + p] = s;
+        if (p < P) mu[c * P + p] = s;
+        else bias[c] = s;
+    }
+}
+
+// w[k] = sum_n Linv[n, k]^2 (column k of the lower-triangular inverse, column-major): one block per column
+__global__ void __launch_bounds__(256)
+colnorm2_kernel(const double* __restrict__ Linv, int64_t ld, double* __restrict__ w)
+{
+    __shared__ double red[8];
+    const int64_t k = blockIdx.x;
+    const double* col = Linv + k * ld;
+    double s = 0.0;
+    for (int64_t n = k + threadIdx.x; n < ld; n += 256) s = fma(col[n], col[n], s);
+    s = lb_warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        w[k] = t;
     }
 }
 
@@ -1023,13 +1056,16 @@ linv_to_rowmajor_kernel(const double* __restrict__ Linv, int64_t ld, void* __res
 
 __global__ void __launch_bounds__(256)
 sigma2_t32_kernel(const float* __restrict__ norm2, int nparts, int64_t part_stride, int64_t M, double kvv, double noise,
-    double norm_unscale, double* __restrict__ s2)
+    double norm_unscale, const double* __restrict__ bias, double bias_coeff, double* __restrict__ s2)
 {
     const int64_t c = blockIdx.x * (int64_t)256 + threadIdx.x;
     if (c >= M) return;
     double nrm = 0.0;
     for (int p = 0; p < nparts; ++p) nrm += (double)norm2[(int64_t)p * part_stride + c]; // partial sums of the cluster's CTAs
-    double res = kvv - nrm * norm_unscale;
+    // Rounding both operands to an 11-bit significand adds zero-mean noise e_n to every D[c, n]; sum_n D^2 then carries the
+    // positive bias E sum e_n^2 = 2 u_r^2 sum_k k*_k^2 |L^-1 e_k|^2 (u_r^2 = E[relative rounding error^2]), which grows with
+    // cond(K) while the zero-mean part does not: subtract its expectation.
+    double res = kvv - (nrm * norm_unscale - (bias ? bias_coeff * bias[c] : 0.0));
     res = (res <= 2.220446049250313e-16) ? 0.0 : res; // gp.hpp:623
     s2[c] = res + noise;                               // gp.hpp:166
 }
@@ -1102,6 +1138,14 @@ int lb_tf32_prepare(lb_gp* h)
     if (f16) linv_to_rowmajor_kernel<true><<<grid, 256, 0, h->stream>>>(h->dLinv, Np, h->dLinv32, Np, scale);
     else linv_to_rowmajor_kernel<false><<<grid, 256, 0, h->stream>>>(h->dLinv, Np, h->dLinv32, Np, 1.0);
     h->launches++;
+    if (!h->dLinvW || h->linvw_np != Np) {
+        if (h->dLinvW) cudaFree(h->dLinvW);
+        h->dLinvW = nullptr;
+        LB_CUDA(cudaMalloc(&h->dLinvW, sizeof(double) * Np));
+        h->linvw_np = Np;
+    }
+    colnorm2_kernel<<<(unsigned)Np, 256, 0, h->stream>>>(h->dLinv, Np, h->dLinvW); // weights of the rounding-bias correction
+    h->launches++;
     LB_CUDA(cudaGetLastError());
     h->linv32_valid = true;
     return LB_OK;
@@ -1113,7 +1157,7 @@ int lb_tf32_prepare(lb_gp* h)
 // the GEMM, the fp64 CTAs made almost no progress while the GEMM CTA was resident and slowed it by 15 %: 272-285 ms per 1M
 // candidates against 256 ms for plain back-to-back launches, profiles/r01_config4_notes.txt.)
 int lb_launch_kstar_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const double* dQs, int64_t Mcp, float* dKt, double* dMuPart,
-    double* dMu, long long* launches)
+    double* dMu, double* dBias, long long* launches)
 {
     using namespace tf32q;
     const bool f16 = (h->precision == 2);
@@ -1127,7 +1171,7 @@ int lb_launch_kstar_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const doub
             if (ib <= ia || jb <= ja) return;
             const int64_t tiles = (ib - ia) * (jb - ja);
             kstar_t32_kernel<decltype(kid)::value, decltype(f16c)::value, decltype(edgec)::value, DCH_WIDE><<<(unsigned)tiles, 256, 0, st>>>(h->dXs, Np,
-                h->N, dQs, Mcp, Mc, dKt, Np, h->kp, h->dAlpha, h->P, dMuPart, ia, ja, ib - ia, jb - ja);
+                h->N, dQs, Mcp, Mc, dKt, Np, h->kp, h->dAlpha, h->P, dMuPart, ia, ja, ib - ia, jb - ja, dBias ? h->dLinvW : nullptr);
             if (launches) ++*launches;
         };
         auto go_prec = [&](auto kid) {
@@ -1148,7 +1192,7 @@ int lb_launch_kstar_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const doub
     }
     {
         LbProfScope ps(h, st, LB_PC_QREDUCE);
-        mu_reduce_kernel<<<(unsigned)((Mc + 255) / 256), 256, 0, st>>>(dMuPart, (int)(Np / LB_TILE), Mcp, h->P, Mc, dMu);
+        mu_reduce_kernel<<<(unsigned)((Mc + 255) / 256), 256, 0, st>>>(dMuPart, (int)(Np / LB_TILE), Mcp, h->P, Mc, dMu, dBias);
     }
     if (launches) ++*launches;
     LB_CUDA(cudaGetLastError());
@@ -1156,8 +1200,8 @@ int lb_launch_kstar_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const doub
 }
 
 // sigma2 (M, fp64 container of a reduced-precision value) from a K*^T chunk: tcgen05 GEMM + row norms, then the clamp / noise of gp.hpp:618-624
-int lb_launch_sigma_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, int64_t Mcp, const float* dKt, float* dNorm2, int* dErr, double* dS2,
-    long long* launches)
+int lb_launch_sigma_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, int64_t Mcp, const float* dKt, float* dNorm2, int* dErr,
+    const double* dBias, double* dS2, long long* launches)
 {
     using namespace tf32q;
     const bool f16 = (h->precision == 2);
@@ -1177,7 +1221,9 @@ int lb_launch_sigma_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, int64_t Mc
     if (rc) return rc;
     // D was computed from (K* kscale) and (L^-1 scale): |V|^2 = norm / (kscale scale)^2
     const double unscale = 1.0 / ((kscale * h->linv32_scale) * (kscale * h->linv32_scale));
-    sigma2_t32_kernel<<<(unsigned)((Mc + 255) / 256), 256, 0, st>>>(dNorm2, cl, Mcp, Mc, h->kp.sf2, h->kp.noise, unscale, dS2);
+    // u_r^2 for round-to-nearest with an 11-bit significand and log-uniform mantissas: (2^-22 / 3) * 0.541; both operands: x 2
+    const double bias_coeff = 2.0 * (1.0 / 4194304.0 / 3.0) * 0.541;
+    sigma2_t32_kernel<<<(unsigned)((Mc + 255) / 256), 256, 0, st>>>(dNorm2, cl, Mcp, Mc, h->kp.sf2, h->kp.noise, unscale, dBias, bias_coeff, dS2);
     if (launches) *launches += 2;
     LB_CUDA(cudaGetLastError());
     return LB_OK;

@@ -3,9 +3,11 @@ fp64 DMMA path on the same model.  Stated tolerances (tf32 has a 10-bit mantissa
 subtracts two O(1) numbers, SURVEY.md §7):  |d sigma^2| <= 4e-3 k(v,v),  |d mu| <= 1e-9 (the mean is accumulated in fp64 from fp64 kernel values);
 the acquisition argmax is judged on the EI value, not on index equality.
 The sigma^2 error is the rounding of the two operands to an 11-bit significand (identical for tf32 and fp16, both rounded to
-nearest): |L^-1 k*|^2 picks up a positive bias ~ u^2 sum_k k*_k^2 |L^-1 e_k|^2 that grows with cond(K); measured maxima with
-tools/reduced_precision_error.py: 2.5e-3 (SE-ARD, N = 1000, D = 12), 2.9e-3 (Matern-5/2, N = 700), 4.2e-3 (Exp, N = 513),
-6.4e-3 (SE-ARD l = 1, N = 4096, D = 6)."""
+nearest).  |L^-1 k*|^2 picks up (a) zero-mean noise and (b) a positive bias 2 u_r^2 sum_k k*_k^2 |L^-1 e_k|^2 that grows with
+cond(K); (b) is subtracted in expectation (sigma2_t32_kernel; the weights come out of the K* build).  Measured maxima
+(tools/reduced_precision_error.py), without -> with the correction: 4.2e-3 -> 2.8e-3 (Exp, N = 513), 2.5e-3 -> 2.0e-3
+(SE-ARD, N = 1000, D = 12), 2.9e-3 -> 2.3e-3 (Matern-5/2, N = 700), 6.4e-3 -> 2.8e-3 (SE-ARD l = 1, N = 4096, D = 6);
+mean error 1e-3 -> 1e-4."""
 import numpy as np
 import pytest
 
@@ -80,9 +82,9 @@ def test_reduced_precision_edge_shapes(kname, N, D, P, M, prec):
     mu32, s32 = g32.query_batch(Xq)
     assert mu32.shape == (M, P) and s32.shape == (M,)
     assert np.abs(mu64 - mu32).max() <= 1e-9
-    assert np.abs(s64 - s32).max() <= 8e-3  # Exp kernel, l = 1: cond(K) is larger than in the cases above (4.2e-3 measured)
+    assert np.abs(s64 - s32).max() <= 4e-3
     # a second, larger batch on the same handle re-uses and grows the workspace
     Xq2 = synth.points(79, 2 * M + 300, D)
     m2, v2 = g32.query_batch(Xq2)
     m3, v3 = g64.query_batch(Xq2)
-    assert np.abs(m2 - m3).max() <= 1e-9 and np.abs(v2 - v3).max() <= 8e-3
+    assert np.abs(m2 - m3).max() <= 1e-9 and np.abs(v2 - v3).max() <= 4e-3

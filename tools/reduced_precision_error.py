@@ -1,5 +1,8 @@
+"""Max / mean error of the reduced-precision (tf32, fp16) variance and mean against the fp64 path on the same model.
+usage: python tools/reduced_precision_error.py"""
 import numpy as np, sys
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from limbo_b200 import kernel, mean, model, synth
 for kname, N, D in [("Exp", 513, 5), ("SquaredExpARD", 1000, 12), ("MaternFiveHalves", 700, 6), ("SquaredExpARD", 4096, 6)]:
     X = synth.points(77, N, D); y = np.cos(3 * X.sum(1)); Xq = synth.points(78, 2000, D)
