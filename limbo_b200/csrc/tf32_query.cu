@@ -850,19 +850,30 @@ constexpr int DCH_WIDE = 16; // input dimensions staged per pass
 // F16: the stored values are k / sigma_f^2 (in (0, 1]) as half.  EDGE: the tile crosses N or M (zero beyond).
 // Tiles [i_first, i_first + ni) x [j_first, j_first + nj) are walked with a grid-stride loop (training index fastest), so the
 // same kernel runs one tile per CTA or as a small persistent grid.
+// Squared distances on the fp64 TENSOR pipe: z_cn = |q_c|^2 + |x_n|^2 - 2 q_c . x_n with the cross term as an
+// mma.m8n8k4.f64 (candidates = M side, training points = N side, input dimensions = K, zero padded to a multiple of 4).
+// ncu on the FMA version of this kernel showed the fp64 ALU pipe 61 % active and the tensor pipe idle, and on the DMMA GEMMs
+// the reverse (profiles/r01_ncu_*): the two are separate pipes, so moving the D-loop (24 of ~55 fp64 operations per pair at
+// D = 12) to DMMA leaves the ALU pipe to exp / scaling / the mean and bias partials.  The cancellation costs ~1e-16 (|q|^2 +
+// |x|^2) absolute on z, i.e. <= 1e-13 relative on k: inside the 1e-9 bar this path states for mu.
+// A thread ends up with candidate g (+ 8 mb) x training points 2t, 2t+1 (+ 8 nb): two consecutive K-major elements = one
+// half2 / float2 store.
+constexpr int XP = LB_TILE + 4; // pitch of the staged point tiles: the (d = t, point = g) fragment loads of a half-warp hit 16 distinct banks
+
 template <int KID, bool F16, bool EDGE, int DCH>
 __device__ __forceinline__ void kstar_t32_body(const double* __restrict__ Xs, int64_t Np, int64_t N, const double* __restrict__ Qs, int64_t Mp,
     int64_t M, void* __restrict__ Kt_, int64_t ldk, const KernParams& kp, const double* __restrict__ alpha, int P,
     double* __restrict__ mu_part, int64_t i_first, int64_t j_first, int64_t ni, int64_t nj, const double* __restrict__ colw)
 {
-    __shared__ __align__(128) double sxi[DCH][LB_TILE];
-    __shared__ __align__(128) double sxj[DCH][LB_TILE];
+    static_assert(DCH % 4 == 0, "k4 steps");
+    __shared__ __align__(128) double sxi[DCH][XP]; // training points of the tile, dimension-major
+    __shared__ __align__(128) double sxj[DCH][XP]; // candidates
+    __shared__ double sni[LB_TILE], snj[LB_TILE];  // squared norms of the staged coordinates
     __shared__ double spm[8][64];
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int li = lane & 7, lj = lane >> 3;
+    const int g = lane >> 2, t = lane & 3;
     const int D = kp.D;
-    const int r0 = warp * 16 + 2 * li;
     if (tid == 0) {
         lb_mbar_init(&bar, 1);
         lb_fence_barrier_init();
@@ -873,15 +884,18 @@ __device__ __forceinline__ void kstar_t32_body(const double* __restrict__ Xs, in
     for (int64_t tile = blockIdx.x; tile < ni * nj; tile += gridDim.x) {
     const int64_t ti = i_first + tile % ni; // training tile index (also the slot of the mean partial)
     const int64_t i0 = ti * LB_TILE, j0 = (j_first + tile / ni) * LB_TILE; // i: training, j: candidates
+    __syncthreads(); // the previous tile's epilogue has read the norms
+    if (tid < LB_TILE) sni[tid] = 0.0;
+    else snj[tid - LB_TILE] = 0.0;
     for (int h = 0; h < 2; ++h) {
-        double z[8][4];
+        double acc[8][2][2]; // [candidate block mb][training block nb][2 consecutive training points]
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+        for (int mb = 0; mb < 8; ++mb)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) z[c][e] = 0.0;
+            for (int nb = 0; nb < 2; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
         for (int pass = 0; pass < npass; ++pass) {
             const int d0 = pass * DCH;
-            const int dc = min(DCH, D - d0);
+            const int dc = min(DCH, D - d0), dc4 = (dc + 3) & ~3;
             if (!(npass == 1 && h == 1)) {
                 __syncthreads();
                 if (tid == 0) {
@@ -892,84 +906,87 @@ __device__ __forceinline__ void kstar_t32_body(const double* __restrict__ Xs, in
                         lb_bulk_g2s(&sxj[d][0], Qs + (int64_t)(d0 + d) * Mp + j0, LB_TILE * sizeof(double), &bar);
                     }
                 }
+                for (int d = dc; d < dc4; ++d) { // zero rows up to the k4 boundary
+                    if (tid < LB_TILE) sxi[d][tid] = 0.0;
+                    else sxj[d][tid - LB_TILE] = 0.0;
+                }
                 lb_mbar_wait(&bar, phase);
                 phase ^= 1;
+                if (h == 0) { // squared norms, accumulated over the passes (one point per thread)
+                    double s = 0.0;
+                    if (tid < LB_TILE) {
+                        for (int d = 0; d < dc; ++d) s = fma(sxi[d][tid], sxi[d][tid], s);
+                        sni[tid] += s;
+                    }
+                    else {
+                        for (int d = 0; d < dc; ++d) s = fma(sxj[d][tid - LB_TILE], sxj[d][tid - LB_TILE], s);
+                        snj[tid - LB_TILE] += s;
+                    }
+                }
+                __syncthreads();
             }
-            for (int d = 0; d < dc; ++d) {
-                const double2 xi = *reinterpret_cast<const double2*>(&sxi[d][r0]);
+            for (int ks = 0; ks < dc4; ks += 4) {
+                const double b0 = sxi[ks + t][warp * 16 + g], b1 = sxi[ks + t][warp * 16 + 8 + g];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const double2 xj = *reinterpret_cast<const double2*>(&sxj[d][h * 64 + c * 8 + 2 * lj]);
-                    double q;
-                    q = xi.x - xj.x; z[c][0] = fma(q, q, z[c][0]);
-                    q = xi.y - xj.x; z[c][1] = fma(q, q, z[c][1]);
-                    q = xi.x - xj.y; z[c][2] = fma(q, q, z[c][2]);
-                    q = xi.y - xj.y; z[c][3] = fma(q, q, z[c][3]);
+                for (int mb = 0; mb < 8; ++mb) {
+                    const double a = sxj[ks + t][h * 64 + mb * 8 + g];
+                    lb_dmma_8x8x4(acc[mb][0][0], acc[mb][0][1], a, b0);
+                    lb_dmma_8x8x4(acc[mb][1][0], acc[mb][1][1], a, b1);
                 }
             }
         }
-        const int64_t gi = i0 + r0;
+        // kernel values (kept in acc for the partial sums), K-major stores
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int64_t gj = j0 + h * 64 + c * 8 + 2 * lj;
-            float v[4];
+        for (int mb = 0; mb < 8; ++mb) {
+            const int cl = h * 64 + mb * 8 + g; // candidate within the tile
+            const int64_t gj = j0 + cl;
+            const double nq = snj[cl];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                double u = lb_unit_kernel_from_z<KID>(z[c][e], kp);
-                if (EDGE) {
-                    const int64_t ii = gi + (e & 1), jj = gj + (e >> 1);
-                    if (ii >= N || jj >= M) u = 0.0;
+            for (int nb = 0; nb < 2; ++nb) {
+                const int tl = warp * 16 + nb * 8 + 2 * t; // training point within the tile (even)
+                const int64_t gi = i0 + tl;
+                float v[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double z = fmax(nq + sni[tl + e] - 2.0 * acc[mb][nb][e], 0.0);
+                    double u = lb_unit_kernel_from_z<KID>(z, kp);
+                    if (EDGE) {
+                        if (gi + e >= N || gj >= M) u = 0.0;
+                    }
+                    const double k = kp.sf2 * u;
+                    acc[mb][nb][e] = k;
+                    v[e] = (float)(F16 ? u : k);
                 }
-                const double k = kp.sf2 * u;
-                z[c][e] = k;
-                v[e] = (float)(F16 ? u : k);
-            }
-            if (F16) {
-                __half* Kt = reinterpret_cast<__half*>(Kt_);
-                *reinterpret_cast<__half2*>(&Kt[gj * ldk + gi]) = __floats2half2_rn(v[0], v[1]);
-                *reinterpret_cast<__half2*>(&Kt[(gj + 1) * ldk + gi]) = __floats2half2_rn(v[2], v[3]);
-            }
-            else {
-                float* Kt = reinterpret_cast<float*>(Kt_);
-                *reinterpret_cast<float2*>(&Kt[gj * ldk + gi]) = make_float2(tf32_rna(v[0]), tf32_rna(v[1]));
-                *reinterpret_cast<float2*>(&Kt[(gj + 1) * ldk + gi]) = make_float2(tf32_rna(v[2]), tf32_rna(v[3]));
+                if (F16) *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(Kt_) + gj * ldk + gi) = __floats2half2_rn(v[0], v[1]);
+                else *reinterpret_cast<float2*>(reinterpret_cast<float*>(Kt_) + gj * ldk + gi) = make_float2(tf32_rna(v[0]), tf32_rna(v[1]));
             }
         }
         // mean partials from the fp64 kernel values: mu_part[(p * ntiles + tile) * Mp + candidate] = sum over this tile's
-        // 128 training points (lanes -> warps in a fixed order; the tiles are summed in order by mu_reduce_kernel)
+        // 128 training points (lanes -> warps in a fixed order; the tiles are summed in order by mu_reduce_kernel).
         // Pass p == P (when colw != nullptr): sum_k k*_k^2 |L^-1 e_k|^2, the weight of the rounding-noise bias of |L^-1 k*|^2
         // (sigma2_t32_kernel subtracts its expectation).
         for (int p = 0; p < P + (colw ? 1 : 0); ++p) {
             const bool bias = (p == P);
-            const double* wv = bias ? colw : alpha + (int64_t)p * Np;
-            const double a0 = wv[gi], a1 = wv[gi + 1];
+            const double* wv = (bias ? colw : alpha + (int64_t)p * Np) + i0 + warp * 16 + 2 * t;
+            const double w00 = wv[0], w01 = wv[1], w10 = wv[8], w11 = wv[9];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                double s0, s1;
-                if (bias) {
-                    s0 = fma(z[c][1] * z[c][1], a1, z[c][0] * z[c][0] * a0);
-                    s1 = fma(z[c][3] * z[c][3], a1, z[c][2] * z[c][2] * a0);
-                }
-                else {
-                    s0 = fma(z[c][1], a1, z[c][0] * a0);
-                    s1 = fma(z[c][3], a1, z[c][2] * a0);
-                }
-#pragma unroll
-                for (int o = 1; o < 8; o <<= 1) {
-                    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                }
-                if (li == 0) {
-                    spm[warp][c * 8 + 2 * lj] = s0;
-                    spm[warp][c * 8 + 2 * lj + 1] = s1;
-                }
+            for (int mb = 0; mb < 8; ++mb) {
+                double sm;
+                if (bias)
+                    sm = fma(acc[mb][0][0] * acc[mb][0][0], w00, fma(acc[mb][0][1] * acc[mb][0][1], w01,
+                        fma(acc[mb][1][0] * acc[mb][1][0], w10, acc[mb][1][1] * acc[mb][1][1] * w11)));
+                else
+                    sm = fma(acc[mb][0][0], w00, fma(acc[mb][0][1], w01, fma(acc[mb][1][0], w10, acc[mb][1][1] * w11)));
+                sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+                sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+                if (t == 0) spm[warp][mb * 8 + g] = sm;
             }
             __syncthreads();
             if (tid < 64) {
-                double s = spm[0][tid];
+                double sacc = spm[0][tid];
 #pragma unroll
-                for (int w = 1; w < 8; ++w) s += spm[w][tid];
-                mu_part[((int64_t)p * (Np / LB_TILE) + ti) * Mp + j0 + h * 64 + tid] = s;
+                for (int w = 1; w < 8; ++w) sacc += spm[w][tid];
+                mu_part[((int64_t)p * (Np / LB_TILE) + ti) * Mp + j0 + h * 64 + tid] = sacc;
             }
             __syncthreads();
         }
