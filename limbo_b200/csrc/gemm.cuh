@@ -26,9 +26,11 @@ namespace lbg {
 constexpr int BM = 128;
 constexpr int STAGES = 3;
 
-template <int BN_, int WN_, int BK_>
+// DF_ = number of n8-tiles per warp (0 or 1, the last ones) whose 32 x 8 strip is computed with plain DFMA instead of DMMA:
+// ncu shows the fp64 ALU pipe at 0 % while the DMMA (tensor) pipe is the bound of these kernels - they are separate pipes.
+template <int BN_, int WN_, int BK_, int DF_ = 0>
 struct Cfg {
-    static constexpr int BN = BN_, WN = WN_, BK = BK_;
+    static constexpr int BN = BN_, WN = WN_, BK = BK_, DF = DF_;
     static constexpr int THREADS = 128 * WN;
     static constexpr int NT = BN / (8 * WN);      // n8 tiles per warp
     static constexpr int PITCH_A_OC = BM + 4;     // [BK][128+4]
@@ -43,6 +45,7 @@ struct Cfg {
 };
 using CfgWide = Cfg<128, 4, 32>;  // 512 threads, 1 CTA / SM
 using CfgDual = Cfg<64, 2, 16>;   // 256 threads, 2 CTAs / SM
+using CfgDualDF = Cfg<64, 2, 16, 1>; // same, one n8-tile of every warp on the fp64 ALU pipe (experiment: DESIGN.md §4.1)
 using CfgStep = Cfg<64, 4, 32>;   // 512 threads, 64-wide right-hand sides (multi-launch TRSM path)
 
 // Per-thread copy plan for one operand: which 16-byte chunks of a (NOUTER x BK) slab this thread moves.  The
@@ -104,10 +107,11 @@ __device__ __forceinline__ void compute_stage(Acc<C>& acc, const double* sA, con
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;
     const int m_base = wm * 32, n_base = wn * (C::BN / C::WN);
+    constexpr int NTM = C::NT - C::DF; // n8-tiles on the tensor pipe
 #pragma unroll
     for (int k0 = 0; k0 < C::BK; k0 += 4) {
-        // one k4 step: 4 A values (rows g, g+8 of both m16 tiles), NT B values, then 4*NT independent DMMA.8x8x4
-        double a[2][2], b[C::NT];
+        // one k4 step: 4 A values (rows g, g+8 of both m16 tiles), NTM B values, then 4*NTM independent DMMA.8x8x4
+        double a[2][2], b[NTM > 0 ? NTM : 1];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -118,18 +122,41 @@ __device__ __forceinline__ void compute_stage(Acc<C>& acc, const double* sA, con
                 if (NEG_A) a[mt][i] = -a[mt][i];
             }
 #pragma unroll
-        for (int nt = 0; nt < C::NT; ++nt) {
+        for (int nt = 0; nt < NTM; ++nt) {
             int n = n_base + nt * 8 + g;
             int k = k0 + t;
             b[nt] = B_KC ? sB[n * C::PITCH_KC + k] : sB[k * C::PITCH_B_OC + n];
         }
 #pragma unroll
-        for (int nt = 0; nt < C::NT; ++nt)
+        for (int nt = 0; nt < NTM; ++nt)
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
                 lb_dmma_8x8x4(acc.v[mt][nt][0], acc.v[mt][nt][1], a[mt][0], b[nt]);
                 lb_dmma_8x8x4(acc.v[mt][nt][2], acc.v[mt][nt][3], a[mt][1], b[nt]);
             }
+        if (C::DF > 0) {
+            // the last n8-tile on the fp64 ALU pipe, same accumulator layout as a DMMA C fragment: rows g, g+8 (per m16 tile),
+            // columns 2t, 2t+1; every lane needs all four k of the step (the 4 lanes of a row / the 8 lanes of a column pair
+            // read the same words: broadcast)
+            constexpr int nt = C::NT - 1;
+            const int n = n_base + nt * 8 + 2 * t;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = k0 + kk;
+                const double bx = B_KC ? sB[n * C::PITCH_KC + k] : sB[k * C::PITCH_B_OC + n];
+                const double by = B_KC ? sB[(n + 1) * C::PITCH_KC + k] : sB[k * C::PITCH_B_OC + n + 1];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int m = m_base + mt * 16 + g + 8 * i;
+                        double av = A_KC ? sA[m * C::PITCH_KC + k] : sA[k * C::PITCH_A_OC + m];
+                        if (NEG_A) av = -av;
+                        acc.v[mt][nt][2 * i] = fma(av, bx, acc.v[mt][nt][2 * i]);
+                        acc.v[mt][nt][2 * i + 1] = fma(av, by, acc.v[mt][nt][2 * i + 1]);
+                    }
+            }
+        }
     }
 }
 

@@ -12,6 +12,7 @@
 // A non-positive pivot is reported LAPACK-style through info (the reference
 // never checks Eigen's info()).
 #include "gemm.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -270,6 +271,21 @@ syrk_kernel(double* __restrict__ L, int64_t ld, int kb, int kd, int j0, int nc, 
 }
 
 using SyrkCfg = lbg::CfgDual;
+using SyrkCfgDF = lbg::CfgDualDF; // same tile, one n8-tile per warp on the fp64 ALU pipe (LB_SYRK_DF=1)
+static_assert(SyrkCfg::PIPE_BYTES == SyrkCfgDF::PIPE_BYTES && SyrkCfg::THREADS == SyrkCfgDF::THREADS, "same launch shape");
+
+inline bool syrk_df()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LB_SYRK_DF"); v = (e && atoi(e) != 0) ? 1 : 0; }
+    return v != 0;
+}
+// trailing-update launch with the configuration chosen at run time
+#define LB_SYRK_LAUNCH(grid, stream, ...)                                                                              \
+    do {                                                                                                               \
+        if (syrk_df()) syrk_kernel<SyrkCfgDF><<<(grid), SyrkCfg::THREADS, SyrkCfg::PIPE_BYTES, (stream)>>>(__VA_ARGS__); \
+        else syrk_kernel<SyrkCfg><<<(grid), SyrkCfg::THREADS, SyrkCfg::PIPE_BYTES, (stream)>>>(__VA_ARGS__);            \
+    } while (0)
 constexpr int SYRK_SPLIT = LB_TILE / SyrkCfg::BN;
 
 bool g_attr_done = false;
@@ -279,6 +295,7 @@ int set_attrs()
     LB_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTF2_SMEM));
     LB_CUDA(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::CfgWide::PIPE_BYTES));
     LB_CUDA(cudaFuncSetAttribute(syrk_kernel<SyrkCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg::PIPE_BYTES));
+    LB_CUDA(cudaFuncSetAttribute(syrk_kernel<SyrkCfgDF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg::PIPE_BYTES));
     g_attr_done = true;
     return LB_OK;
 }
@@ -351,7 +368,7 @@ int lb_launch_potrf(lb_gp* h)
             }
             {
                 LbProfScope ps(h, side, LB_PC_SYRK_COL);
-                syrk_kernel<SyrkCfg><<<(T - k - 1) * SYRK_SPLIT, SyrkCfg::THREADS, SyrkCfg::PIPE_BYTES, side>>>(h->dL, ld, k, 1, k + 1, 1, T);
+                LB_SYRK_LAUNCH((T - k - 1) * SYRK_SPLIT, side, h->dL, ld, k, 1, k + 1, 1, T);
             }
             {
                 LbProfScope ps(h, side, LB_PC_POTF2);
@@ -374,7 +391,7 @@ int lb_launch_potrf(lb_gp* h)
         const int nca = (T - j0 < 2) ? (T - j0) : 2;
         {
             LbProfScope ps(h, main, LB_PC_SYRK);
-            syrk_kernel<SyrkCfg><<<syrk_tiles(T, j0, nca) * SYRK_SPLIT, SyrkCfg::THREADS, SyrkCfg::PIPE_BYTES, main>>>(h->dL, ld, k, 2, j0, nca, T);
+            LB_SYRK_LAUNCH(syrk_tiles(T, j0, nca) * SYRK_SPLIT, main, h->dL, ld, k, 2, j0, nca, T);
         }
         h->launches++;
         if (side != main) {
@@ -385,7 +402,7 @@ int lb_launch_potrf(lb_gp* h)
         const int ncb = T - j0 - nca;
         if (ncb > 0) {
             LbProfScope ps(h, main, LB_PC_SYRK);
-            syrk_kernel<SyrkCfg><<<syrk_tiles(T, j0 + nca, ncb) * SYRK_SPLIT, SyrkCfg::THREADS, SyrkCfg::PIPE_BYTES, main>>>(h->dL, ld, k, 2, j0 + nca, ncb, T);
+            LB_SYRK_LAUNCH(syrk_tiles(T, j0 + nca, ncb) * SYRK_SPLIT, main, h->dL, ld, k, 2, j0 + nca, ncb, T);
             h->launches++;
         }
     }
@@ -536,7 +553,7 @@ int lb_dchol_panel(lb_gp* h, double* dCols, int64_t Nd, int kpair, double* dInvD
     double* Ib = dInvD - (int64_t)kpair * LB_TILE * LB_TILE;
     potf2_inv_kernel<<<1, 256, POTF2_SMEM, st>>>(Lb, Nd, kpair, Ib, dInfo, 1);
     trsm_panel_kernel<<<T - kpair - 1, lbg::CfgWide::THREADS, lbg::CfgWide::PIPE_BYTES, st>>>(Lb, Nd, kpair, Ib);
-    syrk_kernel<SyrkCfg><<<(T - kpair - 1) * SYRK_SPLIT, SyrkCfg::THREADS, SyrkCfg::PIPE_BYTES, st>>>(Lb, Nd, kpair, 1, kpair + 1, 1, T);
+    LB_SYRK_LAUNCH((T - kpair - 1) * SYRK_SPLIT, st, Lb, Nd, kpair, 1, kpair + 1, 1, T);
     potf2_inv_kernel<<<1, 256, POTF2_SMEM, st>>>(Lb, Nd, kpair + 1, Ib, dInfo, 1);
     h->launches += 4;
     if (kpair + 2 < T) {
