@@ -29,8 +29,8 @@ using Cfg = lbg::CfgWide;
 __global__ void __launch_bounds__(256)
 dk_build_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, KernParams kp, int q, int n_hparams, double* __restrict__ dK)
 {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const int64_t j = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.y * 256 + threadIdx.x; // columns on grid.x (no 65535 limit), 256-row slabs on grid.y
+    const int64_t j = blockIdx.x;
     if (i >= Np) return;
     double out = 0.0;
     if (i < N && j < N) {
@@ -293,7 +293,7 @@ int lb_launch_loo_grad(lb_gp* h, int optimize_noise, double* dGrad)
     double* part_za = h->dScratch + (int64_t)T * Np;
     LbProfScope ps(h, h->stream, LB_PC_GRAD);
     for (int q = 0; q < nh; ++q) {
-        dim3 g1((unsigned)((Np + 255) / 256), (unsigned)Np);
+        dim3 g1((unsigned)Np, (unsigned)((Np + 255) / 256));
         dk_build_kernel<<<g1, 256, 0, h->stream>>>(h->dXs, Np, h->N, h->kp, q, h->n_hparams, h->dWork);
         loo_zeta_kernel<<<T * T, Cfg::THREADS, Cfg::PIPE_BYTES, h->stream>>>(h->dKinv, h->dWork, Np, h->dAlpha, h->P, T, part_zk, part_za);
         loo_grad_reduce_kernel<<<1, 1024, 0, h->stream>>>(h->dKinv, Np, h->N, h->dAlpha, h->P, T, part_zk, part_za, dGrad + q);
@@ -321,7 +321,7 @@ int lb_launch_grad_lambda(lb_gp* h, double* dGrad)
     if ((rc = lb_ensure_scratch(h, sizeof(double) * WDOT_BLOCKS))) return rc;
     const int Dr = h->kp.Draw;
     for (int q = Dr; q < Dr + Dr * h->kp.klam; ++q) {
-        dim3 g1((unsigned)((Np + 255) / 256), (unsigned)Np);
+        dim3 g1((unsigned)Np, (unsigned)((Np + 255) / 256));
         dk_build_kernel<<<g1, 256, 0, h->stream>>>(h->dXs, Np, h->N, h->kp, q, h->n_hparams, h->dWork);
         wdot_kernel<<<WDOT_BLOCKS, 256, 0, h->stream>>>(h->dKinv, h->dWork, Np, h->N, h->dAlpha, h->P, h->dScratch);
         wdot_reduce_kernel<<<1, 256, 0, h->stream>>>(h->dScratch, dGrad + q);

@@ -434,8 +434,8 @@ __global__ void __launch_bounds__(256)
 dchol_build_kernel(const double* __restrict__ Xs, int64_t xs_ld, int64_t N, int64_t Nd, KernParams kp, int rank, int G, int64_t ncols_local,
     double* __restrict__ dLoc)
 {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const int64_t c = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.y * 256 + threadIdx.x; // columns on grid.x (no 65535 limit), 256-row slabs on grid.y
+    const int64_t c = blockIdx.x;
     if (i >= Nd || c >= ncols_local) return;
     const int64_t j = (int64_t)dchol_global_block((int)(c / LB_TILE), rank, G) * LB_TILE + (c % LB_TILE);
     double v;
@@ -531,7 +531,7 @@ int lb_dchol_build(lb_gp* h, int64_t Nd, int rank, int G, int64_t ncols_local, d
     if (!h || !dLoc || Nd % (2 * LB_TILE) || !h->kernel_set || h->N <= 0) return LB_ERR_ARG;
     int rc = lb_launch_scale_x(h);
     if (rc) return rc;
-    dim3 grid((unsigned)((Nd + 255) / 256), (unsigned)ncols_local);
+    dim3 grid((unsigned)ncols_local, (unsigned)((Nd + 255) / 256));
     dchol_build_kernel<<<grid, 256, 0, h->stream>>>(h->dXs, h->Np, h->N, Nd, h->kp, rank, G, ncols_local, dLoc);
     h->launches++;
     LB_CUDA(cudaGetLastError());
