@@ -1,21 +1,26 @@
 // limbo_b200/csrc/tf32_query.cu — reduced-precision candidate scoring on the 5th-generation tensor cores
-// (BASELINE.json config 4: N = 16384, D = 12, 1M EI candidates, tf32).
+// (BASELINE.json config 4: N = 16384, D = 12, 1M EI candidates; LB_PREC_TF32 / LB_PREC_FP16).
 //
 // The per-candidate variance needs |L^-1 k*|^2, i.e. V = L^-1 K* (M N^2 flops, gp.hpp:618-624 once per
 // candidate in the reference).  fp64 has no tcgen05 kind, so the fp64 path runs on DMMA (query.cu).  Here the
-// factor is inverted once in fp64 (lml.cu, recursive trtri), cast to fp32 row-major, and the product
+// factor is inverted once in fp64 (lml.cu, recursive trtri), cast to a row-major tf32 (fp32 container) or fp16 copy, and
 //     D[c, n] = sum_{k <= n} Kt[c, k] * Linv[n, k]          (Kt = K*^T, candidates x training points)
-// runs as a TF32 GEMM on tcgen05.mma with fp32 accumulators in TMEM; the epilogue never writes D: each of the
-// 128 epilogue threads owns one candidate (one TMEM lane) and accumulates sum_n D[c, n]^2 while the next tile's
-// MMAs run into the other half of TMEM.
+// runs on tcgen05.mma with fp32 accumulators in TMEM; the epilogue never writes D: each of the 128 epilogue threads of a
+// CTA owns one candidate (one TMEM lane) and accumulates sum_n D[c, n]^2.
 //
-// Structure of one CTA (persistent, 192 threads):
-//   warp 0      : TMA producer  (cp.async.bulk.tensor 2-D, SWIZZLE_128B boxes of 32 k x {128, 256} rows)
-//   warp 1      : TMEM allocator + MMA issuer (one elected lane: 4 x tcgen05.mma.kind::tf32 m128 n256 k8 per stage,
-//                 tcgen05.commit -> "slot free" / "accumulator full" mbarriers)
-//   warps 2..5  : epilogue (tcgen05.ld 32x32b, squares, per-candidate running sum)
-// 4-stage smem ring (48 KB per stage), 2 x 256 TMEM columns.
-// Every mbarrier wait is bounded: on timeout an error flag is raised instead of hanging the GPU.
+// Kernels (all persistent, 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue; 4-stage shared-memory ring of 128-byte SWIZZLE_128B rows; every mbarrier wait is bounded and
+// raises an error flag instead of hanging the GPU):
+//   pair_gemm_norm_kernel          DEFAULT.  Two CTAs = one MMA pair (tcgen05 ... cta_group::2, UMMA M = 256): each CTA
+//                                  owns 128 candidates and half of every B tile; each A slab feeds two n-tiles (all 512
+//                                  TMEM columns).  24 KB from L2 per 128x256x64-MAC unit instead of 40 KB.
+//   tf32_gemm_norm_cluster_kernel  fallback (LB_TF32_PAIR=0): clusters of 2 / 4 CTAs share the candidate tile by TMA
+//                                  multicast, split the n-tiles, double-buffered accumulators.
+//   tf32_gemm_norm_kernel          single CTA, 128 x 256 tiles (LB_TF32_CLUSTER=1; also the validation entry that can
+//                                  write D).
+// Around them: kstar_t32_kernel (K*^T chunk from fp64 kernel evaluations with the squared distances on the fp64 tensor pipe,
+// mean and rounding-bias partials fused), mu_reduce_kernel, sigma2_t32_kernel (clamp / noise of gp.hpp:623,166 and the
+// rounding-bias correction), linv_to_rowmajor_kernel (+ absmax / colnorm2 for the fp16 scale and the bias weights).
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
