@@ -320,6 +320,20 @@ struct lb_gp {
     void* prof = nullptr; // Profiler* when per-kernel-class event timing is enabled (abi.cu)
 };
 
+// cudaFuncSetAttribute applies to the CURRENT device: once-only flags must be per device (one process may hold handles on
+// several GPUs, e.g. one MultiGP output per device).  need() is true the first time it is called on a device.
+struct LbOncePerDevice {
+    bool done[64] = {};
+    bool need()
+    {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 // per-kernel-class CUDA-event timing (bench.py roofline): no-ops unless enabled
 enum { LB_PC_KBUILD = 0, LB_PC_POTF2, LB_PC_TRSM_PANEL, LB_PC_SYRK, LB_PC_SYRK_COL, LB_PC_TRSV, LB_PC_KSTAR, LB_PC_QSTEP, LB_PC_QREDUCE,
     LB_PC_ACQ, LB_PC_TRTRI, LB_PC_LAUUM, LB_PC_GRAD, LB_PC_OTHER, LB_PC_COUNT };

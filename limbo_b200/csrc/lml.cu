@@ -360,13 +360,12 @@ grad_reduce_kernel(const double* __restrict__ part, int ntiles, int nh, double* 
 }
 
 
-bool g_attr_done = false;
+LbOncePerDevice g_attr_once;
 int set_attrs()
 {
-    if (g_attr_done) return LB_OK;
+    if (!g_attr_once.need()) return LB_OK;
     LB_CUDA(cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::CfgWide::PIPE_BYTES));
     LB_CUDA(cudaFuncSetAttribute(trtri_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::CfgWide::PIPE_BYTES));
-    g_attr_done = true;
     return LB_OK;
 }
 

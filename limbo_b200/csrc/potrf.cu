@@ -288,15 +288,14 @@ inline bool syrk_df()
     } while (0)
 constexpr int SYRK_SPLIT = LB_TILE / SyrkCfg::BN;
 
-bool g_attr_done = false;
+LbOncePerDevice g_attr_once;
 int set_attrs()
 {
-    if (g_attr_done) return LB_OK;
+    if (!g_attr_once.need()) return LB_OK;
     LB_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTF2_SMEM));
     LB_CUDA(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::CfgWide::PIPE_BYTES));
     LB_CUDA(cudaFuncSetAttribute(syrk_kernel<SyrkCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg::PIPE_BYTES));
     LB_CUDA(cudaFuncSetAttribute(syrk_kernel<SyrkCfgDF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg::PIPE_BYTES));
-    g_attr_done = true;
     return LB_OK;
 }
 
@@ -518,7 +517,7 @@ __global__ void dchol_sum_kernel(const double* __restrict__ part, int n, double*
     *out = s;
 }
 
-bool g_dchol_attr = false;
+LbOncePerDevice g_dchol_once;
 
 } // namespace
 
@@ -571,9 +570,8 @@ int lb_dchol_panel(lb_gp* h, double* dCols, int64_t Nd, int kpair, double* dInvD
 int lb_dchol_update(lb_gp* h, double* dLoc, int64_t Nd, const double* dPanel, int kpair, int l0, int l1, int rank, int G)
 {
     if (!h || !dLoc || !dPanel) return LB_ERR_ARG;
-    if (!g_dchol_attr) {
+    if (g_dchol_once.need()) {
         LB_CUDA(cudaFuncSetAttribute(dchol_update_kernel<SyrkCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg::PIPE_BYTES));
-        g_dchol_attr = true;
     }
     const int T = (int)(Nd / LB_TILE);
     int64_t tiles = 0;

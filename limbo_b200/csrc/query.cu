@@ -251,12 +251,11 @@ constexpr size_t step_smem()
     return a + (t > b ? t : b);
 }
 
-bool g_attr_done = false;
+LbOncePerDevice g_attr_once;
 int set_attrs()
 {
-    if (g_attr_done) return LB_OK;
+    if (!g_attr_once.need()) return LB_OK;
     LB_CUDA(cudaFuncSetAttribute(query_step_kernel<StepCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem()));
-    g_attr_done = true;
     return LB_OK;
 }
 
@@ -689,7 +688,7 @@ query_slab_kernel(const double* __restrict__ L, int64_t ld, const double* __rest
     }
 }
 
-bool g_attr = false;
+LbOncePerDevice g_attr_once2;
 
 } // namespace slab
 
@@ -699,9 +698,8 @@ size_t lb_query_fused_scratch_doubles(const lb_gp* h, int grid) { return (size_t
 int lb_launch_query_fused(const lb_gp* h, cudaStream_t st, int64_t M, const double* dQs, int64_t Mp, double* dVscratch,
     int grid, double* dMu, double* dS2, long long* launches)
 {
-    if (!slab::g_attr) {
+    if (slab::g_attr_once2.need()) {
         LB_CUDA(cudaFuncSetAttribute(slab::query_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab::SMEM_BYTES));
-        slab::g_attr = true;
     }
     const int64_t ntiles = (M + 7) / 8;
     // slabs of <= 9 n8-tiles, a multiple of the grid so every CTA gets the same number of slabs

@@ -659,7 +659,7 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K,
     return r == CUDA_SUCCESS ? LB_OK : LB_ERR_CUDA;
 }
 
-bool g_attr = false;
+LbOncePerDevice g_attr_once;
 
 } // namespace tf32q
 
@@ -669,10 +669,9 @@ int lb_launch_tf32_gemm_norm(cudaStream_t st, const void* dA, int64_t lda, const
 {
     using namespace tf32q;
     if (M % BM || N % BN || K % 64) return LB_ERR_ARG;
-    if (!g_attr) {
+    if (g_attr_once.need()) {
         LB_CUDA(cudaFuncSetAttribute(tf32_gemm_norm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         LB_CUDA(cudaFuncSetAttribute(tf32_gemm_norm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        g_attr = true;
     }
     alignas(64) CUtensorMap mapA, mapB;
     int rc;
@@ -692,10 +691,9 @@ static int launch_cluster(cudaStream_t st, const CUtensorMap& mapA, const CUtens
     float* dNorm2, int* dErr, int grid)
 {
     using namespace tf32q;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static LbOncePerDevice attr_once;
+    if (attr_once.need()) {
         LB_CUDA(cudaFuncSetAttribute(tf32_gemm_norm_cluster_kernel<CL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        attr_done = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
@@ -739,10 +737,9 @@ static int launch_pair(cudaStream_t st, const CUtensorMap& mapA, const CUtensorM
     float* dNorm2, int* dErr, int grid)
 {
     using namespace tf32q;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static LbOncePerDevice attr_once;
+    if (attr_once.need()) {
         LB_CUDA(cudaFuncSetAttribute(pair_gemm_norm_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM_BYTES));
-        attr_done = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
