@@ -59,6 +59,10 @@ def load() -> C.CDLL:
         "lb_set_stream": ([p, p], i32),
         "lb_sync": ([p], i32),
         "lb_launch_count": ([p], C.c_longlong),
+        "lb_debug_append_count": ([p], C.c_longlong),
+        "lb_debug_pool_mallocs": ([], C.c_longlong),
+        "lb_debug_pool_hits": ([], C.c_longlong),
+        "lb_pool_trim": ([], i32),
         "lb_set_data": ([p, i64, i32, i32, dp, dp], i32),
         "lb_set_data_dev": ([p, i64, i32, i32, dp, dp], i32),
         "lb_set_kernel": ([p, i32, dp, i32, dbl], i32),

@@ -92,6 +92,8 @@ struct Extra {
     QueryWs ws;
     double* dMisc = nullptr; // small scalars (loglik outputs, grad)
     cudaStream_t own = nullptr; // the handle's own stream (h->stream may point at a caller's stream)
+    double lambda_host[LB_MAX_D * LB_MAX_LAMBDA] = {}; // host mirror of dLambda (lb_set_kernel compares against it)
+    long long n_append = 0; // incremental updates actually taken (tests)
 };
 
 } // namespace
@@ -105,19 +107,37 @@ static inline lb_gp_full* full(const lb_gp* h) { return static_cast<lb_gp_full*>
 namespace {
 
 template <typename T>
-int ensure(T** p, size_t* cap, size_t bytes)
+int ensure(const lb_gp* h, T** p, size_t* cap, size_t bytes)
 {
     if (*cap >= bytes && *p) return LB_OK;
-    if (*p) cudaFree(*p);
+    lb_dfree_sync(h, *p); // kernels in flight may still use the old buffer
     *p = nullptr;
     *cap = 0;
-    size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc((void**)p, want);
-    if (e != cudaSuccess) {
-        lb_set_last_cuda_error(e, __FILE__, __LINE__);
-        return LB_ERR_ALLOC;
-    }
+    const size_t want = bytes + 256;
+    int rc = lb_dalloc(h, p, want);
+    if (rc) return rc;
     *cap = want;
+    return LB_OK;
+}
+
+// Make *p private to h before h writes it (copy-on-write for buffers lb_clone shares).  preserve = keep the contents;
+// otherwise the caller overwrites the whole buffer and the copy is skipped.  A missing buffer is allocated.
+template <typename T>
+int make_unique(lb_gp* h, T** p, size_t bytes, bool preserve, bool* fresh = nullptr)
+{
+    if (fresh) *fresh = false;
+    if (*p && !lb_pool_shared(*p)) return LB_OK;
+    T* n = nullptr;
+    LB_ALLOC(h, n, bytes);
+    if (fresh) *fresh = true;
+    if (*p) {
+        if (preserve) {
+            LB_CUDA(cudaMemcpyAsync(n, *p, bytes, cudaMemcpyDeviceToDevice, h->stream));
+            LB_CUDA(cudaStreamSynchronize(h->stream)); // the other holder may write the buffer once it is its sole owner
+        }
+        lb_pool_free(*p);
+    }
+    *p = n;
     return LB_OK;
 }
 
@@ -217,18 +237,19 @@ __global__ void append_row_kernel(double* __restrict__ L, int64_t np, int64_t n,
     }
 }
 
+// callers synchronise the handle's stream first
 void free_ws(QueryWs& w)
 {
-    cudaFree(w.dQraw); cudaFree(w.dQs); cudaFree(w.dV); cudaFree(w.dMu); cudaFree(w.dS2); cudaFree(w.dAcq);
-    cudaFree(w.dBlkVal); cudaFree(w.dBlkIdx); cudaFree(w.dBest); cudaFree(w.dBestIdx); cudaFree(w.dMean);
-    cudaFree(w.dKt); cudaFree(w.dNorm2); cudaFree(w.dErr); cudaFree(w.dBias);
+    void* all[] = {w.dQraw, w.dQs, w.dV, w.dMu, w.dS2, w.dAcq, w.dBlkVal, w.dBlkIdx, w.dBest, w.dBestIdx, w.dMean, w.dKt, w.dNorm2,
+        w.dErr, w.dBias};
+    for (void* p : all) lb_pool_free(p);
     w = QueryWs();
 }
 
 void free_model(lb_gp* h)
 {
-    cudaFree(h->dX); cudaFree(h->dXs); cudaFree(h->dY); cudaFree(h->dL); cudaFree(h->dInvD); cudaFree(h->dAlpha);
-    cudaFree(h->dLinv); cudaFree(h->dKinv); cudaFree(h->dFlags); cudaFree(h->dLinv32); cudaFree(h->dWork); cudaFree(h->dLinvW);
+    void* all[] = {h->dX, h->dXs, h->dY, h->dL, h->dInvD, h->dAlpha, h->dLinv, h->dKinv, h->dFlags, h->dLinv32, h->dWork, h->dLinvW};
+    for (void* p : all) lb_pool_free(p); // shared buffers (lb_clone) only lose this handle's reference
     h->dWork = nullptr; h->work_np = 0; h->dLinvW = nullptr; h->linvw_np = 0;
     h->dLinv32 = nullptr; h->linv32_valid = false; h->linv32_rows = 0;
     h->dX = h->dXs = h->dY = h->dL = h->dInvD = h->dAlpha = h->dLinv = h->dKinv = nullptr;
@@ -239,15 +260,26 @@ void free_model(lb_gp* h)
 int alloc_model(lb_gp* h, int64_t Np, int D, int P)
 {
     const int64_t T = Np / LB_TILE;
-    LB_CUDA(cudaMalloc(&h->dX, sizeof(double) * D * Np));
-    LB_CUDA(cudaMalloc(&h->dXs, sizeof(double) * (D + LB_MAX_LAMBDA) * Np));
-    LB_CUDA(cudaMalloc(&h->dY, sizeof(double) * P * Np));
-    LB_CUDA(cudaMalloc(&h->dAlpha, sizeof(double) * P * Np));
-    LB_CUDA(cudaMalloc(&h->dL, sizeof(double) * Np * Np));
-    LB_CUDA(cudaMalloc(&h->dInvD, sizeof(double) * T * LB_TILE * LB_TILE));
-    LB_CUDA(cudaMemset(h->dInvD, 0, sizeof(double) * T * LB_TILE * LB_TILE)); // upper triangles stay zero
-    LB_CUDA(cudaMalloc(&h->dFlags, sizeof(int) * (T + 8)));
+    LB_ALLOC(h, h->dX, sizeof(double) * D * Np);
+    LB_ALLOC(h, h->dY, sizeof(double) * P * Np);
+    LB_ALLOC(h, h->dFlags, sizeof(int) * (T + 8));
     h->Np = Np;
+    return LB_OK; // Xs, L, invD, alpha: ensure_fit_buffers (a clone that refits never needs its source's copies)
+}
+
+// Private Xs / L / invD / alpha for a handle that is about to (re)factorise: allocated when missing, replaced without a
+// copy when still shared with a clone (every byte is rewritten by the fit).
+int ensure_fit_buffers(lb_gp* h)
+{
+    const int64_t Np = h->Np, T = Np / LB_TILE;
+    int rc;
+    bool fresh = false;
+    if ((rc = make_unique(h, &h->dXs, sizeof(double) * (h->D + LB_MAX_LAMBDA) * Np, false))) return rc;
+    if ((rc = make_unique(h, &h->dL, sizeof(double) * Np * Np, false))) return rc;
+    if ((rc = make_unique(h, &h->dAlpha, sizeof(double) * h->P * Np, false))) return rc;
+    if ((rc = make_unique(h, &h->dInvD, sizeof(double) * T * LB_TILE * LB_TILE, false, &fresh))) return rc;
+    if (fresh) // the panel kernels only write the lower part of every block; consumers read whole blocks
+        LB_CUDA(cudaMemsetAsync(h->dInvD, 0, sizeof(double) * T * LB_TILE * LB_TILE, h->stream));
     return LB_OK;
 }
 
@@ -271,11 +303,17 @@ int upload_kernel_scaled(lb_gp* h)
 
 int lb_ensure_scratch(lb_gp* h, size_t bytes)
 {
-    return ensure(&h->dScratch, &h->scratch_bytes, bytes);
+    return ensure(h, &h->dScratch, &h->scratch_bytes, bytes);
 }
 
 extern "C" {
 int lb_profile_enable(lb_gp* h, int on);
+
+// Streams and events of destroyed handles are kept for the next lb_create on the same device: a likelihood
+// evaluation clones and destroys one handle (kernel_lf_opt.hpp:79), and stream / event creation is not free either.
+struct Shell { cudaStream_t own = nullptr, side = nullptr; cudaEvent_t ev[6] = {}; };
+static std::mutex g_shell_mu;
+static std::vector<Shell> g_shells[64];
 
 int lb_create(lb_gp** out, int device, int precision)
 {
@@ -283,29 +321,39 @@ int lb_create(lb_gp** out, int device, int precision)
     if (precision != LB_PREC_FP64 && precision != LB_PREC_TF32 && precision != LB_PREC_FP16) return LB_ERR_UNSUPPORTED;
     int ndev = 0;
     LB_CUDA(cudaGetDeviceCount(&ndev));
-    if (device < 0 || device >= ndev) return LB_ERR_ARG;
-    LB_CUDA(cudaSetDevice(device));
+    if (device < 0 || device >= ndev || device >= 64) return LB_ERR_ARG;
     lb_gp_full* h = new (std::nothrow) lb_gp_full();
     if (!h) return LB_ERR_ALLOC;
     h->device = device;
+    DeviceGuard guard(h);
+    if (!guard.ok) { delete h; return LB_ERR_CUDA; }
     h->precision = precision;
-    if (cudaStreamCreateWithFlags(&h->ex.own, cudaStreamNonBlocking) != cudaSuccess) {
-        delete h;
-        return LB_ERR_CUDA;
-    }
-    h->stream = h->ex.own;
-    h->own_stream = true;
+    Shell sh;
+    bool cached = false;
     {
+        std::lock_guard<std::mutex> lk(g_shell_mu);
+        if (!g_shells[device].empty()) { sh = g_shells[device].back(); g_shells[device].pop_back(); cached = true; }
+    }
+    if (!cached) {
+        if (cudaStreamCreateWithFlags(&sh.own, cudaStreamNonBlocking) != cudaSuccess) {
+            delete h;
+            return LB_ERR_CUDA;
+        }
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi) != cudaSuccess) h->side = nullptr;
-        for (int i = 0; i < 6; ++i) cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming);
+        if (cudaStreamCreateWithPriority(&sh.side, cudaStreamNonBlocking, hi) != cudaSuccess) sh.side = nullptr;
+        for (int i = 0; i < 6; ++i) cudaEventCreateWithFlags(&sh.ev[i], cudaEventDisableTiming);
     }
-    if (cudaMalloc(&h->dInfo, 4 * sizeof(int)) != cudaSuccess || cudaMalloc(&h->ex.dMisc, 256 * sizeof(double)) != cudaSuccess) {
-        delete h;
+    h->ex.own = sh.own;
+    h->stream = sh.own;
+    h->own_stream = true;
+    h->side = sh.side;
+    for (int i = 0; i < 6; ++i) h->ev[i] = sh.ev[i];
+    if (lb_dalloc(h, &h->dInfo, 4 * sizeof(int)) || lb_dalloc(h, &h->ex.dMisc, (LB_MAX_HPARAMS + 16) * sizeof(double))) {
+        lb_destroy(h);
         return LB_ERR_ALLOC;
     }
-    cudaMemset(h->dInfo, 0, 4 * sizeof(int));
+    cudaMemsetAsync(h->dInfo, 0, 4 * sizeof(int), h->stream);
     h->kp.id = LB_K_SE_ARD;
     *out = h;
     return LB_OK;
@@ -315,18 +363,30 @@ int lb_destroy(lb_gp* hh)
 {
     if (!hh) return LB_OK;
     lb_gp_full* h = full(hh);
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h);
     cudaStreamSynchronize(h->stream);
+    if (h->ex.own && h->ex.own != h->stream) cudaStreamSynchronize(h->ex.own);
+    if (h->side) cudaStreamSynchronize(h->side);
     lb_profile_enable(h, 0);
     free_model(h);
     free_ws(h->ex.ws);
-    cudaFree(h->dInfo);
-    cudaFree(h->dScratch);
-    cudaFree(h->dLambda);
-    cudaFree(h->ex.dMisc);
-    if (h->ex.own) cudaStreamDestroy(h->ex.own);
-    if (h->side) cudaStreamDestroy(h->side);
-    for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    lb_pool_free(h->dInfo);
+    lb_pool_free(h->dScratch);
+    lb_pool_free(h->dLambda);
+    lb_pool_free(h->ex.dMisc);
+    Shell sh;
+    sh.own = h->ex.own; sh.side = h->side;
+    for (int i = 0; i < 6; ++i) sh.ev[i] = h->ev[i];
+    bool kept = false;
+    if (sh.own && h->device >= 0 && h->device < 64) {
+        std::lock_guard<std::mutex> lk(g_shell_mu);
+        if (g_shells[h->device].size() < 64) { g_shells[h->device].push_back(sh); kept = true; }
+    }
+    if (!kept) {
+        if (sh.own) cudaStreamDestroy(sh.own);
+        if (sh.side) cudaStreamDestroy(sh.side);
+        for (int i = 0; i < 6; ++i) if (sh.ev[i]) cudaEventDestroy(sh.ev[i]);
+    }
     delete h;
     return LB_OK;
 }
@@ -334,6 +394,7 @@ int lb_destroy(lb_gp* hh)
 int lb_set_stream(lb_gp* h, void* s)
 {
     if (!h) return LB_ERR_ARG;
+    LB_DEVICE(h);
     lb_gp_full* f = full(h);
     LB_CUDA(cudaStreamSynchronize(f->stream));
     f->stream = s ? (cudaStream_t)s : f->ex.own;
@@ -343,7 +404,19 @@ int lb_set_stream(lb_gp* h, void* s)
 int lb_sync(lb_gp* h)
 {
     if (!h) return LB_ERR_ARG;
+    LB_DEVICE(h);
     LB_CUDA(cudaStreamSynchronize(h->stream));
+    // device-side wait timeouts of the reduced-precision scoring path, for callers of the *_dev entry points (which
+    // return before the kernels have run)
+    lb_gp_full* f = full(h);
+    if (f->ex.ws.dErr) {
+        int herr = 0;
+        LB_CUDA(cudaMemcpy(&herr, f->ex.ws.dErr, sizeof(int), cudaMemcpyDeviceToHost));
+        if (herr) {
+            LB_CUDA(cudaMemset(f->ex.ws.dErr, 0, sizeof(int)));
+            return LB_ERR_TIMEOUT;
+        }
+    }
     return LB_OK;
 }
 
@@ -354,13 +427,18 @@ static int set_data_common(lb_gp* h, int64_t N, int D, int P, const double* X, c
 {
     if (!h || N < 0 || D < 1 || D > LB_MAX_D || P < 1) return LB_ERR_ARG;
     if (N > 0 && (!X || !Y)) return LB_ERR_ARG;
-    LB_CUDA(cudaSetDevice(h->device));
+    LB_DEVICE(h);
     const int64_t Np = std::max<int64_t>(LB_TILE, (N + LB_TILE - 1) / LB_TILE * LB_TILE);
     if (Np != h->Np || D != h->D || P != h->P) {
         LB_CUDA(cudaStreamSynchronize(h->stream));
         free_model(h);
         int rc = alloc_model(h, Np, D, P);
         if (rc) return rc;
+    }
+    else { // same shape: rewrite in place unless a clone still reads the buffers
+        int rc;
+        if ((rc = make_unique(h, &h->dX, sizeof(double) * D * Np, false))) return rc;
+        if ((rc = make_unique(h, &h->dY, sizeof(double) * P * Np, false))) return rc;
     }
     if (D != h->D) h->kp.klam = 0; // the Lambda matrix belongs to the previous input dimension
     h->N = N; h->D = D; h->P = P;
@@ -390,12 +468,12 @@ static int set_data_common(lb_gp* h, int64_t N, int D, int P, const double* X, c
 int lb_dchol_set_points(lb_gp* h, int64_t N, int D, const double* X)
 {
     if (!h || N <= 0 || D < 1 || D > LB_MAX_D || !X) return LB_ERR_ARG;
-    LB_CUDA(cudaSetDevice(h->device));
+    LB_DEVICE(h);
     LB_CUDA(cudaStreamSynchronize(h->stream));
     free_model(h);
     const int64_t Np = (N + LB_TILE - 1) / LB_TILE * LB_TILE;
-    LB_CUDA(cudaMalloc(&h->dX, sizeof(double) * D * Np));
-    LB_CUDA(cudaMalloc(&h->dXs, sizeof(double) * (D + LB_MAX_LAMBDA) * Np));
+    LB_ALLOC(h, h->dX, sizeof(double) * D * Np);
+    LB_ALLOC(h, h->dXs, sizeof(double) * (D + LB_MAX_LAMBDA) * Np);
     h->Np = Np;
     if (D != h->D) h->kp.klam = 0;
     h->N = N; h->D = D; h->P = 0;
@@ -436,6 +514,11 @@ int lb_set_kernel(lb_gp* h, int kernel_id, const double* p, int n_hparams, doubl
     }
     else if (n_hparams != 2)
         return LB_ERR_ARG;
+    LB_DEVICE(h);
+    bool lambda_same = true;
+    const KernParams old = h->kp;
+    const bool was_set = h->kernel_set;
+    const int old_nh = h->n_hparams;
     KernParams& kp = h->kp;
     kp.id = kernel_id;
     kp.Draw = h->D;
@@ -448,8 +531,10 @@ int lb_set_kernel(lb_gp* h, int kernel_id, const double* p, int n_hparams, doubl
         kp.sf2 = std::exp(2.0 * p[n_hparams - 1]);
         kp.l = 1.0;
         if (klam > 0) { // _A(i, j) = p((j + 1) * D + i): already column-major
-            LB_CUDA(cudaSetDevice(h->device));
-            if (!h->dLambda) LB_CUDA(cudaMalloc(&h->dLambda, sizeof(double) * LB_MAX_D * LB_MAX_LAMBDA));
+            if (!h->dLambda) LB_ALLOC(h, h->dLambda, sizeof(double) * LB_MAX_D * LB_MAX_LAMBDA);
+            double* lh = full(h)->ex.lambda_host;
+            lambda_same = (old.klam == klam) && std::memcmp(lh, p + h->D, sizeof(double) * h->D * klam) == 0;
+            std::memcpy(lh, p + h->D, sizeof(double) * h->D * klam);
             LB_CUDA(cudaMemcpyAsync(h->dLambda, p + h->D, sizeof(double) * h->D * klam, cudaMemcpyHostToDevice, h->stream));
             LB_CUDA(cudaStreamSynchronize(h->stream));
             kp.lambda = h->dLambda;
@@ -465,17 +550,24 @@ int lb_set_kernel(lb_gp* h, int kernel_id, const double* p, int n_hparams, doubl
     else if (kernel_id == LB_K_EXP) kp.c1 = 1.0 / (kp.l * kp.l);
     h->n_hparams = n_hparams;
     h->kernel_set = true;
-    h->fitted = false; h->linv_valid = false; h->kinv_valid = false; h->linv32_valid = false;
+    // The same functor state again (add_sample pushes the kernel before every lb_append, gp.hpp:126-152 never touches
+    // it): the factor stays valid.
+    bool same = was_set && old_nh == n_hparams && klam == old.klam && lambda_same && old.id == kp.id && old.D == kp.D && old.Draw == kp.Draw
+        && old.sf2 == kp.sf2 && old.l == kp.l && old.noise == kp.noise && old.c1 == kp.c1 && old.c2 == kp.c2;
+    if (same && kernel_id == LB_K_SE_ARD)
+        for (int d = 0; d < h->D; ++d) same = same && (old.inv_ell[d] == kp.inv_ell[d]);
+    if (!same) { h->fitted = false; h->linv_valid = false; h->kinv_valid = false; h->linv32_valid = false; }
     return LB_OK;
 }
 
 int lb_fit(lb_gp* h)
 {
     if (!h) return LB_ERR_ARG;
-    if (!h->kernel_set || h->Np == 0 || !h->dL) return LB_ERR_STATE;
-    LB_CUDA(cudaSetDevice(h->device));
+    if (!h->kernel_set || h->Np == 0 || !h->dX) return LB_ERR_STATE;
+    LB_DEVICE(h);
     if (h->N == 0) return LB_ERR_STATE; // gp.hpp:90 assert(samples.size() != 0)
     int rc;
+    if ((rc = ensure_fit_buffers(h))) return rc;
     if ((rc = lb_launch_scale_x(h))) return rc;
     if ((rc = lb_launch_kbuild(h, h->dL))) return rc;
     if ((rc = lb_launch_potrf(h))) return rc;
@@ -487,8 +579,10 @@ int lb_fit(lb_gp* h)
 int lb_fit_async(lb_gp* h) // same as lb_fit without the final host sync / info read (bench "value" leg)
 {
     if (!h) return LB_ERR_ARG;
-    if (!h->kernel_set || h->Np == 0 || h->N == 0 || !h->dL) return LB_ERR_STATE;
+    if (!h->kernel_set || h->Np == 0 || h->N == 0 || !h->dX) return LB_ERR_STATE;
+    LB_DEVICE(h);
     int rc;
+    if ((rc = ensure_fit_buffers(h))) return rc;
     if ((rc = lb_launch_scale_x(h))) return rc;
     if ((rc = lb_launch_kbuild(h, h->dL))) return rc;
     if ((rc = lb_launch_potrf(h))) return rc;
@@ -496,8 +590,20 @@ int lb_fit_async(lb_gp* h) // same as lb_fit without the final host sync / info 
     return lb_launch_solve_alpha(h);
 }
 
-int lb_check_info(lb_gp* h) { return h ? check_info(h) : LB_ERR_ARG; }
-int lb_debug_potf2(lb_gp* h, int k, long long* out, int n) { return h ? lb_debug_potf2_clocks(h, k, out, n) : LB_ERR_ARG; }
+int lb_check_info(lb_gp* h)
+{
+    if (!h) return LB_ERR_ARG;
+    LB_DEVICE(h);
+    return check_info(h);
+}
+int lb_debug_potf2(lb_gp* h, int k, long long* out, int n)
+{
+    if (!h) return LB_ERR_ARG;
+    LB_DEVICE(h);
+    return lb_debug_potf2_clocks(h, k, out, n);
+}
+// testing hook: how many times lb_append took the incremental path on this handle
+long long lb_debug_append_count(const lb_gp* h) { return h ? full(h)->ex.n_append : 0; }
 // testing hook: force the multi-launch (unfused) query path
 int lb_debug_force_unfused_query(lb_gp* h, int on) { if (!h) return LB_ERR_ARG; h->force_unfused = on != 0; return LB_OK; }
 
@@ -505,14 +611,17 @@ int lb_debug_force_unfused_query(lb_gp* h, int on) { if (!h) return LB_ERR_ARG; 
 int lb_stage_kbuild(lb_gp* h)
 {
     if (!h || !h->kernel_set || h->N == 0) return LB_ERR_STATE;
+    LB_DEVICE(h);
     int rc;
+    if ((rc = ensure_fit_buffers(h))) return rc;
     if ((rc = lb_launch_scale_x(h))) return rc;
     h->fitted = false;
     return lb_launch_kbuild(h, h->dL);
 }
 int lb_stage_potrf(lb_gp* h)
 {
-    if (!h || h->N == 0) return LB_ERR_STATE;
+    if (!h || h->N == 0 || !h->dL) return LB_ERR_STATE;
+    LB_DEVICE(h);
     int rc = lb_launch_potrf(h);
     if (!rc) h->fitted = true;
     return rc;
@@ -520,6 +629,7 @@ int lb_stage_potrf(lb_gp* h)
 int lb_stage_alpha(lb_gp* h)
 {
     if (!h || !h->fitted) return LB_ERR_STATE;
+    LB_DEVICE(h);
     return lb_launch_solve_alpha(h);
 }
 
@@ -529,10 +639,11 @@ int lb_load_factor(lb_gp* h, const double* L_colmajor, const double* alpha_colma
 {
     if (!h || !L_colmajor || !alpha_colmajor) return LB_ERR_ARG;
     if (!h->kernel_set || h->N == 0 || h->Np == 0) return LB_ERR_STATE;
-    LB_CUDA(cudaSetDevice(h->device));
+    LB_DEVICE(h);
     const int64_t N = h->N, Np = h->Np;
     const int T = (int)(Np / LB_TILE);
     int rc;
+    if ((rc = ensure_fit_buffers(h))) return rc;
     if ((rc = lb_launch_scale_x(h))) return rc;
     LB_CUDA(cudaMemsetAsync(h->dL, 0, sizeof(double) * Np * Np, h->stream));
     LB_CUDA(cudaMemcpy2DAsync(h->dL, Np * 8, L_colmajor, N * 8, N * 8, N, cudaMemcpyHostToDevice, h->stream));
@@ -551,8 +662,11 @@ int lb_refit_alpha(lb_gp* h, const double* Y)
 {
     if (!h || !Y) return LB_ERR_ARG;
     if (!h->fitted) return LB_ERR_STATE;
+    LB_DEVICE(h);
     int rc = lb_ensure_scratch(h, sizeof(double) * (size_t)h->N * h->P);
     if (rc) return rc;
+    if ((rc = make_unique(h, &h->dY, sizeof(double) * h->P * h->Np, false))) return rc;
+    if ((rc = make_unique(h, &h->dAlpha, sizeof(double) * h->P * h->Np, false))) return rc;
     LB_CUDA(cudaMemcpyAsync(h->dScratch, Y, sizeof(double) * h->N * h->P, cudaMemcpyHostToDevice, h->stream));
     dim3 g2((unsigned)((h->Np + 255) / 256), (unsigned)h->P);
     pad_cols_kernel<<<g2, 256, 0, h->stream>>>(h->dScratch, h->N, h->P, h->dY, h->Np);
@@ -565,7 +679,7 @@ int lb_append(lb_gp* h, const double* x, const double* Yall)
 {
     if (!h || !x || !Yall) return LB_ERR_ARG;
     if (!h->kernel_set) return LB_ERR_STATE;
-    LB_CUDA(cudaSetDevice(h->device));
+    LB_DEVICE(h);
     if (h->N == 0 || !h->fitted) return LB_ERR_STATE; // first sample goes through lb_set_data + lb_fit
     const int64_t n = h->N;
     const int D = h->D, P = h->P;
@@ -574,13 +688,13 @@ int lb_append(lb_gp* h, const double* x, const double* Yall)
         const int64_t oldT = oldNp / LB_TILE, newT = newNp / LB_TILE;
         double *nX, *nXs, *nY, *nA, *nL, *nI; int* nF;
         LB_CUDA(cudaStreamSynchronize(h->stream));
-        LB_CUDA(cudaMalloc(&nX, sizeof(double) * D * newNp));
-        LB_CUDA(cudaMalloc(&nXs, sizeof(double) * (D + LB_MAX_LAMBDA) * newNp));
-        LB_CUDA(cudaMalloc(&nY, sizeof(double) * P * newNp));
-        LB_CUDA(cudaMalloc(&nA, sizeof(double) * P * newNp));
-        LB_CUDA(cudaMalloc(&nL, sizeof(double) * newNp * newNp));
-        LB_CUDA(cudaMalloc(&nI, sizeof(double) * newT * LB_TILE * LB_TILE));
-        LB_CUDA(cudaMalloc(&nF, sizeof(int) * (newT + 8)));
+        LB_ALLOC(h, nX, sizeof(double) * D * newNp);
+        LB_ALLOC(h, nXs, sizeof(double) * (D + LB_MAX_LAMBDA) * newNp);
+        LB_ALLOC(h, nY, sizeof(double) * P * newNp);
+        LB_ALLOC(h, nA, sizeof(double) * P * newNp);
+        LB_ALLOC(h, nL, sizeof(double) * newNp * newNp);
+        LB_ALLOC(h, nI, sizeof(double) * newT * LB_TILE * LB_TILE);
+        LB_ALLOC(h, nF, sizeof(int) * (newT + 8));
         LB_CUDA(cudaMemsetAsync(nX, 0, sizeof(double) * D * newNp, h->stream));
         LB_CUDA(cudaMemsetAsync(nY, 0, sizeof(double) * P * newNp, h->stream));
         LB_CUDA(cudaMemcpy2DAsync(nX, newNp * 8, h->dX, oldNp * 8, oldNp * 8, D, cudaMemcpyDeviceToDevice, h->stream));
@@ -590,8 +704,8 @@ int lb_append(lb_gp* h, const double* x, const double* Yall)
         identity_blocks_kernel<<<(unsigned)(newT - oldT), 256, 0, h->stream>>>(nI, (int)oldT, (int)newT);
         h->launches += 2;
         LB_CUDA(cudaStreamSynchronize(h->stream));
-        cudaFree(h->dX); cudaFree(h->dXs); cudaFree(h->dY); cudaFree(h->dAlpha); cudaFree(h->dL); cudaFree(h->dInvD);
-        cudaFree(h->dFlags); cudaFree(h->dLinv); cudaFree(h->dKinv);
+        lb_pool_free(h->dX); lb_pool_free(h->dXs); lb_pool_free(h->dY); lb_pool_free(h->dAlpha); lb_pool_free(h->dL); lb_pool_free(h->dInvD);
+        lb_pool_free(h->dFlags); lb_pool_free(h->dLinv); lb_pool_free(h->dKinv);
         h->dX = nX; h->dXs = nXs; h->dY = nY; h->dAlpha = nA; h->dL = nL; h->dInvD = nI; h->dFlags = nF;
         h->dLinv = h->dKinv = nullptr;
         h->Np = newNp;
@@ -599,6 +713,16 @@ int lb_append(lb_gp* h, const double* x, const double* Yall)
     const int64_t Np = h->Np;
     int rc = lb_ensure_scratch(h, sizeof(double) * (size_t)((n + 1) * P + D + Np));
     if (rc) return rc;
+    { // copy-on-write: a clone may still read these (the row update keeps the rest of X, L, invD)
+        const int64_t T = Np / LB_TILE;
+        if ((rc = make_unique(h, &h->dX, sizeof(double) * D * Np, true))) return rc;
+        if ((rc = make_unique(h, &h->dL, sizeof(double) * Np * Np, true))) return rc;
+        if ((rc = make_unique(h, &h->dInvD, sizeof(double) * T * LB_TILE * LB_TILE, true))) return rc;
+        if ((rc = make_unique(h, &h->dY, sizeof(double) * P * Np, false))) return rc;
+        if ((rc = make_unique(h, &h->dXs, sizeof(double) * (D + LB_MAX_LAMBDA) * Np, false))) return rc;
+        if ((rc = make_unique(h, &h->dAlpha, sizeof(double) * P * Np, false))) return rc;
+    }
+    full(h)->ex.n_append++;
     double* dYs = h->dScratch;
     double* dx = dYs + (n + 1) * P;
     double* dk = dx + D;
@@ -633,15 +757,15 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
     if (!Xq) return LB_ERR_ARG;
     lb_gp_full* h = full(hc);
     if (h->D <= 0 || !h->kernel_set) return LB_ERR_STATE;
-    LB_CUDA(cudaSetDevice(h->device));
+    LB_DEVICE(h);
     std::lock_guard<std::mutex> lock(h->ex.qmutex);
     QueryWs& w = h->ex.ws;
     cudaStream_t st = h->stream;
     const int D = h->D, De = h->kp.D, P = h->P > 0 ? h->P : 1; // raw / staged input dimension
     const int64_t Mp = (M + LB_TILE - 1) / LB_TILE * LB_TILE;
     int rc;
-    if ((rc = ensure(&w.dMu, &w.mu_bytes, sizeof(double) * M * P))) return rc;
-    if ((rc = ensure(&w.dS2, &w.s2_bytes, sizeof(double) * M))) return rc;
+    if ((rc = ensure(h, &w.dMu, &w.mu_bytes, sizeof(double) * M * P))) return rc;
+    if ((rc = ensure(h, &w.dS2, &w.s2_bytes, sizeof(double) * M))) return rc;
     const bool prior = (h->N == 0 || !h->fitted);
     if (prior && h->N != 0) return LB_ERR_STATE;
     if (prior) { // gp.hpp:161-163: mu = mean(v) (added by the caller), sigma2 = k(v,v) + noise
@@ -652,7 +776,7 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
     else {
         const double* dQraw = Xq;
         if (!xq_dev) {
-            if ((rc = ensure(&w.dQraw, &w.qraw_bytes, sizeof(double) * M * D))) return rc;
+            if ((rc = ensure(h, &w.dQraw, &w.qraw_bytes, sizeof(double) * M * D))) return rc;
             LB_CUDA(cudaMemcpyAsync(w.dQraw, Xq, sizeof(double) * M * D, cudaMemcpyHostToDevice, st));
             dQraw = w.dQraw;
         }
@@ -667,12 +791,12 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
             const int64_t cap = std::max<int64_t>(CH, ((int64_t)4 << 30) / (4 * h->Np) / CH * CH);
             int64_t Mc = (cap >= wave) ? cap / wave * wave : cap;
             Mc = std::min((M + CH - 1) / CH * CH, Mc);
-            if ((rc = ensure(&w.dQs, &w.qs_bytes, sizeof(double) * De * Mc))) return rc;
-            if ((rc = ensure(&w.dKt, &w.kt_bytes, sizeof(float) * (size_t)Mc * h->Np))) return rc;
-            if ((rc = ensure(&w.dNorm2, &w.norm2_bytes, sizeof(float) * (size_t)Mc * 4))) return rc; // up to 4 cluster partials
-            if ((rc = ensure(&w.dV, &w.v_bytes, sizeof(double) * (size_t)(P + 1) * (h->Np / LB_TILE) * Mc))) return rc; // mean (+ bias) partials per training tile
-            if ((rc = ensure(&w.dBias, &w.bias_bytes, sizeof(double) * Mc))) return rc;
-            if (!w.dErr) LB_CUDA(cudaMalloc(&w.dErr, sizeof(int)));
+            if ((rc = ensure(h, &w.dQs, &w.qs_bytes, sizeof(double) * De * Mc))) return rc;
+            if ((rc = ensure(h, &w.dKt, &w.kt_bytes, sizeof(float) * (size_t)Mc * h->Np))) return rc;
+            if ((rc = ensure(h, &w.dNorm2, &w.norm2_bytes, sizeof(float) * (size_t)Mc * 4))) return rc; // up to 4 cluster partials
+            if ((rc = ensure(h, &w.dV, &w.v_bytes, sizeof(double) * (size_t)(P + 1) * (h->Np / LB_TILE) * Mc))) return rc; // mean (+ bias) partials per training tile
+            if ((rc = ensure(h, &w.dBias, &w.bias_bytes, sizeof(double) * Mc))) return rc;
+            if (!w.dErr) LB_ALLOC(h, w.dErr, sizeof(int));
             LB_CUDA(cudaMemsetAsync(w.dErr, 0, sizeof(int), st));
             for (int64_t m0 = 0; m0 < M; m0 += Mc) {
                 const int64_t mc = std::min(Mc, M - m0);
@@ -696,8 +820,8 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
             LB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
             const int64_t ntiles = (M + 7) / 8;
             const int grid = (int)std::min<int64_t>(sms, ntiles);
-            if ((rc = ensure(&w.dQs, &w.qs_bytes, sizeof(double) * De * Mp))) return rc;
-            if ((rc = ensure(&w.dV, &w.v_bytes, sizeof(double) * lb_query_fused_scratch_doubles(h, grid)))) return rc;
+            if ((rc = ensure(h, &w.dQs, &w.qs_bytes, sizeof(double) * De * Mp))) return rc;
+            if ((rc = ensure(h, &w.dV, &w.v_bytes, sizeof(double) * lb_query_fused_scratch_doubles(h, grid)))) return rc;
             dim3 g1((unsigned)((Mp + 255) / 256), (unsigned)De);
             pack_soa_kernel<<<g1, 256, 0, st>>>(dQraw, M, D, w.dQs, Mp, h->kp, 1);
             h->launches++;
@@ -708,8 +832,8 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
         int64_t Mc = Mp;
         const int64_t maxcols = std::max<int64_t>(LB_TILE, ((int64_t)4 << 30) / (8 * h->Np) / LB_TILE * LB_TILE);
         if (Mc > maxcols) Mc = maxcols;
-        if ((rc = ensure(&w.dQs, &w.qs_bytes, sizeof(double) * De * Mc))) return rc;
-        if ((rc = ensure(&w.dV, &w.v_bytes, sizeof(double) * h->Np * Mc))) return rc;
+        if ((rc = ensure(h, &w.dQs, &w.qs_bytes, sizeof(double) * De * Mc))) return rc;
+        if ((rc = ensure(h, &w.dV, &w.v_bytes, sizeof(double) * h->Np * Mc))) return rc;
         for (int64_t m0 = 0; m0 < M; m0 += Mc) {
             const int64_t mc = std::min(Mc, M - m0);
             const int64_t mcp = (mc + LB_TILE - 1) / LB_TILE * LB_TILE;
@@ -723,20 +847,21 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
     if (with_acq) {
         const int nblk = (int)((M + 255) / 256);
         if ((size_t)nblk > w.blk_cap) {
-            cudaFree(w.dBlkVal); cudaFree(w.dBlkIdx);
-            LB_CUDA(cudaMalloc(&w.dBlkVal, sizeof(double) * nblk));
-            LB_CUDA(cudaMalloc(&w.dBlkIdx, sizeof(long long) * nblk));
+            lb_dfree_sync(h, w.dBlkVal); lb_dfree_sync(h, w.dBlkIdx);
+            w.dBlkVal = nullptr; w.dBlkIdx = nullptr; w.blk_cap = 0;
+            LB_ALLOC(h, w.dBlkVal, sizeof(double) * nblk);
+            LB_ALLOC(h, w.dBlkIdx, sizeof(long long) * nblk);
             w.blk_cap = nblk;
         }
         if (!w.dBest) {
-            LB_CUDA(cudaMalloc(&w.dBest, sizeof(double)));
-            LB_CUDA(cudaMalloc(&w.dBestIdx, sizeof(long long)));
+            LB_ALLOC(h, w.dBest, sizeof(double));
+            LB_ALLOC(h, w.dBestIdx, sizeof(long long));
         }
         const double* dMean = nullptr;
         if (mean_at_q) {
             if (out_dev) dMean = mean_at_q;
             else {
-                if ((rc = ensure(&w.dMean, &w.mean_bytes, sizeof(double) * M))) return rc;
+                if ((rc = ensure(h, &w.dMean, &w.mean_bytes, sizeof(double) * M))) return rc;
                 LB_CUDA(cudaMemcpyAsync(w.dMean, mean_at_q, sizeof(double) * M, cudaMemcpyHostToDevice, st));
                 dMean = w.dMean;
             }
@@ -745,7 +870,7 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
         if (acq_out) {
             if (out_dev) dAcq = acq_out;
             else {
-                if ((rc = ensure(&w.dAcq, &w.acq_bytes, sizeof(double) * M))) return rc;
+                if ((rc = ensure(h, &w.dAcq, &w.acq_bytes, sizeof(double) * M))) return rc;
                 dAcq = w.dAcq;
             }
         }
@@ -806,6 +931,7 @@ int lb_log_lik(lb_gp* hh, double* out)
 {
     if (!hh || !out) return LB_ERR_ARG;
     if (!hh->fitted) return LB_ERR_STATE;
+    LB_DEVICE(hh);
     lb_gp_full* h = full(hh);
     int rc = lb_launch_loglik(h, h->ex.dMisc);
     if (rc) return rc;
@@ -821,6 +947,7 @@ int lb_compute_inv_kernel(lb_gp* h)
     if (!h) return LB_ERR_ARG;
     if (!h->fitted) return LB_ERR_STATE;
     if (h->kinv_valid) return LB_OK;
+    LB_DEVICE(h);
     return lb_launch_kinv(h);
 }
 
@@ -828,11 +955,12 @@ int lb_kernel_grad_log_lik(lb_gp* hh, int optimize_noise, double* grad)
 {
     if (!hh || !grad) return LB_ERR_ARG;
     if (!hh->fitted) return LB_ERR_STATE;
+    LB_DEVICE(hh);
     lb_gp_full* h = full(hh);
     int rc;
     if (!h->kinv_valid && (rc = lb_launch_kinv(h))) return rc;
     const int nh = h->n_hparams + (optimize_noise ? 1 : 0);
-    if (nh > 128) return LB_ERR_ARG;
+    if (nh > LB_MAX_HPARAMS) return LB_ERR_ARG;
     if ((rc = lb_launch_grad(h, optimize_noise, h->ex.dMisc + 8))) return rc;
     LB_CUDA(cudaMemcpyAsync(grad, h->ex.dMisc + 8, sizeof(double) * nh, cudaMemcpyDeviceToHost, h->stream));
     LB_CUDA(cudaStreamSynchronize(h->stream));
@@ -843,6 +971,7 @@ int lb_log_loo_cv(lb_gp* hh, double* out)
 {
     if (!hh || !out) return LB_ERR_ARG;
     if (!hh->fitted) return LB_ERR_STATE;
+    LB_DEVICE(hh);
     lb_gp_full* h = full(hh);
     int rc = lb_launch_loo_value(h, h->ex.dMisc + 4);
     if (rc) return rc;
@@ -855,9 +984,10 @@ int lb_kernel_grad_log_loo_cv(lb_gp* hh, int optimize_noise, double* grad)
 {
     if (!hh || !grad) return LB_ERR_ARG;
     if (!hh->fitted) return LB_ERR_STATE;
+    LB_DEVICE(hh);
     lb_gp_full* h = full(hh);
     const int nh = h->n_hparams + (optimize_noise ? 1 : 0);
-    if (nh > 128) return LB_ERR_ARG;
+    if (nh > LB_MAX_HPARAMS) return LB_ERR_ARG;
     int rc = lb_launch_loo_grad(h, optimize_noise, h->ex.dMisc + 8);
     if (rc) return rc;
     LB_CUDA(cudaMemcpyAsync(grad, h->ex.dMisc + 8, sizeof(double) * nh, cudaMemcpyDeviceToHost, h->stream));
@@ -869,15 +999,16 @@ int lb_kinv_obs_mean(lb_gp* h, double* out)
 {
     if (!h || !out) return LB_ERR_ARG;
     if (!h->fitted) return LB_ERR_STATE;
+    LB_DEVICE(h);
     double* dOut = nullptr;
-    LB_CUDA(cudaMalloc(&dOut, sizeof(double) * h->N * h->P));
+    LB_ALLOC(h, dOut, sizeof(double) * h->N * h->P);
     int rc = lb_launch_kinv_obs(h, dOut);
     if (!rc) {
         if (cudaMemcpyAsync(out, dOut, sizeof(double) * h->N * h->P, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess
             || cudaStreamSynchronize(h->stream) != cudaSuccess)
             rc = LB_ERR_CUDA;
     }
-    cudaFree(dOut);
+    lb_dfree_sync(h, dOut);
     return rc;
 }
 
@@ -885,6 +1016,7 @@ int lb_get(lb_gp* h, int what, double* dst)
 {
     if (!h || !dst) return LB_ERR_ARG;
     if (h->N == 0) return LB_ERR_STATE;
+    LB_DEVICE(h);
     const int64_t N = h->N, Np = h->Np;
     int rc;
     if (what == LB_GET_ALPHA) {
@@ -900,6 +1032,7 @@ int lb_get(lb_gp* h, int what, double* dst)
     int lower = 0;
     if (what == LB_GET_K) {
         if (!h->kernel_set) return LB_ERR_STATE;
+        if ((rc = make_unique(h, &h->dXs, sizeof(double) * (h->D + LB_MAX_LAMBDA) * Np, false))) return rc;
         if ((rc = lb_launch_scale_x(h))) return rc;
         if ((rc = lb_launch_kbuild(h, dTmp))) return rc;
         src = dTmp;
@@ -928,37 +1061,44 @@ int lb_get(lb_gp* h, int what, double* dst)
     return LB_OK;
 }
 
+// The copy constructor KernelLFOptimization relies on (model/gp/kernel_lf_opt.hpp:79).  Nothing is copied: the clone
+// references the source's buffers, and whichever of the two writes first (lb_fit, lb_append, lb_set_data, ...) takes a
+// private buffer from the pool at that point (make_unique).  K^-1 / L^-1 are not carried over (the reference's copy
+// keeps _inv_kernel, but every consumer recomputes it after recompute(), and lb_compute_inv_kernel rebuilds it on demand).
 int lb_clone(const lb_gp* src, lb_gp** out)
 {
     if (!src || !out) return LB_ERR_ARG;
+    LB_DEVICE(src);
     lb_gp* h = nullptr;
     int rc = lb_create(&h, src->device, src->precision);
     if (rc) return rc;
-    cudaStream_t st = src->stream;
+    // pending writes of the source (e.g. lb_fit_async) must be complete before another stream reads the shared buffers
+    if (cudaStreamSynchronize(src->stream) != cudaSuccess) { lb_destroy(h); return LB_ERR_CUDA; }
     h->kp = src->kp; h->kernel_set = src->kernel_set; h->n_hparams = src->n_hparams;
     h->N = src->N; h->D = src->D; h->P = src->P;
     h->kp.lambda = nullptr;
-    if (src->kp.klam > 0) { // own copy of the Lambda matrix
-        if (cudaMalloc(&h->dLambda, sizeof(double) * LB_MAX_D * LB_MAX_LAMBDA) != cudaSuccess
-            || cudaMemcpyAsync(h->dLambda, src->dLambda, sizeof(double) * LB_MAX_D * LB_MAX_LAMBDA, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+    std::memcpy(full(h)->ex.lambda_host, full(src)->ex.lambda_host, sizeof(full(h)->ex.lambda_host));
+    if (src->kp.klam > 0) { // own copy of the Lambda matrix (rewritten by every lb_set_kernel)
+        if (lb_dalloc(h, &h->dLambda, sizeof(double) * LB_MAX_D * LB_MAX_LAMBDA)
+            || cudaMemcpyAsync(h->dLambda, src->dLambda, sizeof(double) * LB_MAX_D * LB_MAX_LAMBDA, cudaMemcpyDeviceToDevice, h->stream) != cudaSuccess) {
             lb_destroy(h);
             return LB_ERR_CUDA;
         }
         h->kp.lambda = h->dLambda;
     }
     if (src->Np > 0) {
-        if ((rc = alloc_model(h, src->Np, src->D, src->P))) { lb_destroy(h); return rc; }
-        const int64_t Np = src->Np, T = Np / LB_TILE;
-        cudaMemcpyAsync(h->dX, src->dX, sizeof(double) * src->D * Np, cudaMemcpyDeviceToDevice, st);
-        cudaMemcpyAsync(h->dXs, src->dXs, sizeof(double) * src->kp.D * Np, cudaMemcpyDeviceToDevice, st);
-        cudaMemcpyAsync(h->dY, src->dY, sizeof(double) * src->P * Np, cudaMemcpyDeviceToDevice, st);
+        h->Np = src->Np;
+        auto share = [](double* p) { lb_pool_retain(p); return p; };
+        h->dX = share(src->dX);
+        h->dY = share(src->dY);
+        h->dXs = share(src->dXs);
         if (src->fitted) {
-            cudaMemcpyAsync(h->dAlpha, src->dAlpha, sizeof(double) * src->P * Np, cudaMemcpyDeviceToDevice, st);
-            cudaMemcpyAsync(h->dL, src->dL, sizeof(double) * Np * Np, cudaMemcpyDeviceToDevice, st);
-            cudaMemcpyAsync(h->dInvD, src->dInvD, sizeof(double) * T * LB_TILE * LB_TILE, cudaMemcpyDeviceToDevice, st);
+            h->dAlpha = share(src->dAlpha);
+            h->dL = share(src->dL);
+            h->dInvD = share(src->dInvD);
             h->fitted = true;
         }
-        if (cudaStreamSynchronize(st) != cudaSuccess) { lb_destroy(h); return LB_ERR_CUDA; }
+        if (src->dFlags && lb_dalloc(h, &h->dFlags, sizeof(int) * (src->Np / LB_TILE + 8))) { lb_destroy(h); return LB_ERR_ALLOC; }
     }
     *out = h;
     return LB_OK;
@@ -968,6 +1108,7 @@ int lb_clone(const lb_gp* src, lb_gp** out)
 int lb_profile_enable(lb_gp* h, int on)
 {
     if (!h) return LB_ERR_ARG;
+    LB_DEVICE(h);
     if (on && !h->prof) h->prof = new Profiler();
     if (!on && h->prof) {
         cudaStreamSynchronize(h->stream);
@@ -983,6 +1124,7 @@ int lb_profile_enable(lb_gp* h, int on)
 int lb_profile_read(lb_gp* h, double* ms_out, long long* count_out, int reset)
 {
     if (!h || !h->prof) return LB_ERR_STATE;
+    LB_DEVICE(h);
     Profiler* p = (Profiler*)h->prof;
     LB_CUDA(cudaStreamSynchronize(h->stream));
     std::lock_guard<std::mutex> lk(p->mu);

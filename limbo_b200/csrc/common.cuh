@@ -42,6 +42,7 @@ void lb_set_last_cuda_error(cudaError_t e, const char* file, int line);
 enum { LB_K_SE_ARD = 0, LB_K_MATERN52 = 1, LB_K_MATERN32 = 2, LB_K_EXP = 3 };
 #define LB_MAX_D 64
 #define LB_MAX_LAMBDA 4 // columns of the SE-ARD Lambda matrix (Params::kernel_squared_exp_ard::k)
+#define LB_MAX_HPARAMS (LB_MAX_D * (1 + LB_MAX_LAMBDA) + 2) // SE-ARD: log ell, Lambda columns, log sigma_f, (noise)
 
 // Kernel parameters passed by value to device code.
 struct KernParams {
@@ -320,6 +321,29 @@ struct lb_gp {
     void* prof = nullptr; // Profiler* when per-kernel-class event timing is enabled (abi.cu)
 };
 
+// Every extern "C" entry that takes a handle runs on the handle's device and restores the caller's current device on
+// return (one process may hold handles on several GPUs, e.g. one MultiGP output per device).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(const lb_gp* h)
+    {
+        if (!h) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != h->device && cudaSetDevice(h->device) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) {
+            int cur = -1;
+            if (cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+        }
+    }
+};
+#define LB_DEVICE(h)                        \
+    DeviceGuard lb_dev_guard__(h);          \
+    if (!lb_dev_guard__.ok) return LB_ERR_CUDA
+
 // cudaFuncSetAttribute applies to the CURRENT device: once-only flags must be per device (one process may hold handles on
 // several GPUs, e.g. one MultiGP output per device).  need() is true the first time it is called on a device.
 struct LbOncePerDevice {
@@ -333,6 +357,32 @@ struct LbOncePerDevice {
         return true;
     }
 };
+
+// pooled, reference-counted device buffers (pool.cu): every buffer a handle owns comes from here
+void* lb_pool_alloc(int device, size_t bytes);
+void lb_pool_free(void* p);     // drops one reference; the buffer returns to the pool with the last one
+void lb_pool_retain(void* p);
+bool lb_pool_shared(void* p);   // more than one handle references the buffer
+template <typename T>
+inline int lb_dalloc(const lb_gp* h, T** p, size_t bytes)
+{
+    *p = static_cast<T*>(lb_pool_alloc(h->device, bytes));
+    return *p ? LB_OK : LB_ERR_ALLOC;
+}
+// cudaFree synchronises implicitly, the pool does not: wait for the handle's pending work before a buffer that
+// kernels in flight may still use goes back to the pool
+template <typename H>
+inline void lb_dfree_sync(H* h, void* p)
+{
+    if (!p) return;
+    cudaStreamSynchronize(h->stream);
+    lb_pool_free(p);
+}
+#define LB_ALLOC(h, ptr, bytes)                      \
+    do {                                             \
+        int rc_alloc__ = lb_dalloc((h), &(ptr), (bytes)); \
+        if (rc_alloc__) return rc_alloc__;           \
+    } while (0)
 
 // per-kernel-class CUDA-event timing (bench.py roofline): no-ops unless enabled
 enum { LB_PC_KBUILD = 0, LB_PC_POTF2, LB_PC_TRSM_PANEL, LB_PC_SYRK, LB_PC_SYRK_COL, LB_PC_TRSV, LB_PC_KSTAR, LB_PC_QSTEP, LB_PC_QREDUCE,

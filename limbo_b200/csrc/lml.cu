@@ -386,10 +386,10 @@ int lb_launch_linv(lb_gp* h)
     const int T = (int)(h->Np / LB_TILE);
     const size_t bytes = sizeof(double) * h->Np * h->Np;
     if (!h->dLinv) {
-        LB_CUDA(cudaMalloc(&h->dLinv, bytes));
+        LB_ALLOC(h, h->dLinv, bytes);
         LB_CUDA(cudaMemsetAsync(h->dLinv, 0, bytes, h->stream)); // strict upper part stays zero
     }
-    if (!h->dKinv) LB_CUDA(cudaMalloc(&h->dKinv, bytes)); // doubles as the W workspace of the recursion
+    if (!h->dKinv) LB_ALLOC(h, h->dKinv, bytes); // doubles as the W workspace of the recursion
     LbProfScope ps(h, h->stream, LB_PC_TRTRI);
     trtri_diag_copy_kernel<<<T, 256, 0, h->stream>>>(h->dInvD, h->dLinv, h->Np);
     h->launches++;
@@ -415,7 +415,7 @@ int lb_launch_kinv(lb_gp* h)
         if (rc) return rc;
     }
     const int T = (int)(h->Np / LB_TILE);
-    if (!h->dKinv) LB_CUDA(cudaMalloc(&h->dKinv, sizeof(double) * h->Np * h->Np));
+    if (!h->dKinv) LB_ALLOC(h, h->dKinv, sizeof(double) * h->Np * h->Np);
     LbProfScope ps(h, h->stream, LB_PC_LAUUM);
     lauum_kernel<<<T * (T + 1) / 2, lbg::CfgWide::THREADS, lbg::CfgWide::PIPE_BYTES, h->stream>>>(h->dLinv, h->Np, h->dKinv, T);
     h->launches++;

@@ -282,9 +282,9 @@ int lb_launch_loo_grad(lb_gp* h, int optimize_noise, double* dGrad)
     const int T = (int)(Np / LB_TILE);
     const int nh = h->n_hparams + (optimize_noise ? 1 : 0);
     if (!h->dWork || h->work_np != Np) {
-        if (h->dWork) cudaFree(h->dWork);
+        lb_dfree_sync(h, h->dWork);
         h->dWork = nullptr;
-        LB_CUDA(cudaMalloc(&h->dWork, sizeof(double) * Np * Np));
+        LB_ALLOC(h, h->dWork, sizeof(double) * Np * Np);
         h->work_np = Np;
     }
     if ((rc = lb_ensure_scratch(h, sizeof(double) * (size_t)(h->P + 1) * T * Np))) return rc;
@@ -313,9 +313,9 @@ int lb_launch_grad_lambda(lb_gp* h, double* dGrad)
     if (rc) return rc;
     const int64_t Np = h->Np;
     if (!h->dWork || h->work_np != Np) {
-        if (h->dWork) cudaFree(h->dWork);
+        lb_dfree_sync(h, h->dWork);
         h->dWork = nullptr;
-        LB_CUDA(cudaMalloc(&h->dWork, sizeof(double) * Np * Np));
+        LB_ALLOC(h, h->dWork, sizeof(double) * Np * Np);
         h->work_np = Np;
     }
     if ((rc = lb_ensure_scratch(h, sizeof(double) * WDOT_BLOCKS))) return rc;

@@ -1132,9 +1132,9 @@ int lb_tf32_prepare(lb_gp* h)
     const int64_t Np = h->Np, Nr = (Np + BN * cl - 1) / (BN * cl) * (BN * cl);
     const size_t esz = f16 ? 2 : 4;
     if (!h->dLinv32 || h->linv32_rows != Nr) {
-        if (h->dLinv32) cudaFree(h->dLinv32);
+        lb_dfree_sync(h, h->dLinv32);
         h->dLinv32 = nullptr;
-        LB_CUDA(cudaMalloc((void**)&h->dLinv32, esz * Nr * Np));
+        LB_ALLOC(h, h->dLinv32, esz * Nr * Np);
         h->linv32_rows = Nr;
     }
     double scale = 1.0;
@@ -1158,9 +1158,9 @@ int lb_tf32_prepare(lb_gp* h)
     else linv_to_rowmajor_kernel<false><<<grid, 256, 0, h->stream>>>(h->dLinv, Np, h->dLinv32, Np, 1.0);
     h->launches++;
     if (!h->dLinvW || h->linvw_np != Np) {
-        if (h->dLinvW) cudaFree(h->dLinvW);
+        lb_dfree_sync(h, h->dLinvW);
         h->dLinvW = nullptr;
-        LB_CUDA(cudaMalloc(&h->dLinvW, sizeof(double) * Np));
+        LB_ALLOC(h, h->dLinvW, sizeof(double) * Np);
         h->linvw_np = Np;
     }
     colnorm2_kernel<<<(unsigned)Np, 256, 0, h->stream>>>(h->dLinv, Np, h->dLinvW); // weights of the rounding-bias correction

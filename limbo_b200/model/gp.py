@@ -84,6 +84,10 @@ class GP:
     def launch_count(self) -> int:
         return int(self._lib.lb_launch_count(self._h))
 
+    def append_count(self) -> int:
+        """how many add_sample calls took the incremental Cholesky path (lb_append) on this handle"""
+        return int(self._lib.lb_debug_append_count(self._h))
+
     def _push_kernel(self) -> None:
         k = self._kernel_function
         own = np.ascontiguousarray(k.params(), dtype=np.float64)
@@ -107,8 +111,9 @@ class GP:
         assert len(observations) != 0
         assert len(samples) == len(observations)
         # std::vector<Eigen::VectorXd> in the reference; a 2-D array (one point per row) is taken as is
-        X = np.ascontiguousarray(samples, dtype=np.float64)
-        Y = np.ascontiguousarray(observations, dtype=np.float64)
+        # the reference copies the caller's vectors (gp.hpp:104-105: _samples = samples); never alias the caller's arrays
+        X = np.array(samples, dtype=np.float64, order="C", copy=True)
+        Y = np.array(observations, dtype=np.float64, order="C", copy=True)
         if X.ndim == 1:
             X = X[:, None]
         if Y.ndim == 1:
@@ -426,11 +431,11 @@ class GP:
         if n == 1 or int(self._lib.lb_nb_samples(self._h)) != n - 1:
             self._compute_full_kernel()
             return
-        self._push_kernel()
+        self._push_kernel()  # unchanged functor state keeps the factor (lb_set_kernel compares)
         x = np.ascontiguousarray(self._samples[-1])
         Y = np.asfortranarray(self._obs_mean)
         rc = self._lib.lb_append(self._h, _ptr(x), _ptr(Y))
-        if rc == -3:  # factor not resident (e.g. compute(..., compute_kernel=False) before)
+        if rc == -3:  # factor not resident (compute(..., compute_kernel=False) before, or the h-params changed since the fit)
             self._compute_full_kernel()
             return
         if rc < 0:

@@ -40,12 +40,10 @@ class _KernelLFOptimization:
         self._work = None
 
     def __call__(self, params, compute_grad: bool):
-        # kernel_lf_opt.hpp:79: GP gp(this->_original_gp).  The copy shares nothing
-        # mutable with the original; we keep ONE workspace copy per functor (a
-        # fresh device clone per evaluation would only re-copy identical X/Y).
-        if self._work is None:
-            self._work = self._original_gp.copy()
-        gp = self._work
+        # kernel_lf_opt.hpp:79: GP gp(this->_original_gp) - a fresh copy per evaluation, like the reference.  lb_clone
+        # shares the source's device buffers (copy-on-write) and the refit draws its N x N buffers from the pool, so
+        # after the first evaluation this allocates and copies nothing on the device.
+        gp = self._original_gp.copy()
         gp.kernel_function().set_h_params(np.asarray(params, dtype=np.float64))
         gp.recompute(False)
         lik = gp.compute_log_lik()
@@ -73,9 +71,7 @@ class _KernelLooOptimization:
         self._work = None
 
     def __call__(self, params, compute_grad: bool):
-        if self._work is None:  # kernel_loo_opt.hpp:79 copies the GP per evaluation; one workspace copy is equivalent
-            self._work = self._original_gp.copy()
-        gp = self._work
+        gp = self._original_gp.copy()  # kernel_loo_opt.hpp:79 (device buffers shared copy-on-write / pooled)
         gp.kernel_function().set_h_params(np.asarray(params, dtype=np.float64))
         gp.recompute(False)
         loo = gp.compute_log_loo_cv()
@@ -145,3 +141,18 @@ class _MeanLFOptimization:
         if not compute_grad:
             return _opt.no_grad(lik)
         return lik, gp.compute_mean_grad_log_lik()
+
+
+class ParallelLFOpt(HPOpt):
+    """model/multi_gp/parallel_lf_opt.hpp:57-70: optimise every inner GP of a MultiGP independently with `inner`
+    (an HPOpt class, e.g. KernelLFOpt).  The reference fans the loop over tools::par; the inner GPs here are separate
+    device handles (own streams), the host loop only enqueues work."""
+
+    def __init__(self, params=None, inner=None, optimizer=None):
+        super().__init__(params, optimizer)
+        self._inner = inner if inner is not None else NoLFOpt
+
+    def __call__(self, gp) -> None:
+        self._called = True
+        for g in gp.gp_models():
+            self._inner(self._params, self._optimizer)(g)
