@@ -21,7 +21,9 @@
 #include <limbo/model/gp/kernel_lf_opt.hpp>
 #include <limbo/opt/rprop.hpp>
 #undef protected
+#include <chrono>
 #include <cstring>
+#include <thread>
 
 using namespace limbo;
 
@@ -196,9 +198,59 @@ int run_mean_grad(long N, int D, int Pout, const double* X, const double* Y, dou
     return 0;
 }
 
+// Timing entry (bench.py --impl reference / cpu_baseline): the reference's own GP::compute (gp.hpp:88-116: kernel loops,
+// LLT, alpha) once on the calling thread - Eigen's LLT is single-threaded - then acqui::UCB (ucb.hpp:83-90 -> GP::query,
+// gp.hpp:159-167) over M candidates, one at a time as the reference does, fanned over `nthreads` host threads the way
+// tools::par / opt::ParallelRepeater spread evaluations (query() is const).  Returns seconds for both parts.
+template <typename P, typename Kernel>
+int run_bench(long N, int D, const double* X, const double* Y, double noise, long M, const double* Xq, int nthreads, double* t_fit,
+    double* t_query, double* best, long* best_idx)
+{
+    using clk = std::chrono::steady_clock;
+    P::kernel::set_noise(noise);
+    using GP_t = model::GP<P, Kernel, mean::Data<P>, model::gp::KernelLFOpt<P, opt::Rprop<P>>>;
+    auto samples = rows_of(X, N, D);
+    auto obs = rows_of(Y, N, 1);
+    GP_t gp(D, 1);
+    auto t0 = clk::now();
+    gp.compute(samples, obs);
+    *t_fit = std::chrono::duration<double>(clk::now() - t0).count();
+    auto cands = rows_of(Xq, M, D);
+    std::vector<double> val((size_t)M);
+    acqui::UCB<P, GP_t> a_ucb(gp);
+    t0 = clk::now();
+    {
+        std::vector<std::thread> th;
+        const int nt = nthreads < 1 ? 1 : nthreads;
+        for (int t = 0; t < nt; ++t)
+            th.emplace_back([&, t] {
+                FirstElem afun;
+                for (long q = t; q < M; q += nt) val[(size_t)q] = opt::fun(a_ucb(cands[(size_t)q], afun, false));
+            });
+        for (auto& x : th) x.join();
+    }
+    long bi = 0;
+    for (long q = 1; q < M; ++q)
+        if (val[(size_t)q] > val[(size_t)bi]) bi = q;
+    *t_query = std::chrono::duration<double>(clk::now() - t0).count();
+    if (best) *best = M > 0 ? val[(size_t)bi] : 0.0;
+    if (best_idx) *best_idx = bi;
+    return 0;
+}
+
 } // namespace
 
 extern "C" {
+
+int ref_gp_bench(int kernel_id, long N, int D, const double* X, const double* Y, double noise, long M, const double* Xq, int nthreads,
+    double* t_fit, double* t_query, double* best, long* best_idx)
+{
+    switch (kernel_id) {
+    case 0: return run_bench<Params, kernel::SquaredExpARD<Params>>(N, D, X, Y, noise, M, Xq, nthreads, t_fit, t_query, best, best_idx);
+    case 1: return run_bench<Params, kernel::MaternFiveHalves<Params>>(N, D, X, Y, noise, M, Xq, nthreads, t_fit, t_query, best, best_idx);
+    default: return 1;
+    }
+}
 
 int ref_gp_mean_grad(int kernel_id, long N, int D, int P, const double* X, const double* Y, double noise, const double* hp, int nh,
     const double* mean_hp, int n_mean_hp, double* loglik, double* mean_grad, double* mu_at_x0)

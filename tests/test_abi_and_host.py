@@ -204,16 +204,29 @@ def test_archives_write_the_reference_formats(tmp_path):
 
 
 def test_bench_cpu_legs_run_on_a_tiny_sample(oracle_mod):
-    """bench.py's CPU legs (the oracle port = `--impl reference` arm, and the scipy / LAPACK comparison) on a tiny sample:
-    both produce a positive extrapolated rate, and the two agree on the mathematics (same sigma^2 for a candidate)."""
+    """bench.py's CPU legs (the `--impl reference` arm: oracle/_ref when present, else the oracle port; and the scipy /
+    LAPACK comparison) on a tiny sample: positive extrapolated rates, both CPU kinds, and the roofline table picks the
+    kernel class with the largest share of the step."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     s = bench.cpu_sample(256, 16, 2)
     assert s["t_fit"] > 0 and s["t_query"] > 0
-    assert bench.cpu_extrapolate(s, 256, 16) > 0
+    st = bench.cpu_step(512, 16, 2)
+    assert st["sec"] > 0 and st["sec_fit"] > 0 and st["sec_query"] > 0
+    assert "N=" in bench.sample_text(bench.cpu_kind(), st, 512, 16, 2)
+    if bench.ref_lib() is not None:  # the port leg too
+        bench._REF_LIB = False
+        assert bench.cpu_kind() == "port"
+        s2 = bench.cpu_sample(256, 16, 2)
+        assert s2["t_fit"] > 0 and s2["t_query"] > 0
+        bench._REF_LIB = None
     lap = bench.cpu_lapack_sample(256, 64)
     assert lap is None or lap["value"] > 0
-    cfg = bench.workload_config(1)
-    assert "workload" in cfg
+    cfg = bench.workload_config(4)
+    assert "workload" in cfg and cfg["candidates_per_gpu"] == 2500
+    prof = {"qstep": {"ms_total": 96.0, "launches": 1}, "syrk": {"ms_total": 50.0, "launches": 125}, "kbuild": {"ms_total": 0.4, "launches": 1}}
+    table = bench.roofline_table(prof, 1, 152.0, 16384, 6, 10000)
+    assert table[0]["class"] == "qstep" and abs(table[0]["achieved"] - 1e4 * 16384 ** 2 / 96e-3 / 1e12) < 1e-6
+    assert {r["class"] for r in table} == {"qstep", "syrk", "kbuild"}

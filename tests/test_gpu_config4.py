@@ -1,0 +1,67 @@
+"""Reduced-precision candidate scoring pinned AT CONFIG-4 SIZE (BASELINE.json configs[3]: N=16384, D=12, SquaredExpARD,
+>= 10^5 EI candidates) against the fp64 DMMA path of the same handle type - which is itself pinned to the oracle /
+reference at 1e-10 (tests/test_gpu_parity.py, tests/test_golden.py) and, at this size, by the residual / batch==single
+properties of tests/test_gpu_fullsize.py.
+
+Stated tolerances (model/gp.hpp:618-624 computes sigma^2 = k(v,v) - |L^-1 k*|^2 in fp64; here the GEMM operands carry an
+11-bit significand, fp32 accumulation):
+    |d mu|                <= 1e-9           (the mean never leaves fp64)
+    |d sigma^2|           <= 4e-3 k(v,v)    absolute, every candidate
+    |d sigma^2| / sigma^2 <= 0.25 max, <= 0.05 at the 99th percentile, <= 0.01 median   (sigma^2 floors at the noise 0.01,
+                                                                                        where the absolute bound is 40 %)
+    EI regret             <= 2 %: EI_fp64(argmax EI_reduced) >= 0.98 max EI_fp64
+The measured table goes to gpurun_out/r02_config4_parity.json (committed copy: profiles/r02_config4_parity.json)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reduced_precision_at_config4_size():
+    import torch
+    from limbo_b200 import acqui, kernel, mean, model, synth
+    if torch.cuda.mem_get_info()[0] < 40e9:
+        pytest.skip("needs ~40 GB of device memory")
+    N, D, M = 16384, 12, 131072
+    X = synth.points(1234, N, D)
+    y = synth.targets(X)
+    Xq = synth.points(4321, M, D)
+    kw = dict(kernel=kernel.SquaredExpARD, mean=mean.Data)
+    g64 = model.GP(D, 1, **kw)
+    g64.compute(X, y[:, None])
+    mu64, s64 = g64.query_batch(Xq)
+    ei64 = acqui.EI(g64)
+    best64, i64, v64 = ei64.argmax_batch(Xq, return_values=True)
+    table = {"config": f"N={N}, D={D}, SquaredExpARD (ell=1, sigma_f=1, noise=0.01), M={M} candidates", "sigma2_fp64": {
+        "min": float(s64.min()), "median": float(np.median(s64)), "max": float(s64.max())}, "ei_fp64_max": float(best64), "modes": {}}
+    del g64
+    for prec in ("tf32", "fp16"):
+        g = model.GP(D, 1, precision=prec, **kw)
+        g.compute(X, y[:, None])
+        mu, s2 = g.query_batch(Xq)
+        best, idx, v = acqui.EI(g).argmax_batch(Xq, return_values=True)
+        d = np.abs(s2 - s64)
+        rel = d / s64
+        regret = float((best64 - v64[idx]) / best64) if best64 > 0 else 0.0
+        row = {"max_abs_dmu": float(np.abs(mu - mu64).max()), "max_abs_dsigma2": float(d.max()), "mean_dsigma2": float((s2 - s64).mean()),
+               "rel_dsigma2": {"median": float(np.median(rel)), "p90": float(np.percentile(rel, 90)), "p99": float(np.percentile(rel, 99)),
+                               "p999": float(np.percentile(rel, 99.9)), "max": float(rel.max())},
+               "ei_argmax_same_index": bool(idx == i64), "ei_regret_rel": regret, "max_abs_dei": float(np.abs(v - v64).max()),
+               "ei_rank_of_choice_under_fp64": int((v64 > v64[idx]).sum())}
+        table["modes"][prec] = row
+        del g
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "r02_config4_parity.json"), "w") as f:
+        json.dump(table, f, indent=1)
+    print(json.dumps(table))
+    for prec, row in table["modes"].items():
+        assert row["max_abs_dmu"] <= 1e-9, (prec, row)
+        assert row["max_abs_dsigma2"] <= 4e-3, (prec, row)
+        assert row["rel_dsigma2"]["max"] <= 0.25 and row["rel_dsigma2"]["p99"] <= 0.05 and row["rel_dsigma2"]["median"] <= 0.01, (prec, row)
+        assert row["ei_regret_rel"] <= 0.02, (prec, row)
