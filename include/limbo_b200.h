@@ -69,6 +69,10 @@ typedef struct lb_gp lb_gp;
 /* same path with fp16 operands (same 11-bit significand as tf32, half the operand bytes, twice the tensor rate);
  * K* is scaled by 1/sigma_f^2 and L^-1 by a power of two so that both stay inside the fp16 range */
 #define LB_PREC_FP16 2
+/* fp16 split operands: every operand is hi + 2^-11 lo (two fp16 planes, 22 significant bits), three tensor-core products per
+ * k-step, hi x hi and the cross terms in separate fp32 accumulators, combined and squared in fp64.  About 3x the scoring time of
+ * LB_PREC_FP16; |d sigma^2| ~ 1e-6 k(v,v) at N = 16384 (tests/test_gpu_config4.py) */
+#define LB_PREC_FP16X3 3
 
 /* Lifetime.  Replaces GP(int dim_in, int dim_out) / ~GP / the copy constructor
  * KernelLFOptimization relies on (model/gp/kernel_lf_opt.hpp:79). */

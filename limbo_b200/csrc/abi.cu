@@ -318,7 +318,7 @@ static std::vector<Shell> g_shells[64];
 int lb_create(lb_gp** out, int device, int precision)
 {
     if (!out) return LB_ERR_ARG;
-    if (precision != LB_PREC_FP64 && precision != LB_PREC_TF32 && precision != LB_PREC_FP16) return LB_ERR_UNSUPPORTED;
+    if (precision != LB_PREC_FP64 && precision != LB_PREC_TF32 && precision != LB_PREC_FP16 && precision != LB_PREC_FP16X3) return LB_ERR_UNSUPPORTED;
     int ndev = 0;
     LB_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev || device >= 64) return LB_ERR_ARG;
@@ -780,7 +780,7 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
             LB_CUDA(cudaMemcpyAsync(w.dQraw, Xq, sizeof(double) * M * D, cudaMemcpyHostToDevice, st));
             dQraw = w.dQraw;
         }
-        if (h->precision == LB_PREC_TF32 || h->precision == LB_PREC_FP16) {
+        if (h->precision == LB_PREC_TF32 || h->precision == LB_PREC_FP16 || h->precision == LB_PREC_FP16X3) {
             // reduced-precision variance on tcgen05 (tf32_query.cu); mu is accumulated in fp64 from the fp64 kernel values
             if ((rc = lb_tf32_prepare(h))) return rc;
             // Candidate chunks of k x (SMs / 2 CTA pairs x 256 candidates): whole waves of the persistent tcgen05 GEMM (a 65536
@@ -793,9 +793,10 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
             Mc = std::min((M + CH - 1) / CH * CH, Mc);
             if ((rc = ensure(h, &w.dQs, &w.qs_bytes, sizeof(double) * De * Mc))) return rc;
             if ((rc = ensure(h, &w.dKt, &w.kt_bytes, sizeof(float) * (size_t)Mc * h->Np))) return rc;
-            if ((rc = ensure(h, &w.dNorm2, &w.norm2_bytes, sizeof(float) * (size_t)Mc * 4))) return rc; // up to 4 cluster partials
+            if ((rc = ensure(h, &w.dNorm2, &w.norm2_bytes, sizeof(float) * (size_t)Mc * 4))) return rc; // up to 4 cluster partials (split mode: Mc doubles)
             if ((rc = ensure(h, &w.dV, &w.v_bytes, sizeof(double) * (size_t)(P + 1) * (h->Np / LB_TILE) * Mc))) return rc; // mean (+ bias) partials per training tile
             if ((rc = ensure(h, &w.dBias, &w.bias_bytes, sizeof(double) * Mc))) return rc;
+            double* dBiasUse = (h->precision == LB_PREC_FP16X3) ? nullptr : w.dBias; // 22-bit operands: no rounding-bias term
             if (!w.dErr) LB_ALLOC(h, w.dErr, sizeof(int));
             LB_CUDA(cudaMemsetAsync(w.dErr, 0, sizeof(int), st));
             for (int64_t m0 = 0; m0 < M; m0 += Mc) {
@@ -804,8 +805,8 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
                 dim3 g1((unsigned)((mcp + 255) / 256), (unsigned)De);
                 pack_soa_kernel<<<g1, 256, 0, st>>>(dQraw + m0 * D, mc, D, w.dQs, mcp, h->kp, 1);
                 h->launches++;
-                if ((rc = lb_launch_kstar_tf32(h, st, mc, w.dQs, mcp, w.dKt, w.dV, w.dMu + m0 * P, w.dBias, &h->launches))) return rc;
-                if ((rc = lb_launch_sigma_tf32(h, st, mc, mcp, w.dKt, w.dNorm2, w.dErr, w.dBias, w.dS2 + m0, &h->launches))) return rc;
+                if ((rc = lb_launch_kstar_tf32(h, st, mc, w.dQs, mcp, w.dKt, w.dV, w.dMu + m0 * P, dBiasUse, &h->launches))) return rc;
+                if ((rc = lb_launch_sigma_tf32(h, st, mc, mcp, w.dKt, w.dNorm2, w.dErr, dBiasUse, w.dS2 + m0, &h->launches))) return rc;
             }
             if (!out_dev) {
                 int herr = 0;

@@ -630,6 +630,152 @@ pair_gemm_norm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Split-operand variant of the CTA-pair kernel (LB_PREC_FP16X3): every operand is carried as hi + 2^-11 lo with hi, lo
+// both fp16 (22 significant bits), and
+//     D = A_hi B_hi + 2^-11 (A_hi B_lo + A_lo B_hi)            (the 2^-22 A_lo B_lo term is dropped)
+// is formed from three fp16 MMAs per k-step into TWO fp32 accumulators (acc0 = hi x hi in TMEM columns [0, 256),
+// acc1 = the cross terms in [256, 512)), combined in the epilogue in fp64, where sum_n D^2 is accumulated in fp64 as well.
+// One n-tile (256 rows of L^-1) per pass; otherwise the pipeline of pair_gemm_norm_kernel (both CTAs produce, the leader
+// issues, commits are multicast).  3x the MMA work and 2x the operand bytes of LB_PREC_FP16 buy |d sigma^2| ~ 1e-6 instead
+// of ~2e-3 (tests/test_gpu_config4.py).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SPLIT_STAGES = 3;
+constexpr int SPLIT_STAGE_BYTES = 2 * A_BYTES + 2 * HB_BYTES; // A_hi, A_lo, B_hi half, B_lo half = 64 KB
+constexpr size_t SPLIT_SMEM_BYTES = (size_t)SPLIT_STAGES * SPLIT_STAGE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(THREADS, 1)
+pair_split_gemm_norm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+    const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, int64_t M, int64_t N, int64_t K, int tri,
+    double* __restrict__ norm2, int* __restrict__ err)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + (size_t)SPLIT_STAGES * SPLIT_STAGE_BYTES);
+    uint64_t* empty = full + SPLIT_STAGES;
+    uint64_t* tfull = empty + SPLIT_STAGES;
+    uint64_t* tempty = tfull + 1;
+    uint32_t* tmem_base_s = (uint32_t*)(tempty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int m_pairs = (int)(M / (2 * BM)), n_tiles = (int)(N / BN);
+    constexpr int BKE = bke<true>();
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SPLIT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(lb_smem_u32(tmem_base_s)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_base_s;
+
+    auto kblocks_of = [&](int nt) {
+        const int64_t kend = tri ? (int64_t)(nt + 1) * BN : K;
+        return (int)((kend < K ? kend : K) / BKE);
+    };
+
+    if (warp == 0) {
+        if (lane == 0) { // ===== TMA producer (both CTAs): own A rows (hi, lo), own half of the B tile (hi, lo) =====
+            int s = 0; uint32_t ph = 0; bool ok = true;
+            for (int mt = pair_id; mt < m_pairs && ok; mt += npairs) {
+                for (int nt = 0; nt < n_tiles && ok; ++nt) {
+                    const int kbn = kblocks_of(nt);
+                    for (int kb = 0; kb < kbn; ++kb) {
+                        if (!mbar_wait(&empty[s], ph ^ 1, err)) { ok = false; break; }
+                        uint8_t* sa = smem + (size_t)s * SPLIT_STAGE_BYTES;
+                        const uint32_t lfull = mapa_u32(lb_smem_u32(&full[s]), 0);
+                        if (rank == 0) mbar_expect_tx(&full[s], 2u * (uint32_t)SPLIT_STAGE_BYTES);
+                        tma_load_2d_pair(sa, &mapAh, kb * BKE, mt * 2 * BM + rank * BM, lfull);
+                        tma_load_2d_pair(sa + A_BYTES, &mapAl, kb * BKE, mt * 2 * BM + rank * BM, lfull);
+                        tma_load_2d_pair(sa + 2 * A_BYTES, &mapBh, kb * BKE, nt * BN + rank * (BN / 2), lfull);
+                        tma_load_2d_pair(sa + 2 * A_BYTES + HB_BYTES, &mapBl, kb * BKE, nt * BN + rank * (BN / 2), lfull);
+                        if (++s == SPLIT_STAGES) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    }
+    else if (warp == 1) {
+        if (lane == 0 && rank == 0) { // ===== MMA issuer: leader CTA only =====
+            int s = 0; uint32_t ph = 0; bool ok = true;
+            uint32_t tph = 0;
+            for (int mt = pair_id; mt < m_pairs && ok; mt += npairs) {
+                for (int nt = 0; nt < n_tiles && ok; ++nt) {
+                    const int kbn = kblocks_of(nt);
+                    if (!mbar_wait(tempty, tph ^ 1, err)) { ok = false; break; }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int kb = 0; kb < kbn; ++kb) {
+                        if (!mbar_wait(&full[s], ph, err)) { ok = false; break; }
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sa = lb_smem_u32(smem + (size_t)s * SPLIT_STAGE_BYTES);
+                        const uint64_t ah = make_desc(sa), al = make_desc(sa + A_BYTES), bh = make_desc(sa + 2 * A_BYTES),
+                                       bl = make_desc(sa + 2 * A_BYTES + HB_BYTES);
+#pragma unroll
+                        for (int k = 0; k < MMAS_PER_STAGE; ++k) umma_pair<true>(tmem_base, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), (kb | k) != 0);
+#pragma unroll
+                        for (int k = 0; k < MMAS_PER_STAGE; ++k) {
+                            umma_pair<true>(tmem_base + (uint32_t)BN, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), (kb | k) != 0);
+                            umma_pair<true>(tmem_base + (uint32_t)BN, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), 1);
+                        }
+                        umma_commit_pair(&empty[s]);
+                        if (++s == SPLIT_STAGES) { s = 0; ph ^= 1; }
+                    }
+                    umma_commit_pair(tfull);
+                    tph ^= 1;
+                }
+            }
+        }
+    }
+    else { // ===== epilogue (both CTAs): D = acc0 + 2^-11 acc1 and sum_n D^2, both in fp64 =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t ltempty = mapa_u32(lb_smem_u32(tempty), 0);
+        uint32_t tph = 0; bool ok = true;
+        for (int mt = pair_id; mt < m_pairs && ok; mt += npairs) {
+            double acc = 0.0;
+            for (int nt = 0; nt < n_tiles && ok; ++nt) {
+                if (!mbar_wait_warp(tfull, tph, err)) { ok = false; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(taddr + c, v0);
+                    tmem_ld32(taddr + BN + c, v1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const double d = fma((double)__uint_as_float(v1[j]), 1.0 / 2048.0, (double)__uint_as_float(v0[j]));
+                        acc = fma(d, d, acc);
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(ltempty);
+                tph ^= 1;
+            }
+            if (ok) norm2[(int64_t)mt * 2 * BM + rank * BM + row] = acc;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -711,6 +857,8 @@ static int launch_cluster(cudaStream_t st, const CUtensorMap& mapA, const CUtens
 
 int lb_launch_pair_gemm_norm(cudaStream_t st, const void* dA, int64_t lda, const void* dB, int64_t ldb, int64_t M, int64_t N, int64_t K,
     int tri, float* dNorm2, int* dErr, int sms, int f16);
+int lb_launch_pair_split_gemm_norm(cudaStream_t st, const void* dAh, const void* dAl, int64_t lda, const void* dBh, const void* dBl, int64_t ldb,
+    int64_t M, int64_t N, int64_t K, int tri, double* dNorm2, int* dErr, int sms);
 
 int lb_launch_tf32_gemm_norm_cluster(cudaStream_t st, const void* dA, int64_t lda, const void* dB, int64_t ldb, int64_t M, int64_t N,
     int64_t K, int tri, float* dNorm2, int* dErr, int sms, int cl, int f16)
@@ -769,6 +917,38 @@ int lb_launch_pair_gemm_norm(cudaStream_t st, const void* dA, int64_t lda, const
     if (npairs > M / (2 * BM)) npairs = (int)(M / (2 * BM));
     return f16 ? launch_pair<true>(st, mapA, mapB, M, N, K, tri, dNorm2, dErr, 2 * npairs)
                : launch_pair<false>(st, mapA, mapB, M, N, K, tri, dNorm2, dErr, 2 * npairs);
+}
+
+// Split-operand launch (fp16 hi / lo planes): dA*: M x K, dB*: N x K row-major halves; M % 256 == 0, N % 256 == 0; dNorm2: M doubles.
+int lb_launch_pair_split_gemm_norm(cudaStream_t st, const void* dAh, const void* dAl, int64_t lda, const void* dBh, const void* dBl, int64_t ldb,
+    int64_t M, int64_t N, int64_t K, int tri, double* dNorm2, int* dErr, int sms)
+{
+    using namespace tf32q;
+    if (M % (2 * BM) || N % BN || K % 64) return LB_ERR_ARG;
+    static LbOncePerDevice attr_once;
+    if (attr_once.need()) {
+        LB_CUDA(cudaFuncSetAttribute(pair_split_gemm_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPLIT_SMEM_BYTES));
+    }
+    alignas(64) CUtensorMap mAh, mAl, mBh, mBl;
+    int rc;
+    if ((rc = make_map(&mAh, dAh, M, K, lda, BM, true))) return rc;
+    if ((rc = make_map(&mAl, dAl, M, K, lda, BM, true))) return rc;
+    if ((rc = make_map(&mBh, dBh, N, K, ldb, BN / 2, true))) return rc;
+    if ((rc = make_map(&mBl, dBl, N, K, ldb, BN / 2, true))) return rc;
+    int npairs = sms / 2;
+    if (npairs > M / (2 * BM)) npairs = (int)(M / (2 * BM));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * npairs));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SPLIT_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    LB_CUDA(cudaLaunchKernelEx(&cfg, pair_split_gemm_norm_kernel, mAh, mAl, mBh, mBl, M, N, K, tri, dNorm2, dErr));
+    return LB_OK;
 }
 
 extern "C" int lb_debug_pair_gemm(const void* dA, const void* dB, long long M, long long N, long long K, int tri, float* dNorm2, int f16)
@@ -865,7 +1045,8 @@ constexpr int XP = LB_TILE + 4; // pitch of the staged point tiles: the (d = t, 
 template <int KID, bool F16, bool EDGE, int DCH>
 __device__ __forceinline__ void kstar_t32_body(const double* __restrict__ Xs, int64_t Np, int64_t N, const double* __restrict__ Qs, int64_t Mp,
     int64_t M, void* __restrict__ Kt_, int64_t ldk, const KernParams& kp, const double* __restrict__ alpha, int P,
-    double* __restrict__ mu_part, int64_t i_first, int64_t j_first, int64_t ni, int64_t nj, const double* __restrict__ colw)
+    double* __restrict__ mu_part, int64_t i_first, int64_t j_first, int64_t ni, int64_t nj, const double* __restrict__ colw,
+    void* __restrict__ Kt_lo = nullptr)
 {
     static_assert(DCH % 4 == 0, "k4 steps");
     __shared__ __align__(128) double sxi[DCH][XP]; // training points of the tile, dimension-major
@@ -948,6 +1129,7 @@ __device__ __forceinline__ void kstar_t32_body(const double* __restrict__ Xs, in
                 const int tl = warp * 16 + nb * 8 + 2 * t; // training point within the tile (even)
                 const int64_t gi = i0 + tl;
                 float v[2];
+                double uu[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const double z = fmax(nq + sni[tl + e] - 2.0 * acc[mb][nb][e], 0.0);
@@ -957,9 +1139,18 @@ __device__ __forceinline__ void kstar_t32_body(const double* __restrict__ Xs, in
                     }
                     const double k = kp.sf2 * u;
                     acc[mb][nb][e] = k;
+                    uu[e] = u;
                     v[e] = (float)(F16 ? u : k);
                 }
-                if (F16) *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(Kt_) + gj * ldk + gi) = __floats2half2_rn(v[0], v[1]);
+                if (F16) {
+                    const __half2 hi = __floats2half2_rn(v[0], v[1]);
+                    *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(Kt_) + gj * ldk + gi) = hi;
+                    if (Kt_lo) { // split operands (LB_PREC_FP16X3): lo = (u - hi) * 2^11, the next 11 bits of the value
+                        const float2 hf = __half22float2(hi);
+                        *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(Kt_lo) + gj * ldk + gi)
+                            = __floats2half2_rn((float)((uu[0] - (double)hf.x) * 2048.0), (float)((uu[1] - (double)hf.y) * 2048.0));
+                    }
+                }
                 else *reinterpret_cast<float2*>(reinterpret_cast<float*>(Kt_) + gj * ldk + gi) = make_float2(tf32_rna(v[0]), tf32_rna(v[1]));
             }
         }
@@ -1001,9 +1192,10 @@ template <int KID, bool F16, bool EDGE, int DCH>
 __global__ void __launch_bounds__(256, 2)
 kstar_t32_kernel(const double* __restrict__ Xs, int64_t Np, int64_t N, const double* __restrict__ Qs, int64_t Mp, int64_t M,
     void* __restrict__ Kt_, int64_t ldk, KernParams kp, const double* __restrict__ alpha, int P,
-    double* __restrict__ mu_part, int64_t i_first, int64_t j_first, int64_t ni, int64_t nj, const double* __restrict__ colw)
+    double* __restrict__ mu_part, int64_t i_first, int64_t j_first, int64_t ni, int64_t nj, const double* __restrict__ colw,
+    void* __restrict__ Kt_lo)
 {
-    kstar_t32_body<KID, F16, EDGE, DCH>(Xs, Np, N, Qs, Mp, M, Kt_, ldk, kp, alpha, P, mu_part, i_first, j_first, ni, nj, colw);
+    kstar_t32_body<KID, F16, EDGE, DCH>(Xs, Np, N, Qs, Mp, M, Kt_, ldk, kp, alpha, P, mu_part, i_first, j_first, ni, nj, colw, Kt_lo);
 }
 // mu[c*P + p] = sum over the training tiles of the partials written by kstar_t32_kernel (fixed order)
 __global__ void __launch_bounds__(256)
@@ -1060,17 +1252,33 @@ absmax_kernel(const double* __restrict__ A, int64_t n, double* __restrict__ out)
 // LinvR[n * ldr + k] = (float) Linv[n + k * ld]  (column-major fp64 -> row-major fp32, 32 x 32 smem transpose)
 template <bool F16>
 __global__ void __launch_bounds__(256)
-linv_to_rowmajor_kernel(const double* __restrict__ Linv, int64_t ld, void* __restrict__ R_, int64_t ldr, double scale)
+linv_to_rowmajor_kernel(const double* __restrict__ Linv, int64_t ld, void* __restrict__ R_, int64_t ldr, double scale, void* __restrict__ Rlo_)
 {
-    __shared__ float tile[32][33];
+    __shared__ double tile[32][33];
     const int64_t n0 = (int64_t)blockIdx.x * 32, k0 = (int64_t)blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int kk = ty; kk < 32; kk += 8) tile[kk][tx] = (k0 + kk <= n0 + tx) ? (float)(Linv[n0 + tx + (k0 + kk) * ld] * scale) : 0.f;
+    for (int kk = ty; kk < 32; kk += 8) tile[kk][tx] = (k0 + kk <= n0 + tx) ? Linv[n0 + tx + (k0 + kk) * ld] * scale : 0.0;
     __syncthreads();
     for (int nn = ty; nn < 32; nn += 8) {
-        if (F16) reinterpret_cast<__half*>(R_)[(n0 + nn) * ldr + k0 + tx] = __float2half_rn(tile[tx][nn]);
-        else reinterpret_cast<float*>(R_)[(n0 + nn) * ldr + k0 + tx] = tf32_rna(tile[tx][nn]);
+        const double v = tile[tx][nn];
+        if (F16) {
+            const __half hi = __float2half_rn((float)v);
+            reinterpret_cast<__half*>(R_)[(n0 + nn) * ldr + k0 + tx] = hi;
+            if (Rlo_) reinterpret_cast<__half*>(Rlo_)[(n0 + nn) * ldr + k0 + tx] = __float2half_rn((float)((v - (double)__half2float(hi)) * 2048.0));
+        }
+        else reinterpret_cast<float*>(R_)[(n0 + nn) * ldr + k0 + tx] = tf32_rna((float)v);
     }
+}
+
+// sigma^2 from fp64 norms (split-operand mode): no rounding-bias term
+__global__ void __launch_bounds__(256)
+sigma2_split_kernel(const double* __restrict__ norm2, int64_t M, double kvv, double noise, double norm_unscale, double* __restrict__ s2)
+{
+    const int64_t c = blockIdx.x * (int64_t)256 + threadIdx.x;
+    if (c >= M) return;
+    double res = kvv - norm2[c] * norm_unscale;
+    res = (res <= 2.220446049250313e-16) ? 0.0 : res; // gp.hpp:623
+    s2[c] = res + noise;                               // gp.hpp:166
 }
 
 __global__ void __launch_bounds__(256)
@@ -1125,12 +1333,13 @@ int lb_tf32_prepare(lb_gp* h)
 {
     using namespace tf32q;
     if (h->linv32_valid) return LB_OK;
-    const bool f16 = (h->precision == 2);
+    const bool split = (h->precision == 3); // fp16 hi / lo planes (LB_PREC_FP16X3)
+    const bool f16 = (h->precision == 2) || split;
     int rc;
     if (!h->linv_valid && (rc = lb_launch_linv(h))) return rc;
     const int cl = lb_tf32_pair_mode() ? 2 : lb_tf32_cluster_size(); // the pair kernel walks two 256-row n-tiles per group
     const int64_t Np = h->Np, Nr = (Np + BN * cl - 1) / (BN * cl) * (BN * cl);
-    const size_t esz = f16 ? 2 : 4;
+    const size_t esz = split ? 4 : (f16 ? 2 : 4); // split: two fp16 planes of Nr x Np
     if (!h->dLinv32 || h->linv32_rows != Nr) {
         lb_dfree_sync(h, h->dLinv32);
         h->dLinv32 = nullptr;
@@ -1151,11 +1360,13 @@ int lb_tf32_prepare(lb_gp* h)
         scale = std::ldexp(1.0, 14 - (int)std::ceil(std::log2(mx)));
     }
     h->linv32_scale = scale;
-    if (Nr > Np) LB_CUDA(cudaMemsetAsync((char*)h->dLinv32 + esz * Np * Np, 0, esz * (Nr - Np) * Np, h->stream));
+    __half* lo_plane = split ? reinterpret_cast<__half*>(h->dLinv32) + Nr * Np : nullptr;
+    if (split) LB_CUDA(cudaMemsetAsync(h->dLinv32, 0, esz * Nr * Np, h->stream)); // both planes incl. the padding rows
+    else if (Nr > Np) LB_CUDA(cudaMemsetAsync((char*)h->dLinv32 + esz * Np * Np, 0, esz * (Nr - Np) * Np, h->stream));
     dim3 grid((unsigned)(Np / 32), (unsigned)(Np / 32));
     LbProfScope ps(h, h->stream, LB_PC_OTHER);
-    if (f16) linv_to_rowmajor_kernel<true><<<grid, 256, 0, h->stream>>>(h->dLinv, Np, h->dLinv32, Np, scale);
-    else linv_to_rowmajor_kernel<false><<<grid, 256, 0, h->stream>>>(h->dLinv, Np, h->dLinv32, Np, 1.0);
+    if (f16) linv_to_rowmajor_kernel<true><<<grid, 256, 0, h->stream>>>(h->dLinv, Np, h->dLinv32, Np, scale, lo_plane);
+    else linv_to_rowmajor_kernel<false><<<grid, 256, 0, h->stream>>>(h->dLinv, Np, h->dLinv32, Np, 1.0, nullptr);
     h->launches++;
     if (!h->dLinvW || h->linvw_np != Np) {
         lb_dfree_sync(h, h->dLinvW);
@@ -1179,8 +1390,10 @@ int lb_launch_kstar_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const doub
     double* dMu, double* dBias, long long* launches)
 {
     using namespace tf32q;
-    const bool f16 = (h->precision == 2);
+    const bool split = (h->precision == 3);
+    const bool f16 = (h->precision == 2) || split;
     const int64_t Np = h->Np;
+    void* dKtLo = split ? (void*)(reinterpret_cast<__half*>(dKt) + Mcp * Np) : nullptr; // lo plane behind the hi plane of this chunk
     {
         LbProfScope ps(h, st, LB_PC_KSTAR);
         // interior tiles without bounds checks; the last tile row / column (when N or Mc is not a multiple of 128) with
@@ -1190,7 +1403,7 @@ int lb_launch_kstar_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, const doub
             if (ib <= ia || jb <= ja) return;
             const int64_t tiles = (ib - ia) * (jb - ja);
             kstar_t32_kernel<decltype(kid)::value, decltype(f16c)::value, decltype(edgec)::value, DCH_WIDE><<<(unsigned)tiles, 256, 0, st>>>(h->dXs, Np,
-                h->N, dQs, Mcp, Mc, dKt, Np, h->kp, h->dAlpha, h->P, dMuPart, ia, ja, ib - ia, jb - ja, dBias ? h->dLinvW : nullptr);
+                h->N, dQs, Mcp, Mc, dKt, Np, h->kp, h->dAlpha, h->P, dMuPart, ia, ja, ib - ia, jb - ja, dBias ? h->dLinvW : nullptr, dKtLo);
             if (launches) ++*launches;
         };
         auto go_prec = [&](auto kid) {
@@ -1223,12 +1436,29 @@ int lb_launch_sigma_tf32(const lb_gp* h, cudaStream_t st, int64_t Mc, int64_t Mc
     const double* dBias, double* dS2, long long* launches)
 {
     using namespace tf32q;
-    const bool f16 = (h->precision == 2);
+    const bool split = (h->precision == 3);
+    const bool f16 = (h->precision == 2) || split;
     const int64_t Np = h->Np;
     const double kscale = f16 ? 1.0 / h->kp.sf2 : 1.0;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     int rc;
+    if (split) { // hi / lo planes, three MMAs per k-step, fp64 combination and norm (dNorm2 holds Mcp doubles)
+        if (Mcp % (2 * BM) || h->linv32_rows % BN) return LB_ERR_ARG;
+        const __half* Ah = reinterpret_cast<const __half*>(dKt);
+        const __half* Bh = reinterpret_cast<const __half*>(h->dLinv32);
+        {
+            LbProfScope ps(h, st, LB_PC_QSTEP);
+            rc = lb_launch_pair_split_gemm_norm(st, Ah, Ah + Mcp * Np, Np, Bh, Bh + h->linv32_rows * Np, Np, Mcp, h->linv32_rows, Np, 1,
+                reinterpret_cast<double*>(dNorm2), dErr, sms);
+        }
+        if (rc) return rc;
+        const double un = 1.0 / ((kscale * h->linv32_scale) * (kscale * h->linv32_scale));
+        sigma2_split_kernel<<<(unsigned)((Mc + 255) / 256), 256, 0, st>>>(reinterpret_cast<const double*>(dNorm2), Mc, h->kp.sf2, h->kp.noise, un, dS2);
+        if (launches) *launches += 2;
+        LB_CUDA(cudaGetLastError());
+        return LB_OK;
+    }
     const bool pair = lb_tf32_pair_mode() && (Mcp % (2 * BM) == 0) && (h->linv32_rows % (2 * BN) == 0);
     const int cl = pair ? 1 : lb_tf32_cluster_size(); // number of partial norms per candidate
     {

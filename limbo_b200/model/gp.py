@@ -44,7 +44,7 @@ class GP:
         self._device = device
         self._lib = _lib.load()
         h = C.c_void_p()
-        self._precision = {"fp64": 0, "tf32": 1, "fp16": 2}[precision]
+        self._precision = {"fp64": 0, "tf32": 1, "fp16": 2, "fp16x3": 3}[precision]
         _lib.check(self._lib.lb_create(C.byref(h), device, self._precision), "lb_create")
         self._h = h
         self._host_cache: dict[str, np.ndarray] = {}

@@ -15,9 +15,11 @@
 #include <limbo/model/gp/kernel_lf_opt.hpp>
 #include <limbo/model/gp/kernel_loo_opt.hpp>
 #include <limbo/model/gp/kernel_mean_lf_opt.hpp>
+#include <limbo/model/multi_gp.hpp>
 #include <limbo/opt/rprop.hpp>
 
 #include <limbo_b200/model/gp.hpp>
+#include <limbo_b200/opt/batched_random.hpp>
 
 using namespace limbo;
 
@@ -33,6 +35,9 @@ struct Params {
     struct acqui_ei : public defaults::acqui_ei {};
     struct mean_constant {
         BO_PARAM(double, constant, 0.5);
+    };
+    struct opt_batchedrandom : public limbo_b200::defaults::opt_batchedrandom {
+        BO_PARAM(int, candidates, 4000);
     };
 };
 
@@ -149,9 +154,155 @@ int run_hp_case(const char* name, int N, int D, bool loo)
     return (dg < 1e-9 && dh < 1e-7 && dm < 1e-7 && dv < 1e-9) ? 0 : 1;
 }
 
+// model::MultiGP (model/multi_gp.hpp:60-63: template-template GP parameter) instantiated over the drop-in and over the
+// reference's GP, side by side: compute, incremental add_sample, query.
+int run_multigp()
+{
+    using Kernel = kernel::MaternFiveHalves<Params>;
+    using Mean = mean::Constant<Params>;
+    using RefM = model::MultiGP<Params, model::GP, Kernel, Mean>;
+    using NewM = model::MultiGP<Params, limbo_b200::model::GP, Kernel, Mean>;
+    unsigned long long seed = 5;
+    const int N = 90, D = 2, P = 3;
+    std::vector<Eigen::VectorXd> X, Y;
+    for (int i = 0; i < N + 4; ++i) {
+        Eigen::VectorXd x((Eigen::Index)D), y((Eigen::Index)P);
+        for (int d = 0; d < D; ++d) x(d) = u01(seed);
+        y(0) = std::cos(3.0 * x(0)) + x(1);
+        y(1) = std::sin(4.0 * x(1));
+        y(2) = x(0) * x(1);
+        X.push_back(x);
+        Y.push_back(y);
+    }
+    std::vector<Eigen::VectorXd> X0(X.begin(), X.begin() + N), Y0(Y.begin(), Y.begin() + N);
+    RefM ref(D, P);
+    NewM gpu(D, P);
+    ref.compute(X0, Y0);
+    gpu.compute(X0, Y0);
+    for (int i = N; i < N + 4; ++i) { ref.add_sample(X[i], Y[i]); gpu.add_sample(X[i], Y[i]); } // multi_gp.hpp:139-176
+    double dmu = 0, ds = 0;
+    for (int q = 0; q < 40; ++q) {
+        Eigen::VectorXd v((Eigen::Index)D);
+        for (int d = 0; d < D; ++d) v(d) = u01(seed);
+        Eigen::VectorXd m1, s1, m2, s2;
+        std::tie(m1, s1) = ref.query(v);
+        std::tie(m2, s2) = gpu.query(v);
+        for (int p = 0; p < P; ++p) {
+            dmu = std::max(dmu, std::fabs(m1(p) - m2(p)));
+            ds = std::max(ds, std::fabs(s1(p) - s2(p)));
+        }
+        Eigen::VectorXd mm = gpu.mu(v), ss = gpu.sigma(v);
+        for (int p = 0; p < P; ++p) {
+            dmu = std::max(dmu, std::fabs(mm(p) - m2(p)));
+            ds = std::max(ds, std::fabs(ss(p) - s2(p)));
+        }
+    }
+    const bool dims = gpu.dim_in() == D && gpu.dim_out() == P && gpu.nb_samples() == N + 4 && (int)gpu.gp_models().size() == P;
+    std::printf("MultiGP<limbo_b200::model::GP> N=%d D=%d P=%d dmu=%.3e dsigma2=%.3e dims_ok=%d\n", N + 4, D, P, dmu, ds, (int)dims);
+    return (dmu < 1e-9 && ds < 1e-10 && dims) ? 0 : 1;
+}
+
+// The inner loop of bayes_opt::BOptimizer::optimize (boptimizer.hpp:139-170; BOptimizer itself needs Boost.Parameter, which
+// this image lacks) with the batched acquisition optimiser: acquisition functor built per iteration, the optimiser only
+// sees the closure f(x, gradient), add_sample after every evaluation.
+template <template <typename, typename> class Acq>
+int run_bo_loop(const char* name)
+{
+    using Kernel = kernel::MaternFiveHalves<Params>;
+    using GP_t = limbo_b200::model::GP<Params, Kernel, mean::Data<Params>, model::gp::NoLFOpt<Params>>;
+    using Acq_t = Acq<Params, GP_t>;
+    unsigned long long seed = 99;
+    const int D = 2;
+    Eigen::VectorXd sol((Eigen::Index)D);
+    sol(0) = 0.25; sol(1) = 0.75;
+    auto sfun = [&](const Eigen::VectorXd& x) { Eigen::VectorXd y((Eigen::Index)1); y(0) = -(x - sol).squaredNorm(); return y; };
+    std::vector<Eigen::VectorXd> S, O;
+    for (int i = 0; i < 10; ++i) { // init::RandomSampling
+        Eigen::VectorXd x((Eigen::Index)D);
+        for (int d = 0; d < D; ++d) x(d) = u01(seed);
+        S.push_back(x);
+        O.push_back(sfun(x));
+    }
+    GP_t model(D, 1);
+    model.compute(S, O);
+    limbo_b200::opt::BatchedRandom<Params> acqui_optimizer;
+    FirstElem afun;
+    for (int it = 0; it < 25; ++it) {
+        Acq_t acqui(model, it);
+        auto acqui_optimization = [&](const Eigen::VectorXd& x, bool g) { return acqui(x, afun, g); };
+        Eigen::VectorXd start((Eigen::Index)D);
+        for (int d = 0; d < D; ++d) start(d) = u01(seed);
+        Eigen::VectorXd nx = acqui_optimizer(acqui_optimization, start, true);
+        S.push_back(nx);
+        O.push_back(sfun(nx));
+        model.add_sample(S.back(), O.back());
+    }
+    double best = -1e300;
+    Eigen::VectorXd bx;
+    for (size_t i = 0; i < O.size(); ++i)
+        if (O[i](0) > best) { best = O[i](0); bx = S[i]; }
+    const double err = (bx - sol).squaredNorm();
+    std::printf("BO loop with %s + BatchedRandom: 10 + 25 evaluations, |x* - sol|^2 = %.3e\n", name, err);
+    return err < 1e-3 ? 0 : 1;
+}
+
+// BatchedRandom over a batch-aware functor and over the reference's own one-point acqui::UCB must pick the same candidate.
+struct ArgmaxProbe : limbo_b200::opt::BatchedRandom<Params> {
+    template <typename F>
+    static std::pair<double, long> run(const F& f, const std::vector<Eigen::VectorXd>& c) { return _argmax(f, c); }
+};
+int run_batch_equivalence()
+{
+    using Kernel = kernel::SquaredExpARD<Params>;
+    using GP_t = limbo_b200::model::GP<Params, Kernel, mean::Data<Params>, model::gp::NoLFOpt<Params>>;
+    unsigned long long seed = 7;
+    const int N = 80, D = 3, M = 600;
+    std::vector<Eigen::VectorXd> X, Y, C;
+    for (int i = 0; i < N; ++i) {
+        Eigen::VectorXd x((Eigen::Index)D), y((Eigen::Index)1);
+        double s = 0;
+        for (int d = 0; d < D; ++d) { x(d) = u01(seed); s += std::cos(3.0 * x(d)); }
+        y(0) = s;
+        X.push_back(x);
+        Y.push_back(y);
+    }
+    for (int i = 0; i < M; ++i) {
+        Eigen::VectorXd c((Eigen::Index)D);
+        for (int d = 0; d < D; ++d) c(d) = u01(seed);
+        C.push_back(c);
+    }
+    GP_t gp(D, 1);
+    gp.compute(X, Y);
+    FirstElem afun;
+    int bad = 0;
+    {
+        limbo_b200::acqui::UCB<Params, GP_t> batch(gp);
+        acqui::UCB<Params, GP_t> single(gp); // the reference's functor over the drop-in model: one query() per candidate
+        auto fb = [&](const Eigen::VectorXd& x, bool g) { return batch(x, afun, g); };
+        auto fs = [&](const Eigen::VectorXd& x, bool g) { return single(x, afun, g); };
+        auto rb = ArgmaxProbe::run(fb, C), rs = ArgmaxProbe::run(fs, C);
+        std::printf("UCB argmax over %d candidates: batched (%.12g, %ld) one-by-one (%.12g, %ld)\n", M, rb.first, rb.second, rs.first, rs.second);
+        bad += !(rb.second == rs.second && std::fabs(rb.first - rs.first) < 1e-10);
+    }
+    {
+        limbo_b200::acqui::EI<Params, GP_t> batch(gp);
+        acqui::EI<Params, GP_t> single(gp);
+        auto fb = [&](const Eigen::VectorXd& x, bool g) { return batch(x, afun, g); };
+        auto fs = [&](const Eigen::VectorXd& x, bool g) { return single(x, afun, g); };
+        auto rb = ArgmaxProbe::run(fb, C), rs = ArgmaxProbe::run(fs, C);
+        std::printf("EI  argmax over %d candidates: batched (%.12g, %ld) one-by-one (%.12g, %ld)\n", M, rb.first, rb.second, rs.first, rs.second);
+        bad += !(rb.second == rs.second && std::fabs(rb.first - rs.first) < 1e-10);
+    }
+    return bad;
+}
+
 int main()
 {
     int bad = 0;
+    bad += run_multigp();
+    bad += run_batch_equivalence();
+    bad += run_bo_loop<limbo_b200::acqui::UCB>("limbo_b200::acqui::UCB");
+    bad += run_bo_loop<limbo_b200::acqui::EI>("limbo_b200::acqui::EI");
     bad += run_hp_case<model::gp::KernelLooOpt<Params, opt::Rprop<Params>>, mean::Data<Params>>("KernelLooOpt", 70, 2, true);
     bad += run_hp_case<model::gp::KernelMeanLFOpt<Params, opt::Rprop<Params>>, mean::FunctionARD<Params, mean::Constant<Params>>>(
         "KernelMeanLFOpt", 70, 2, false);

@@ -35,23 +35,55 @@ def test_save_load_roundtrip(tmp_path):
 
 
 def test_multi_gp_matches_plain_gps():
+    """model::MultiGP against plain single-output GPs (test_gp.cpp:912-952: 1e-6; the reference tests it with
+    mean::Constant).  The mean lives at the MultiGP level like the reference's (multi_gp.hpp:63,112-118): with mean::Data,
+    add_sample leaves the earlier observations centred on the OLD mean (multi_gp.hpp:168-175) until recompute(true) - that
+    reference behaviour is reproduced, not "fixed"."""
     from limbo_b200 import kernel, mean, model, synth
+
+    class P:
+        class mean_constant:
+            constant = 0.7
     X = synth.points(3, 150, 3)
     Y = np.stack([synth.targets(X), np.sin(4 * X[:, 1]), X[:, 2] ** 2], axis=1)
-    mgp = model.MultiGP(3, 3, kernel=kernel.MaternFiveHalves, mean=mean.Data)
+    Xq = synth.points(4, 200, 3)
+    # mean::Constant, incremental: identical to plain GPs with the same mean
+    mgp = model.MultiGP(3, 3, params=P, kernel=kernel.MaternFiveHalves, mean=mean.Constant)
     mgp.compute(X[:140], Y[:140])
     for i in range(140, 150):
         mgp.add_sample(X[i], Y[i])
-    Xq = synth.points(4, 200, 3)
+    assert all(g.append_count() == 10 for g in mgp.gp_models())
     mu, s2 = mgp.query_batch(Xq)
     assert mu.shape == (200, 3) and s2.shape == (200, 3)
     for p in range(3):
-        gp = model.GP(3, 1, kernel=kernel.MaternFiveHalves, mean=mean.Data)
+        gp = model.GP(3, 1, params=P, kernel=kernel.MaternFiveHalves, mean=mean.Constant)
         gp.compute(X, Y[:, p:p + 1])
         m, s = gp.query_batch(Xq)
         assert np.abs(m[:, 0] - mu[:, p]).max() <= 1e-6 and np.abs(s - s2[:, p]).max() <= 1e-6
     m1, s1 = mgp.query(Xq[0])
-    assert np.array_equal(m1, mu[0]) and np.array_equal(s1, s2[0])
+    assert np.abs(m1 - mu[0]).max() <= 1e-12 and np.array_equal(s1, s2[0])
+    # mean::Data: equal after compute(); stale-centred after add_sample (reference semantics); equal again after recompute
+    mgd = model.MultiGP(3, 3, kernel=kernel.MaternFiveHalves, mean=mean.Data)
+    mgd.compute(X[:140], Y[:140])
+    plain = []
+    for p in range(3):
+        gp = model.GP(3, 1, kernel=kernel.MaternFiveHalves, mean=mean.Data)
+        gp.compute(X[:140], Y[:140, p:p + 1])
+        plain.append(gp)
+    mu, s2 = mgd.query_batch(Xq)
+    for p in range(3):
+        m, s = plain[p].query_batch(Xq)
+        assert np.abs(m[:, 0] - mu[:, p]).max() <= 1e-10 and np.abs(s - s2[:, p]).max() <= 1e-10
+    for i in range(140, 150):
+        mgd.add_sample(X[i], Y[i])
+        for p in range(3):
+            plain[p].add_sample(X[i], Y[i, p:p + 1])
+    assert np.allclose(mgd.mean_observation(), Y.mean(axis=0))
+    mgd.recompute(True, True)
+    mu, s2 = mgd.query_batch(Xq)
+    for p in range(3):
+        m, s = plain[p].query_batch(Xq)
+        assert np.abs(m[:, 0] - mu[:, p]).max() <= 1e-9 and np.abs(s - s2[:, p]).max() <= 1e-10
 
 
 @pytest.mark.parametrize("acq", ["UCB", "EI"])

@@ -88,3 +88,28 @@ def test_reduced_precision_edge_shapes(kname, N, D, P, M, prec):
     m2, v2 = g32.query_batch(Xq2)
     m3, v3 = g64.query_batch(Xq2)
     assert np.abs(m2 - m3).max() <= 1e-9 and np.abs(v2 - v3).max() <= 4e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kname,N,D,P,M", [("SquaredExpARD", 1000, 12, 1, 3000), ("MaternFiveHalves", 700, 6, 2, 1500), ("Exp", 513, 5, 1, 300),
+                                             ("SquaredExpARD", 4096, 6, 1, 2000), ("MaternThreeHalves", 130, 3, 1, 1)])
+def test_split_operand_mode_buys_five_digits(kname, N, D, P, M):
+    """LB_PREC_FP16X3: hi + 2^-11 lo fp16 operands, three tensor-core products, fp64 combination / norm.  Stated tolerance:
+    |d sigma^2| <= 2e-5 k(v,v) (three orders below the one-plane modes), |d mu| <= 1e-9; no rounding-bias model involved."""
+    from limbo_b200 import acqui, kernel, mean, model, synth
+    X = synth.points(77, N, D)
+    Y = np.stack([np.cos(3 * X.sum(1) + p) for p in range(P)], axis=1)
+    Xq = synth.points(78, M, D)
+    kw = dict(kernel=getattr(kernel, kname), mean=mean.Data)
+    g64, g3 = model.GP(D, P, **kw), model.GP(D, P, precision="fp16x3", **kw)
+    g64.compute(X, Y)
+    g3.compute(X, Y)
+    mu64, s64 = g64.query_batch(Xq)
+    mu3, s3 = g3.query_batch(Xq)
+    print(kname, N, "max |d sigma^2|", np.abs(s64 - s3).max(), "mean", (s3 - s64).mean())
+    assert np.abs(mu64 - mu3).max() <= 1e-9
+    assert np.abs(s64 - s3).max() <= 2e-5
+    if P == 1 and M > 1:
+        b64, i64, v64 = acqui.EI(g64).argmax_batch(Xq, return_values=True)
+        b3, i3, v3 = acqui.EI(g3).argmax_batch(Xq, return_values=True)
+        assert np.abs(v64 - v3).max() <= 1e-4 and v64[i3] >= b64 - 1e-5 * max(1.0, abs(b64))
