@@ -71,7 +71,8 @@ typedef struct lb_gp lb_gp;
 #define LB_PREC_FP16 2
 /* fp16 split operands: every operand is hi + 2^-11 lo (two fp16 planes, 22 significant bits), three tensor-core products per
  * k-step, hi x hi and the cross terms in separate fp32 accumulators, combined and squared in fp64.  About 3x the scoring time of
- * LB_PREC_FP16; |d sigma^2| ~ 1e-6 k(v,v) at N = 16384 (tests/test_gpu_config4.py) */
+ * LB_PREC_FP16; |d sigma^2| <= 2e-5 k(v,v) up to N = 4096 and <= 1e-4 at N = 16384, cond(K) ~ 1.6e6 (the fp32 accumulation of the
+ * tensor core is the floor there; tests/test_gpu_tf32.py, tests/test_gpu_config4.py), against 2-4e-3 for the one-plane modes */
 #define LB_PREC_FP16X3 3
 
 /* Lifetime.  Replaces GP(int dim_in, int dim_out) / ~GP / the copy constructor

@@ -20,6 +20,9 @@ int lb_launch_loo_value(lb_gp* h, double* dOut);
 int lb_launch_loo_grad(lb_gp* h, int optimize_noise, double* dGrad);
 int lb_launch_kinv_obs(lb_gp* h, double* dOut);
 int lb_query_fused_supported(const lb_gp* h);
+size_t lb_query_panel_scratch_doubles(const lb_gp* h, int64_t Mp);
+int lb_launch_query_panel(lb_gp* h, cudaStream_t st, int64_t M, const double* dQs, int64_t Mp, double* dWork, double* dMu, double* dS2,
+    long long* launches);
 size_t lb_query_fused_scratch_doubles(const lb_gp* h, int grid);
 int lb_launch_query_fused(const lb_gp* h, cudaStream_t st, int64_t M, const double* dQs, int64_t Mp, double* dVscratch,
     int grid, double* dMu, double* dS2, long long* launches);
@@ -444,7 +447,7 @@ static int set_data_common(lb_gp* h, int64_t N, int D, int P, const double* X, c
     h->N = N; h->D = D; h->P = P;
     h->kp.Draw = D;
     h->kp.D = D + h->kp.klam;
-    h->fitted = false; h->linv_valid = false; h->kinv_valid = false; h->linv32_valid = false;
+    h->fitted = false; h->linv_valid = false; h->linv_levels = 0; h->kinv_valid = false; h->linv32_valid = false;
     const double* dXr = X;
     const double* dYr = Y;
     if (!dev && N > 0) {
@@ -479,7 +482,7 @@ int lb_dchol_set_points(lb_gp* h, int64_t N, int D, const double* X)
     h->N = N; h->D = D; h->P = 0;
     h->kp.Draw = D;
     h->kp.D = D + h->kp.klam;
-    h->fitted = false; h->linv_valid = false; h->kinv_valid = false; h->linv32_valid = false;
+    h->fitted = false; h->linv_valid = false; h->linv_levels = 0; h->kinv_valid = false; h->linv32_valid = false;
     int rc = lb_ensure_scratch(h, sizeof(double) * (size_t)N * D);
     if (rc) return rc;
     LB_CUDA(cudaMemcpyAsync(h->dScratch, X, sizeof(double) * N * D, cudaMemcpyHostToDevice, h->stream));
@@ -556,7 +559,7 @@ int lb_set_kernel(lb_gp* h, int kernel_id, const double* p, int n_hparams, doubl
         && old.sf2 == kp.sf2 && old.l == kp.l && old.noise == kp.noise && old.c1 == kp.c1 && old.c2 == kp.c2;
     if (same && kernel_id == LB_K_SE_ARD)
         for (int d = 0; d < h->D; ++d) same = same && (old.inv_ell[d] == kp.inv_ell[d]);
-    if (!same) { h->fitted = false; h->linv_valid = false; h->kinv_valid = false; h->linv32_valid = false; }
+    if (!same) { h->fitted = false; h->linv_valid = false; h->linv_levels = 0; h->kinv_valid = false; h->linv32_valid = false; }
     return LB_OK;
 }
 
@@ -571,7 +574,7 @@ int lb_fit(lb_gp* h)
     if ((rc = lb_launch_scale_x(h))) return rc;
     if ((rc = lb_launch_kbuild(h, h->dL))) return rc;
     if ((rc = lb_launch_potrf(h))) return rc;
-    h->fitted = true; h->linv_valid = false; h->kinv_valid = false; h->linv32_valid = false;
+    h->fitted = true; h->linv_valid = false; h->linv_levels = 0; h->kinv_valid = false; h->linv32_valid = false;
     if ((rc = lb_launch_solve_alpha(h))) return rc;
     return check_info(h);
 }
@@ -586,7 +589,7 @@ int lb_fit_async(lb_gp* h) // same as lb_fit without the final host sync / info 
     if ((rc = lb_launch_scale_x(h))) return rc;
     if ((rc = lb_launch_kbuild(h, h->dL))) return rc;
     if ((rc = lb_launch_potrf(h))) return rc;
-    h->fitted = true; h->linv_valid = false; h->kinv_valid = false; h->linv32_valid = false;
+    h->fitted = true; h->linv_valid = false; h->linv_levels = 0; h->kinv_valid = false; h->linv32_valid = false;
     return lb_launch_solve_alpha(h);
 }
 
@@ -654,7 +657,7 @@ int lb_load_factor(lb_gp* h, const double* L_colmajor, const double* alpha_colma
     h->launches++;
     for (int k = 0; k < T; ++k)
         if ((rc = lb_launch_potf2_block(h, k, 0))) return rc;
-    h->fitted = true; h->linv_valid = false; h->kinv_valid = false; h->linv32_valid = false;
+    h->fitted = true; h->linv_valid = false; h->linv_levels = 0; h->kinv_valid = false; h->linv32_valid = false;
     return check_info(h);
 }
 
@@ -743,9 +746,28 @@ int lb_append(lb_gp* h, const double* x, const double* Yall)
     append_row_kernel<<<1, 256, 0, h->stream>>>(h->dL, Np, n, dk, knn, h->dInfo);
     h->launches++;
     if ((rc = lb_launch_potf2_block(h, (int)(n / LB_TILE), 0))) return rc;
-    h->linv_valid = false; h->kinv_valid = false; h->linv32_valid = false;
+    h->linv_valid = false; h->linv_levels = 0; h->kinv_valid = false; h->linv32_valid = false;
     if ((rc = lb_launch_solve_alpha(h))) return rc;
     return check_info(h);
+}
+
+// batches of at least this many candidates take the panel path (LB_QUERY_PANEL_MIN overrides; the slab kernel below it
+// keeps the one-point / small-batch latency)
+static int64_t g_query_panel_min = -1;
+static int64_t query_panel_min()
+{
+    if (g_query_panel_min < 0) {
+        const char* e = getenv("LB_QUERY_PANEL_MIN");
+        int64_t v = e ? (int64_t)atoll(e) : 4096;
+        g_query_panel_min = v < 1 ? 1 : v;
+    }
+    return g_query_panel_min;
+}
+// testing hook: batch size from which lb_query / lb_acq_argmax take the panel path (<= 0 restores the default)
+extern "C" int lb_debug_set_query_panel_min(long long m)
+{
+    g_query_panel_min = m > 0 ? (int64_t)m : -1;
+    return LB_OK;
 }
 
 static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_dev, double* mu_out, double* s2_out,
@@ -813,6 +835,22 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
                 LB_CUDA(cudaMemcpyAsync(&herr, w.dErr, sizeof(int), cudaMemcpyDeviceToHost, st));
                 LB_CUDA(cudaStreamSynchronize(st));
                 if (herr) return LB_ERR_TIMEOUT;
+            }
+        }
+        else if (M >= query_panel_min() && !h->force_unfused) {
+            // large batches: blocked solve over 2048-row super-blocks on the GEMM core (query.cu, namespace panel);
+            // candidate chunks bounded so that V (Np x Mc) stays <= ~6 GiB
+            const int64_t maxcols = std::max<int64_t>(LB_TILE, ((int64_t)6 << 30) / (8 * h->Np) / LB_TILE * LB_TILE);
+            const int64_t Mc = std::min(Mp, maxcols);
+            if ((rc = ensure(h, &w.dQs, &w.qs_bytes, sizeof(double) * De * Mc))) return rc;
+            if ((rc = ensure(h, &w.dV, &w.v_bytes, sizeof(double) * lb_query_panel_scratch_doubles(h, Mc)))) return rc;
+            for (int64_t m0 = 0; m0 < M; m0 += Mc) {
+                const int64_t mc = std::min(Mc, M - m0);
+                const int64_t mcp = (mc + LB_TILE - 1) / LB_TILE * LB_TILE;
+                dim3 g1((unsigned)((mcp + 255) / 256), (unsigned)De);
+                pack_soa_kernel<<<g1, 256, 0, st>>>(dQraw + m0 * D, mc, D, w.dQs, mcp, h->kp, 1);
+                h->launches++;
+                if ((rc = lb_launch_query_panel(h, st, mc, w.dQs, mcp, w.dV, w.dMu + m0 * P, w.dS2 + m0, &h->launches))) return rc;
             }
         }
         else if (lb_query_fused_supported(h) && !h->force_unfused) {

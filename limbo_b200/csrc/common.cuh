@@ -311,6 +311,7 @@ struct lb_gp {
 
     bool fitted = false;
     bool linv_valid = false;
+    int linv_levels = 0;     // diagonal blocks of this many 128-tiles of dLinv hold the inverse (0: nothing, >= T: all of L^-1)
     bool kinv_valid = false;
     bool kinv_sym = false;   // upper triangle of dKinv mirrored (needed by the LOO products and lb_get)
     double* dWork = nullptr; int64_t work_np = 0; // Np x Np workspace (dK/dtheta of the LOO gradient)
@@ -407,6 +408,7 @@ int lb_launch_acq(const lb_gp* h, cudaStream_t st, int acq_id, double p0, double
     const double* dS2, double* dAcq, double* dBestVal, long long* dBestIdx, long long* launches);
 int lb_launch_loglik(lb_gp* h, double* dOut /*3 doubles: a, logdet, loglik*/);
 int lb_launch_kinv(lb_gp* h);
+int lb_launch_linv_levels(lb_gp* h, int want_tiles); // lml.cu: inverse of the diagonal blocks of `want_tiles` 128-tiles (power of two)
 int lb_launch_grad(lb_gp* h, int optimize_noise, double* dGrad);
 int lb_ensure_scratch(lb_gp* h, size_t bytes);
 int lb_tf32_prepare(lb_gp* h);

@@ -379,7 +379,10 @@ int lb_launch_loglik(lb_gp* h, double* dOut)
     return LB_OK;
 }
 
-int lb_launch_linv(lb_gp* h)
+// Inverse of the diagonal blocks of L made of `want_tiles` 128-tiles (a power of two; >= T: all of L^-1), by the levels of
+// the recursion above; levels already present are kept (the batched query wants 16-tile blocks, the likelihood gradient
+// all of L^-1 - the second continues where the first stopped).  dKinv is the W workspace of the recursion.
+int lb_launch_linv_levels(lb_gp* h, int want_tiles)
 {
     int rc = set_attrs();
     if (rc) return rc;
@@ -388,22 +391,36 @@ int lb_launch_linv(lb_gp* h)
     if (!h->dLinv) {
         LB_ALLOC(h, h->dLinv, bytes);
         LB_CUDA(cudaMemsetAsync(h->dLinv, 0, bytes, h->stream)); // strict upper part stays zero
+        h->linv_levels = 0;
     }
     if (!h->dKinv) LB_ALLOC(h, h->dKinv, bytes); // doubles as the W workspace of the recursion
     LbProfScope ps(h, h->stream, LB_PC_TRTRI);
-    trtri_diag_copy_kernel<<<T, 256, 0, h->stream>>>(h->dInvD, h->dLinv, h->Np);
-    h->launches++;
-    for (int sb = 1; sb < T; sb *= 2) {
+    if (h->linv_levels == 0) {
+        trtri_diag_copy_kernel<<<T, 256, 0, h->stream>>>(h->dInvD, h->dLinv, h->Np);
+        h->launches++;
+        h->linv_levels = 1;
+    }
+    for (int sb = h->linv_levels; sb < want_tiles && sb < T; sb *= 2) {
         const int nprob = (T + 2 * sb - 1) / (2 * sb);
+        h->kinv_valid = false; // W overwrites dKinv
         for (int step = 1; step <= 2; ++step) {
             trtri_level_kernel<<<nprob * sb * sb, lbg::CfgWide::THREADS, lbg::CfgWide::PIPE_BYTES, h->stream>>>(h->dL, h->dLinv, h->dKinv, h->Np, sb,
                 step, T);
             h->launches++;
         }
+        h->linv_levels = 2 * sb;
     }
     LB_CUDA(cudaGetLastError());
-    h->linv_valid = true;
+    if (h->linv_levels >= T) h->linv_valid = true;
     return LB_OK;
+}
+
+int lb_launch_linv(lb_gp* h)
+{
+    const int T = (int)(h->Np / LB_TILE);
+    int want = 1;
+    while (want < T) want *= 2;
+    return lb_launch_linv_levels(h, want);
 }
 
 int lb_launch_kinv(lb_gp* h)

@@ -692,6 +692,143 @@ LbOncePerDevice g_attr_once2;
 
 } // namespace slab
 
+// ===========================================================================
+// Panel path for large candidate batches (M >= LB_QUERY_PANEL_MIN): V = L^-1 K* as a blocked solve over super-blocks of
+// SB = 16 row tiles (2048 rows), everything on the GEMM core of gemm.cuh with long K ranges:
+//     update_s :  T_s   = K*_s - L[s, 0:s] V[0:s]            (SB x Mp/128 tiles of 128 x 128, K = s * 2048)
+//     solve_s  :  V_s   = inv(L_ss) T_s                      (same tiles, K = (i + 1) * 128: inv(L_ss) is lower triangular)
+// inv(L_ss) = the 16-tile diagonal blocks of L^-1 from the first levels of the recursive trtri (lml.cu, ~1 % of the flops of a
+// fit, cached until the next fit).  Each V block is read once per SUPER-block instead of once per 128-row block: the
+// fused slab kernel above streams its private V slab T/2 times (86 GB of DRAM traffic at N = 16384, M = 10^4, ncu round 1),
+// this path moves ~10 GB.  mu comes from K* before the solve; |V_c|^2 is reduced per tile in the solve epilogue (fixed
+// order: lanes -> warps -> tiles), so results are run-to-run deterministic and independent of the batch composition
+// (a candidate's value depends only on its own column).
+// ===========================================================================
+namespace panel {
+
+using C = lbg::CfgWide;
+constexpr int SB = 16;
+
+// Tbuf[i, ct] = V[s0 + i, ct] - L[s0 + i, 0:s0] V[0:s0, ct]       grid = nrows * (Mp / 128), row tile fastest
+__global__ void __launch_bounds__(C::THREADS, 1)
+panel_update_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ V, double* __restrict__ Tbuf, int64_t ldt, int s0,
+    int nrows)
+{
+    extern __shared__ __align__(16) double smem[];
+    const int i = blockIdx.x % nrows, ct = blockIdx.x / nrows;
+    const double* Vc = V + (int64_t)ct * LB_TILE * ld;
+    lbg::Acc<C> acc;
+    lbg::load_acc<C>(acc, Vc + (int64_t)(s0 + i) * LB_TILE, ld);
+    if (s0 > 0) lbg::mainloop<C, false, true, true>(acc, L + (int64_t)(s0 + i) * LB_TILE, ld, Vc, ld, s0 * LB_TILE, smem);
+    lbg::store_acc<C>(acc, Tbuf + (int64_t)i * LB_TILE + (int64_t)ct * LB_TILE * ldt, ldt);
+}
+
+// V[s0 + i, ct] = sum_{k <= i} Linv[s0 + i, s0 + k] Tbuf[k, ct];  normpart[(s0 + i) * Mp + c] = sum over the tile's 128 rows of V^2
+__global__ void __launch_bounds__(C::THREADS, 1)
+panel_solve_kernel(const double* __restrict__ Linv, int64_t ld, const double* __restrict__ Tbuf, int64_t ldt, double* __restrict__ V, int s0,
+    int nrows, double* __restrict__ normpart, int64_t Mp)
+{
+    extern __shared__ __align__(16) double smem[];
+    const int i = nrows - 1 - (int)(blockIdx.x % nrows), ct = blockIdx.x / nrows; // longest K ranges first
+    lbg::Acc<C> acc;
+    acc.zero();
+    lbg::mainloop<C, false, true>(acc, Linv + (int64_t)(s0 + i) * LB_TILE + (int64_t)s0 * LB_TILE * ld, ld, Tbuf + (int64_t)ct * LB_TILE * ldt, ldt,
+        (i + 1) * LB_TILE, smem);
+    lbg::store_acc<C>(acc, V + (int64_t)(s0 + i) * LB_TILE + (int64_t)ct * LB_TILE * ld, ld);
+    // column norms of the tile: per thread (2 m16 tiles x 2 row halves), then the 8 row lanes, then the 4 row warps
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;
+    double* sRed = smem; // [4][128]
+#pragma unroll
+    for (int nt = 0; nt < C::NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double sq = 0.0;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                sq = fma(acc.v[mt][nt][e], acc.v[mt][nt][e], sq);
+                sq = fma(acc.v[mt][nt][2 + e], acc.v[mt][nt][2 + e], sq);
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            if (g == 0) sRed[wm * LB_TILE + wn * (C::BN / C::WN) + nt * 8 + 2 * t + e] = sq;
+        }
+    __syncthreads();
+    if (threadIdx.x < LB_TILE) {
+        const double sum = ((sRed[threadIdx.x] + sRed[LB_TILE + threadIdx.x]) + sRed[2 * LB_TILE + threadIdx.x]) + sRed[3 * LB_TILE + threadIdx.x];
+        normpart[(int64_t)(s0 + i) * Mp + (int64_t)ct * LB_TILE + threadIdx.x] = sum;
+    }
+}
+
+// sigma2[c] = k(v,v) - sum_t normpart[t][c], clamp (gp.hpp:623), + noise (gp.hpp:166)
+__global__ void __launch_bounds__(256)
+panel_finish_kernel(const double* __restrict__ normpart, int T, int64_t Mp, int64_t M, double kvv, double noise, double* __restrict__ s2)
+{
+    const int64_t c = blockIdx.x * (int64_t)256 + threadIdx.x;
+    if (c >= M) return;
+    double s = 0.0;
+    for (int tt = 0; tt < T; ++tt) s += normpart[(int64_t)tt * Mp + c];
+    double res = kvv - s;
+    res = (res <= DBL_EPSILON) ? 0.0 : res;
+    s2[c] = res + noise;
+}
+
+LbOncePerDevice g_once;
+
+} // namespace panel
+
+// workspace in doubles behind dV (Np x Mp): Tbuf (SB * 128 x Mp) + norm partials (T x Mp)
+size_t lb_query_panel_scratch_doubles(const lb_gp* h, int64_t Mp)
+{
+    const int64_t T = h->Np / LB_TILE;
+    return (size_t)(h->Np * Mp + (int64_t)panel::SB * LB_TILE * Mp + T * Mp);
+}
+
+int lb_launch_query_panel(lb_gp* h, cudaStream_t st, int64_t M, const double* dQs, int64_t Mp, double* dWork, double* dMu, double* dS2,
+    long long* launches)
+{
+    using namespace panel;
+    if (g_once.need()) {
+        LB_CUDA(cudaFuncSetAttribute(panel_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::PIPE_BYTES));
+        LB_CUDA(cudaFuncSetAttribute(panel_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::PIPE_BYTES));
+    }
+    const int T = (int)(h->Np / LB_TILE);
+    const int64_t ld = h->Np, ldt = (int64_t)SB * LB_TILE;
+    double* dV = dWork;
+    double* dT = dV + ld * Mp;
+    double* dNorm = dT + ldt * Mp;
+    int rc = lb_launch_linv_levels(h, SB); // inverse of the 16-tile diagonal blocks (kept until the next fit)
+    if (rc) return rc;
+    dim3 grid((unsigned)T, (unsigned)(Mp / LB_TILE));
+    {
+        LbProfScope ps(h, st, LB_PC_KSTAR);
+        kstar_kernel<<<grid, 256, 0, st>>>(h->dXs, h->Np, h->N, dQs, Mp, M, dV, h->kp);
+    }
+    {
+        LbProfScope ps(h, st, LB_PC_QREDUCE);
+        mu_kernel<<<(unsigned)M, 256, 0, st>>>(dV, h->Np, h->dAlpha, h->P, dMu);
+    }
+    if (launches) *launches += 2;
+    const unsigned ctiles = (unsigned)(Mp / LB_TILE);
+    {
+        LbProfScope ps(h, st, LB_PC_QSTEP);
+        for (int s0 = 0; s0 < T; s0 += SB) {
+            const int nrows = (T - s0 < SB) ? (T - s0) : SB;
+            panel_update_kernel<<<nrows * ctiles, C::THREADS, C::PIPE_BYTES, st>>>(h->dL, ld, dV, dT, ldt, s0, nrows);
+            panel_solve_kernel<<<nrows * ctiles, C::THREADS, C::PIPE_BYTES, st>>>(h->dLinv, ld, dT, ldt, dV, s0, nrows, dNorm, Mp);
+            if (launches) *launches += 2;
+        }
+    }
+    {
+        LbProfScope ps(h, st, LB_PC_QREDUCE);
+        panel_finish_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(dNorm, T, Mp, M, h->kp.sf2, h->kp.noise, dS2);
+    }
+    if (launches) ++*launches;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
 int lb_query_fused_supported(const lb_gp* h) { return h->kp.D <= slab::DMAXF && h->P <= slab::PMAXF; }
 size_t lb_query_fused_scratch_doubles(const lb_gp* h, int grid) { return (size_t)grid * h->Np * slab::SLAB; }
 

@@ -327,13 +327,59 @@ def test_fused_and_multilaunch_query_paths_agree(oracle_mod, lib):
 def test_query_slab_nine_tiles(oracle_mod):
     """M = 10000 candidates -> slabs of 8 and 9 n8-tiles per CTA (the benchmark shape).  Regression for the B-stage
     loader that skipped the 9th tile (caught by tests/test_gpu_fullsize.py)."""
-    from limbo_b200 import synth
+    from limbo_b200 import _lib, synth
     gp, og, X, Y = _make("SquaredExpARD", 300, 6)
     Xq = synth.points(4321, 10000, 6)
-    mu, s2 = gp.query_batch(Xq)
+    lib = _lib.load()
+    lib.lb_debug_set_query_panel_min(1 << 40)  # keep this batch on the slab kernel (large batches default to the panel path)
+    try:
+        mu, s2 = gp.query_batch(Xq)
+    finally:
+        lib.lb_debug_set_query_panel_min(0)
     mu_o, s2_o = og.query(Xq, nthreads=8)
     assert np.abs(mu - (mu_o + Y.mean(axis=0))).max() <= TOL_ABS
     assert np.abs(s2 - s2_o).max() <= TOL_ABS
+    mu_p, s2_p = gp.query_batch(Xq)  # and the panel path on the same batch
+    assert np.abs(mu_p - (mu_o + Y.mean(axis=0))).max() <= TOL_ABS and np.abs(s2_p - s2_o).max() <= TOL_ABS
+
+
+@pytest.mark.parametrize("kname,N,D,P,M", [("SquaredExpARD", 700, 6, 1, 4500), ("MaternFiveHalves", 2100, 3, 2, 5000), ("Exp", 4096, 12, 1, 4100),
+                                             ("SquaredExpARD", 130, 20, 5, 4200)])
+def test_query_panel_path_matches_oracle(kname, N, D, P, M, oracle_mod):
+    """Batches >= 4096 candidates take the panel path (blocked solve over 2048-row super-blocks: one, several and ragged
+    super-blocks here, D > 16 and P > 4 included): against the oracle at the fp64 bar, against the slab kernel to 1e-12,
+    deterministic, and a candidate's value does not depend on what else is in the batch."""
+    from limbo_b200 import _lib, synth
+    gp, og, X, Y = _make(kname, N, D, P=P)
+    Xq = synth.points(777, M, D)
+    mu, s2 = gp.query_batch(Xq)
+    sub = np.arange(0, M, 23)
+    mu_o, s2_o = og.query(Xq[sub], nthreads=8)
+    assert np.abs(mu[sub] - (mu_o + Y.mean(axis=0))).max() <= TOL_ABS
+    assert np.abs(s2[sub] - s2_o).max() <= TOL_ABS
+    mu2, s22 = gp.query_batch(Xq)
+    assert np.array_equal(mu, mu2) and np.array_equal(s2, s22)
+    perm = np.random.default_rng(0).permutation(M)
+    mu3, s23 = gp.query_batch(Xq[perm])
+    assert np.array_equal(mu3, mu[perm]) and np.array_equal(s23, s2[perm])
+    lib = _lib.load()
+    lib.lb_debug_set_query_panel_min(1 << 40)
+    try:
+        mu_s, s2_s = gp.query_batch(Xq)
+    finally:
+        lib.lb_debug_set_query_panel_min(0)
+    assert np.abs(mu - mu_s).max() <= 1e-12 * max(1.0, np.abs(mu).max()) and np.abs(s2 - s2_s).max() <= 1e-12
+    # the factor changes: the cached diagonal-block inverses must follow
+    gp.kernel_function().set_h_params(gp.kernel_function().h_params() - 0.2)
+    gp.recompute(False)
+    mu4, s24 = gp.query_batch(Xq)
+    lib.lb_debug_set_query_panel_min(1 << 40)
+    try:
+        mu5, s25 = gp.query_batch(Xq)
+    finally:
+        lib.lb_debug_set_query_panel_min(0)
+    assert np.abs(mu4 - mu5).max() <= 1e-12 * max(1.0, np.abs(mu4).max()) and np.abs(s24 - s25).max() <= 1e-12
+    assert np.abs(s24 - s2).max() > 1e-6
 
 
 def test_identical_samples_full_vs_incremental(oracle_mod):
