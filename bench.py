@@ -60,7 +60,7 @@ def workload_config(n_gpus: int) -> dict:
         "global_candidates": M_CAND, "candidates_per_gpu": per,
         "parallelism": (f"fit replicated per GPU, {M_CAND} candidates sharded x{n_gpus} (<= {per} each), one all_gather of 16-byte records for the argmax"
                         if n_gpus > 1 else "single GPU"),
-        "l2": "inputs larger than L2 (factor 2.1 GB, V slabs 1.4 GB vs 126 MB L2); no explicit flush",
+        "l2": "inputs larger than L2 (factor 2.1 GB, K* / V 1.3 GB vs 126 MB L2); no explicit flush",
         "hyperparams": "reference defaults: log ell_d = 0, log sigma_f = 0, noise 0.01, UCB alpha 0.5, mean::Data",
         "seeds": {"data": 1234, "candidates": 1235},
     }
@@ -386,7 +386,11 @@ def roofline_table(prof: dict, steps: int, t_ms: float, n: int, d: int, m_local:
             row["note"] = note
         rows.append(row)
 
-    add("qstep", "query_slab_kernel (fused K* + blocked TRSM + mu / sigma^2, fp64 DMMA)", "tensor", float(m_local) * n * n, 1e12, peak_t, peak_t_src)
+    qname = ("panel_update_kernel + panel_solve_kernel (V = L^-1 K* over 2048-row super-blocks, fp64 DMMA)" if m_local >= 4096
+             else "query_slab_kernel (fused K* + blocked TRSM + mu / sigma^2, fp64 DMMA)")
+    add("qstep", qname, "tensor", float(m_local) * n * n, 1e12, peak_t, peak_t_src,
+        "M N^2 flops per batch (triangular solve, 2 flops per MAC on N^2 / 2); launches of one batch are averaged")
+    add("kstar", "kstar_kernel (K* = k(X, Xq), N x M)", "hbm", 8.0 * n * m_local + 8.0 * (n + m_local) * d, 1e9, peak_h, peak_h_src)
     add("syrk", "syrk_kernel K=256 (Cholesky trailing update, fp64 DMMA)", "tensor", syrk_flops_per_fit(n), 1e12, peak_t, peak_t_src)
     add("kbuild", "kbuild_kernel (N x N kernel matrix)", "hbm", 8.0 * n * n + 8.0 * n * d, 1e9, peak_h, peak_h_src)
     add("trsv", "trsv_fwd/bwd_kernel (alpha = L^-T L^-1 obs_mean)", "hbm", 2 * 4.0 * n * n, 1e9, peak_h, peak_h_src,
@@ -701,7 +705,7 @@ def run_ours(args) -> None:
         if table:
             top = dict(table[0])
             cls = top["class"]
-            kname = {"qstep": "query_slab_kernel", "syrk": "syrk_kernel", "kbuild": "kbuild_kernel"}.get(cls)
+            kname = {"qstep": ("panel_update_kernel" if m_loc >= 4096 else "query_slab_kernel"), "syrk": "syrk_kernel", "kbuild": "kbuild_kernel"}.get(cls)
             tr, cap = ncu_traffic(kname) if kname else (None, None)
             top["traffic"] = tr
             top["traffic_capture"] = cap

@@ -251,7 +251,8 @@ void free_ws(QueryWs& w)
 
 void free_model(lb_gp* h)
 {
-    void* all[] = {h->dX, h->dXs, h->dY, h->dL, h->dInvD, h->dAlpha, h->dLinv, h->dKinv, h->dFlags, h->dLinv32, h->dWork, h->dLinvW};
+    void* all[] = {h->dX, h->dXs, h->dY, h->dL, h->dInvD, h->dAlpha, h->dLinv, h->dKinv, h->dFlags, h->dLinv32, h->dWork, h->dLinvW, h->dTrsvX};
+    h->dTrsvX = nullptr; h->trsvx_np = 0;
     for (void* p : all) lb_pool_free(p); // shared buffers (lb_clone) only lose this handle's reference
     h->dWork = nullptr; h->work_np = 0; h->dLinvW = nullptr; h->linvw_np = 0;
     h->dLinv32 = nullptr; h->linv32_valid = false; h->linv32_rows = 0;

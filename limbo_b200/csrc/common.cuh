@@ -306,7 +306,8 @@ struct lb_gp {
     double* dKinv = nullptr; // Np x Np (lazy: K^-1, lower valid + mirrored)
     float* dLinv32 = nullptr; int64_t linv32_rows = 0; bool linv32_valid = false; double linv32_scale = 1.0; // reduced-precision path: row-major fp32 / fp16 L^-1
     int* dInfo = nullptr;    // [0] first failing pivot (1-based) or 0; [1] solver error
-    int* dFlags = nullptr;   // T+1 ints: trsv progress flags / ticket
+    int* dFlags = nullptr;   // T+8 ints: ticket counters of the persistent solves
+    double* dTrsvX = nullptr; int64_t trsvx_np = 0; // trsv: published solution blocks (sentinel-filled per launch)
     double* dScratch = nullptr; size_t scratch_bytes = 0;
 
     bool fitted = false;

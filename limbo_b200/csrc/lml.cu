@@ -154,31 +154,39 @@ __device__ __forceinline__ void tile_from_index(int t, int& bi, int& bj)
 // grad partials: part[tile][q], q < nh.
 //   sum_{i>=j} w_ij * dK_ij/dtheta_q * (1/2 if i==j)        gp.hpp:299-308
 //   w = alpha alpha^T - K^-1                                  gp.hpp:293-296
-__global__ void __launch_bounds__(256, 2)
-grad_kernel(const double* __restrict__ Xs, const double* __restrict__ Kinv, const double* __restrict__ alpha, int P,
-    int64_t N, int64_t Np, KernParams kp, int optimize_noise, int nh, double* __restrict__ part)
+// One pass over the lower tiles of K^-1 (HBM floor 4 N^2 bytes).  Round 1 ran at 0.085 of that floor: libm exp, two global
+// loads of alpha per element and output, 64-bit index predicates on every element.  Now the kernel id and the edge handling
+// are template parameters (interior tiles carry no predicates), alpha_i / alpha_j are staged in shared memory, and the
+// exponentials use the branch-free lb_exp_nonpos (<= 3e-16 relative, inside the 1e-9 bar of the gradient).
+constexpr int GRAD_PMAX = 4; // outputs staged in shared memory (more: global loads)
+
+template <int KID, bool EDGE>
+__device__ __forceinline__ void grad_tile(const double* __restrict__ Xs, const double* __restrict__ Kinv, const double* __restrict__ alpha, int P,
+    int64_t N, int64_t Np, const KernParams& kp, int optimize_noise, int nh, double* __restrict__ part, int bi, int bj,
+    double (*sxi)[LB_TILE], double (*sxj)[LB_TILE], double (*sai)[LB_TILE], double (*saj)[LB_TILE], double (*sred)[DCH + 4], double* stot,
+    uint64_t* barp)
 {
-    __shared__ __align__(128) double sxi[DCH][LB_TILE];
-    __shared__ __align__(128) double sxj[DCH][LB_TILE];
-    __shared__ double sred[8][DCH + 4];
-    __shared__ double stot[LB_MAX_D + 2];
-    __shared__ __align__(8) uint64_t bar;
-    int bi, bj;
-    tile_from_index(blockIdx.x, bi, bj);
+    uint64_t& bar = *barp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int li = lane & 7, lj = lane >> 3;
     const int D = kp.D;
     const int64_t i0 = (int64_t)bi * LB_TILE, j0 = (int64_t)bj * LB_TILE;
     const int r0 = warp * 16 + 2 * li;
+    constexpr bool ard = (KID == LB_K_SE_ARD);
     if (tid == 0) {
         lb_mbar_init(&bar, 1);
         lb_fence_barrier_init();
     }
     for (int q = tid; q < LB_MAX_D + 2; q += 256) stot[q] = 0.0;
+    const int Ps = P < GRAD_PMAX ? P : GRAD_PMAX;
+    for (int idx = tid; idx < Ps * LB_TILE; idx += 256) {
+        const int p = idx >> 7, c = idx & 127;
+        sai[p][c] = alpha[i0 + c + (int64_t)p * Np];
+        saj[p][c] = alpha[j0 + c + (int64_t)p * Np];
+    }
     __syncthreads();
     uint32_t phase = 0;
     const int npass = (D + DCH - 1) / DCH;
-    const bool ard = (kp.id == LB_K_SE_ARD);
 
     auto stage = [&](int pass) {
         const int d0 = pass * DCH;
@@ -204,6 +212,15 @@ grad_kernel(const double* __restrict__ Xs, const double* __restrict__ Kinv, cons
         for (int c = 0; c < 8; ++c)
 #pragma unroll
             for (int e = 0; e < 4; ++e) z[c][e] = 0.0;
+        // the K^-1 values of this half: issued before the distance sweep so that their latency hides under it
+        const int64_t gi = i0 + r0;
+        double2 kv[8][2];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int64_t gj = j0 + h * 64 + c * 8 + 2 * lj;
+            kv[c][0] = __ldcs(reinterpret_cast<const double2*>(&Kinv[gi + gj * Np]));
+            kv[c][1] = __ldcs(reinterpret_cast<const double2*>(&Kinv[gi + (gj + 1) * Np]));
+        }
         for (int pass = 0; pass < npass; ++pass) {
             int dc = D;
             if (!(npass == 1 && h == 1)) dc = stage(pass);
@@ -221,57 +238,59 @@ grad_kernel(const double* __restrict__ Xs, const double* __restrict__ Kinv, cons
                 }
             }
         }
-        // weights w_ij * f_ij, and the parameter-independent factors
-        const int64_t gi = i0 + r0;
-        double wk[8][4]; // SE-ARD: w*f*k ; others unused
+        // weights w_ij * f_ij and the parameter-independent factors
+        double wk[8][4]; // SE-ARD: w * f * k
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const int64_t gj = j0 + h * 64 + c * 8 + 2 * lj;
-            const double2 kv0 = *reinterpret_cast<const double2*>(&Kinv[gi + gj * Np]);
-            const double2 kv1 = *reinterpret_cast<const double2*>(&Kinv[gi + (gj + 1) * Np]);
-            const double kin[4] = {kv0.x, kv0.y, kv1.x, kv1.y};
+            const int cl = h * 64 + c * 8 + 2 * lj; // local column
+            const int64_t gj = j0 + cl;
+            const double kin[4] = {kv[c][0].x, kv[c][0].y, kv[c][1].x, kv[c][1].y};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int64_t ii = gi + (e & 1), jj = gj + (e >> 1);
+                const int rl = r0 + (e & 1), cc = cl + (e >> 1);
                 double w = -kin[e];
-                for (int p = 0; p < P; ++p) w = fma(alpha[ii + (int64_t)p * Np], alpha[jj + (int64_t)p * Np], w);
-                double f = (ii == jj) ? 0.5 : ((ii > jj) ? 1.0 : 0.0);
-                if (ii >= N || jj >= N) f = 0.0;
-                w *= f;
+                for (int p = 0; p < Ps; ++p) w = fma(sai[p][rl], saj[p][cc], w);
+                for (int p = Ps; p < P; ++p) w = fma(alpha[i0 + rl + (int64_t)p * Np], alpha[j0 + cc + (int64_t)p * Np], w);
+                if (EDGE) { // diagonal tile (strictly upper part does not count, the diagonal counts half) or padding
+                    const int64_t ii = gi + (e & 1), jj = gj + (e >> 1);
+                    double f = (ii == jj) ? 0.5 : ((ii > jj) ? 1.0 : 0.0);
+                    if (ii >= N || jj >= N) f = 0.0;
+                    w *= f;
+                    if (ii == jj) g_noise = fma(w, 2.0 * kp.noise, g_noise); // kernel.hpp:90-93
+                }
                 const double zz = z[c][e];
                 if (ard) { // squared_exp_ard.hpp:127-135
-                    double k = kp.sf2 * exp(-0.5 * zz);
+                    const double k = kp.sf2 * lb_exp_nonpos(-0.5 * zz);
                     wk[c][e] = w * k;
                     g_sf = fma(w, 2.0 * k, g_sf);
                 }
                 else {
                     wk[c][e] = 0.0;
                     double g0, g1;
-                    if (kp.id == LB_K_MATERN52) { // matern_five_halves.hpp:115-133
-                        double d = sqrt(zz), d_sq = d * d, l_sq = kp.l * kp.l;
-                        double term1 = sqrt(5.0) * d / kp.l;
-                        double term2 = 5. * d_sq / (3. * l_sq);
-                        double r = lb_exp_nonpos(-term1);
+                    if (KID == LB_K_MATERN52) { // matern_five_halves.hpp:115-133
+                        const double d = sqrt(zz), d_sq = d * d, l_sq = kp.l * kp.l;
+                        const double term1 = sqrt(5.0) * d / kp.l;
+                        const double term2 = 5. * d_sq / (3. * l_sq);
+                        const double r = lb_exp_nonpos(-term1);
                         g0 = kp.sf2 * (r * term1 * (1 + term1 + term2) + (-term1 - 2. * term2) * r);
                         g1 = 2 * kp.sf2 * (1 + term1 + term2) * r;
                     }
-                    else if (kp.id == LB_K_MATERN32) { // matern_three_halves.hpp:110-124
-                        double d = sqrt(zz);
-                        double term = sqrt(3.0) * d / kp.l;
-                        double r = lb_exp_nonpos(-term);
+                    else if (KID == LB_K_MATERN32) { // matern_three_halves.hpp:110-124
+                        const double d = sqrt(zz);
+                        const double term = sqrt(3.0) * d / kp.l;
+                        const double r = lb_exp_nonpos(-term);
                         g0 = kp.sf2 * (-term * r + (1 + term) * term * r);
                         g1 = 2 * kp.sf2 * (1 + term) * r;
                     }
                     else { // exp.hpp:101-110
-                        double r = zz / (kp.l * kp.l);
-                        double k = kp.sf2 * exp(-0.5 * r);
+                        const double r = zz / (kp.l * kp.l);
+                        const double k = kp.sf2 * lb_exp_nonpos(-0.5 * r);
                         g0 = r * k;
                         g1 = 2 * k;
                     }
                     g_l = fma(w, g0, g_l);
                     g_sf = fma(w, g1, g_sf);
                 }
-                if (ii == jj) g_noise = fma(w, 2.0 * kp.noise, g_noise); // kernel.hpp:90-93
             }
         }
         if (ard) {
@@ -303,8 +322,10 @@ grad_kernel(const double* __restrict__ Xs, const double* __restrict__ Kinv, cons
                 }
 #pragma unroll
                 for (int d = 0; d < DCH; ++d) {
-                    double s = lb_warp_sum(gd[d]);
-                    if (lane == 0) sred[warp][d] = s;
+                    if (d < dc) { // dc is uniform over the CTA
+                        double s = lb_warp_sum(gd[d]);
+                        if (lane == 0) sred[warp][d] = s;
+                    }
                 }
                 __syncthreads();
                 if (tid < dc) {
@@ -340,6 +361,25 @@ grad_kernel(const double* __restrict__ Xs, const double* __restrict__ Kinv, cons
             if (optimize_noise) out[2] = c;
         }
     }
+}
+
+template <int KID>
+__global__ void __launch_bounds__(256, 2)
+grad_kernel(const double* __restrict__ Xs, const double* __restrict__ Kinv, const double* __restrict__ alpha, int P,
+    int64_t N, int64_t Np, KernParams kp, int optimize_noise, int nh, double* __restrict__ part)
+{
+    __shared__ __align__(128) double sxi[DCH][LB_TILE];
+    __shared__ __align__(128) double sxj[DCH][LB_TILE];
+    __shared__ double sai[GRAD_PMAX][LB_TILE];
+    __shared__ double saj[GRAD_PMAX][LB_TILE];
+    __shared__ double sred[8][DCH + 4];
+    __shared__ double stot[LB_MAX_D + 2];
+    __shared__ __align__(8) uint64_t bar;
+    int bi, bj;
+    tile_from_index(blockIdx.x, bi, bj);
+    const bool edge = (bi == bj) || ((int64_t)(bi + 1) * LB_TILE > N);
+    if (edge) grad_tile<KID, true>(Xs, Kinv, alpha, P, N, Np, kp, optimize_noise, nh, part, bi, bj, sxi, sxj, sai, saj, sred, stot, &bar);
+    else grad_tile<KID, false>(Xs, Kinv, alpha, P, N, Np, kp, optimize_noise, nh, part, bi, bj, sxi, sxj, sai, saj, sred, stot, &bar);
 }
 
 __global__ void __launch_bounds__(256)
@@ -459,8 +499,12 @@ int lb_launch_grad(lb_gp* h, int optimize_noise, double* dGrad)
     int rc = lb_ensure_scratch(h, sizeof(double) * (size_t)ntiles * nh);
     if (rc) return rc;
     LbProfScope ps(h, h->stream, LB_PC_GRAD);
-    grad_kernel<<<ntiles, 256, 0, h->stream>>>(h->dXs, h->dKinv, h->dAlpha, h->P, h->N, h->Np, h->kp, optimize_noise, nh,
-        h->dScratch);
+    switch (h->kp.id) {
+    case LB_K_SE_ARD: grad_kernel<LB_K_SE_ARD><<<ntiles, 256, 0, h->stream>>>(h->dXs, h->dKinv, h->dAlpha, h->P, h->N, h->Np, h->kp, optimize_noise, nh, h->dScratch); break;
+    case LB_K_MATERN52: grad_kernel<LB_K_MATERN52><<<ntiles, 256, 0, h->stream>>>(h->dXs, h->dKinv, h->dAlpha, h->P, h->N, h->Np, h->kp, optimize_noise, nh, h->dScratch); break;
+    case LB_K_MATERN32: grad_kernel<LB_K_MATERN32><<<ntiles, 256, 0, h->stream>>>(h->dXs, h->dKinv, h->dAlpha, h->P, h->N, h->Np, h->kp, optimize_noise, nh, h->dScratch); break;
+    default: grad_kernel<LB_K_EXP><<<ntiles, 256, 0, h->stream>>>(h->dXs, h->dKinv, h->dAlpha, h->P, h->N, h->Np, h->kp, optimize_noise, nh, h->dScratch); break;
+    }
     grad_reduce_kernel<<<nh, 256, 0, h->stream>>>(h->dScratch, ntiles, nh, dGrad);
     h->launches += 2;
     LB_CUDA(cudaGetLastError());
