@@ -21,6 +21,8 @@ int lb_launch_loo_grad(lb_gp* h, int optimize_noise, double* dGrad);
 int lb_launch_kinv_obs(lb_gp* h, double* dOut);
 int lb_query_fused_supported(const lb_gp* h);
 size_t lb_query_panel_scratch_doubles(const lb_gp* h, int64_t Mp);
+int lb_launch_query_point(const lb_gp* h, cudaStream_t st, const double* x_host, double* dQs, double* dVscratch, double* dOutMapped,
+    long long* launches);
 int lb_launch_query_panel(lb_gp* h, cudaStream_t st, int64_t M, const double* dQs, int64_t Mp, double* dWork, double* dMu, double* dS2,
     long long* launches);
 size_t lb_query_fused_scratch_doubles(const lb_gp* h, int grid);
@@ -97,6 +99,9 @@ struct Extra {
     cudaStream_t own = nullptr; // the handle's own stream (h->stream may point at a caller's stream)
     double lambda_host[LB_MAX_D * LB_MAX_LAMBDA] = {}; // host mirror of dLambda (lb_set_kernel compares against it)
     long long n_append = 0; // incremental updates actually taken (tests)
+    double* hPoint = nullptr;  // pinned, mapped host buffer for the one-point query (mu[P], sigma^2)
+    double* dPoint = nullptr;  // its device alias
+    int point_cap = 0;
 };
 
 } // namespace
@@ -378,6 +383,7 @@ int lb_destroy(lb_gp* hh)
     lb_pool_free(h->dScratch);
     lb_pool_free(h->dLambda);
     lb_pool_free(h->ex.dMisc);
+    if (h->ex.hPoint) cudaFreeHost(h->ex.hPoint);
     Shell sh;
     sh.own = h->ex.own; sh.side = h->side;
     for (int i = 0; i < 6; ++i) sh.ev[i] = h->ev[i];
@@ -791,6 +797,24 @@ static int query_common(const lb_gp* hc, int64_t M, const double* Xq, bool xq_de
     if ((rc = ensure(h, &w.dS2, &w.s2_bytes, sizeof(double) * M))) return rc;
     const bool prior = (h->N == 0 || !h->fitted);
     if (prior && h->N != 0) return LB_ERR_STATE;
+    if (M == 1 && !prior && !xq_dev && !out_dev && !with_acq && h->precision == LB_PREC_FP64 && lb_query_fused_supported(h) && !h->force_unfused) {
+        // one launch, one synchronisation (query.cu: query_point_kernel)
+        Extra& ex = h->ex;
+        if (ex.point_cap < P + 1) {
+            if (ex.hPoint) cudaFreeHost(ex.hPoint);
+            ex.hPoint = ex.dPoint = nullptr;
+            LB_CUDA(cudaHostAlloc((void**)&ex.hPoint, sizeof(double) * (P + 1 + 7), cudaHostAllocMapped));
+            LB_CUDA(cudaHostGetDevicePointer((void**)&ex.dPoint, ex.hPoint, 0));
+            ex.point_cap = P + 1 + 7;
+        }
+        if ((rc = ensure(h, &w.dQs, &w.qs_bytes, sizeof(double) * De * LB_TILE))) return rc;
+        if ((rc = ensure(h, &w.dV, &w.v_bytes, sizeof(double) * lb_query_fused_scratch_doubles(h, 1)))) return rc;
+        if ((rc = lb_launch_query_point(h, st, Xq, w.dQs, w.dV, ex.dPoint, &h->launches))) return rc;
+        LB_CUDA(cudaStreamSynchronize(st));
+        if (mu_out) std::memcpy(mu_out, ex.hPoint, sizeof(double) * P);
+        if (s2_out) *s2_out = ex.hPoint[P];
+        return LB_OK;
+    }
     if (prior) { // gp.hpp:161-163: mu = mean(v) (added by the caller), sigma2 = k(v,v) + noise
         LB_CUDA(cudaMemsetAsync(w.dMu, 0, sizeof(double) * M * P, st));
         fill_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(w.dS2, M, h->kp.sf2 + h->kp.noise);

@@ -688,6 +688,28 @@ query_slab_kernel(const double* __restrict__ L, int64_t ld, const double* __rest
     }
 }
 
+// One point, one launch: the candidate travels in the kernel arguments (no host-to-device copy, no packing kernel) and
+// mu / sigma^2 are written straight into mapped pinned host memory (no device-to-host copies): a GP::query(v) /
+// mu(v) / sigma(v) call (gp.hpp:159-191 - what the reference's inner optimisers and its regression benchmark issue 10^4
+// times in a row, waf_tools/benchmark_template.cpp:95-120) costs one launch and one stream synchronisation.  Same
+// slab_body as the batched kernel, so the value is bit-identical to the same point inside a slab-path batch.
+struct PointArg { double x[LB_MAX_D]; };
+
+__global__ void __launch_bounds__(THREADS, 1)
+query_point_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ invD, const double* __restrict__ Xs, int64_t N,
+    const __grid_constant__ PointArg q, double* __restrict__ Qs, const double* __restrict__ alpha, int P, const __grid_constant__ KernParams kp,
+    double* __restrict__ Vscratch, double* __restrict__ out)
+{
+    extern __shared__ __align__(16) double sm[];
+    for (int idx = threadIdx.x; idx < kp.D * 8; idx += THREADS) { // staged coordinates of the point in column 0 of an 8-wide tile
+        const int d = idx >> 3, c = idx & 7;
+        Qs[d * LB_TILE + c] = (c == 0) ? lb_staged_coord(kp, d, [&](int r) { return q.x[r]; }) : 0.0;
+    }
+    __threadfence_block();
+    __syncthreads();
+    slab_body<0>(sm, L, ld, invD, Xs, N, Qs, LB_TILE, 1, alpha, P, kp, Vscratch, 0, 1, out, out + P);
+}
+
 LbOncePerDevice g_attr_once2;
 
 } // namespace slab
@@ -831,6 +853,24 @@ int lb_launch_query_panel(lb_gp* h, cudaStream_t st, int64_t M, const double* dQ
 
 int lb_query_fused_supported(const lb_gp* h) { return h->kp.D <= slab::DMAXF && h->P <= slab::PMAXF; }
 size_t lb_query_fused_scratch_doubles(const lb_gp* h, int grid) { return (size_t)grid * h->Np * slab::SLAB; }
+
+// one point (host coordinates x[0..D)), results in dOutMapped[0..P) = mu, [P] = sigma^2 (device alias of pinned host memory)
+int lb_launch_query_point(const lb_gp* h, cudaStream_t st, const double* x_host, double* dQs, double* dVscratch, double* dOutMapped,
+    long long* launches)
+{
+    static LbOncePerDevice once;
+    if (once.need()) {
+        LB_CUDA(cudaFuncSetAttribute(slab::query_point_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab::SMEM_BYTES));
+    }
+    slab::PointArg q;
+    for (int d = 0; d < LB_MAX_D; ++d) q.x[d] = d < h->D ? x_host[d] : 0.0;
+    LbProfScope ps(h, st, LB_PC_QSTEP);
+    slab::query_point_kernel<<<1, slab::THREADS, slab::SMEM_BYTES, st>>>(h->dL, h->Np, h->dInvD, h->dXs, h->N, q, dQs, h->dAlpha, h->P, h->kp,
+        dVscratch, dOutMapped);
+    if (launches) ++*launches;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
 
 int lb_launch_query_fused(const lb_gp* h, cudaStream_t st, int64_t M, const double* dQs, int64_t Mp, double* dVscratch,
     int grid, double* dMu, double* dS2, long long* launches)

@@ -148,8 +148,22 @@ class DistCholesky:
         ev_panel = Ev()      # panel packed (owner)
         ev_bcast = Ev()      # panel arrived
         ev_free = [None, None]  # buffer last read by an update
-        self.info.zero_()
+        # optional per-step timeline (LB_DCHOL_TIMELINE=<file prefix>): CUDA timing events at the end of every panel,
+        # broadcast and update of this rank, dumped as JSON after the run (diagnosis of the critical path; not used by the product)
+        import os as _os
+        tl_prefix = _os.environ.get("LB_DCHOL_TIMELINE")
+        tl = [] if tl_prefix else None
+
+        def mark(tag, p, stream):
+            if tl is not None:
+                e = Ev(enable_timing=True)
+                e.record(stream)
+                tl.append((tag, p, e))
+        with torch.cuda.stream(self.main):
+            self.info.zero_()  # on the stream whose kernels consume it (not torch's current stream)
+        self.side.wait_stream(self.main)
         ev_a.record(self.main)  # after build()
+        mark("start", -1, self.main)
         have_a = True
         for act in schedule(self.npairs, self.rank, self.world):
             kind, p = act[0], act[1]
@@ -164,6 +178,7 @@ class DistCholesky:
                 _lib.check(lib.lb_dchol_panel(self._h_side, cols, self.Nd, 2 * p, self.invD.data_ptr(), self.info.data_ptr(),
                                               buf.data_ptr()), "lb_dchol_panel")
                 ev_panel.record(self.side)
+                mark("panel", p, self.side)
             elif kind == "bcast":
                 owner = act[2]
                 n = PAIR * self._ldp(p)
@@ -175,6 +190,7 @@ class DistCholesky:
                     if self.world > 1:
                         dist.broadcast(buf[:n], src=owner, group=self.group)
                     ev_bcast.record(self.comm)
+                    mark("bcast", p, self.comm)
                 self.main.wait_event(ev_bcast)
             else:
                 _, _, l0, l1, tag = act
@@ -182,6 +198,7 @@ class DistCholesky:
                                                self.world), "lb_dchol_update")
                 if tag == "a":
                     ev_a.record(self.main)
+                mark("update_" + tag, p, self.main)
                 e = Ev()
                 e.record(self.main)
                 ev_free[p % 2] = e
@@ -202,6 +219,13 @@ class DistCholesky:
         allrec = allrec.cpu().numpy()
         infos = allrec[:, 1][allrec[:, 1] > 0]
         self.launches = int(lib.lb_launch_count(self._h_main) + lib.lb_launch_count(self._h_side))
+        if tl is not None:
+            import json as _json
+            torch.cuda.synchronize(self.device)
+            t0 = tl[0][2]
+            rows = [[tag, p, t0.elapsed_time(e)] for tag, p, e in tl]
+            with open(f"{tl_prefix}_rank{self.rank}.json", "w") as f:
+                _json.dump({"world": self.world, "N": self.N, "events_ms": rows}, f)
         return (int(infos.min()) if infos.size else 0), float(2.0 * allrec[:, 0].sum())
 
     # ---- helpers for checks ----------------------------------------------------------------------------------

@@ -1,6 +1,9 @@
-"""Latency sweep in the regime Limbo is normally run in (tens to thousands of samples): device-timed fit, add_sample and
-10^4-candidate UCB argmax per N, with the CPU restatement (oracle, 1 thread fit / all cores query) beside it.
-usage: python tools/small_n_sweep.py [--sizes 64,128,...] [--m 10000]"""
+"""Latency sweep in the regime Limbo is normally run in and benchmarked in by the reference itself (N in {50, ..., 600},
+learning time and 10^4 SEQUENTIAL query() calls: waf_tools/benchmark_template.cpp:95-120, regression_benchmarks.json):
+device-timed fit and 10^4-candidate UCB argmax, host-visible compute() / add_sample() / one-point query() latency (the
+one-launch path: query_point_kernel) per N, with the CPU restatement (oracle: 1-thread fit, 1-thread one-point queries, the
+reference's protocol) beside it.
+usage: python tools/small_n_sweep.py [--sizes 50,100,...] [--m 10000]"""
 import argparse
 import ctypes as C
 import json
@@ -16,7 +19,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--sizes", default="64,128,256,512,1024,2048,4096")
+    ap.add_argument("--sizes", default="50,100,200,300,400,500,600,1024,2048,4096")
     ap.add_argument("--m", type=int, default=10000)
     ap.add_argument("--dim", type=int, default=6)
     ap.add_argument("--cpu", type=int, default=1)
@@ -57,8 +60,16 @@ def main():
         t0 = time.perf_counter(); gp.compute(X[:N], y[:N, None]); t_fit_api = (time.perf_counter() - t0) * 1e3
         t0 = time.perf_counter(); gp.add_sample(X[N], y[N:N + 1]); t_add_api = (time.perf_counter() - t0) * 1e3
         t0 = time.perf_counter(); acqui.UCB(gp).argmax_batch(Xq); t_acq_api = (time.perf_counter() - t0) * 1e3
+        gp.query(Xq[0])
+        nq = 300
+        t0 = time.perf_counter()
+        for i in range(nq):
+            gp.query(Xq[i])  # sequential one-point calls through the public API, like the reference benchmark
+        t_q1 = (time.perf_counter() - t0) / nq * 1e6
+        t0 = time.perf_counter(); gp.query_batch(Xq); t_qb = (time.perf_counter() - t0) * 1e3
         row = {"N": N, "fit_ms_dev": fit_ms, "acq10k_ms_dev": q_ms, "compute_ms_api": t_fit_api, "add_sample_ms_api": t_add_api,
-               "acq10k_ms_api": t_acq_api}
+               "acq10k_ms_api": t_acq_api, "query1_us_api_sequential": t_q1, "query10k_sequential_ms_extrapolated": t_q1 * M / 1e3,
+               "query10k_batched_ms_api": t_qb}
         if a.cpu:
             from oracle import oracle as O
             og = O.OracleGP()
@@ -67,6 +78,8 @@ def main():
             t0 = time.perf_counter(); og.fit(); row["cpu_fit_ms_1thread"] = (time.perf_counter() - t0) * 1e3
             mq = min(M, 2000)
             t0 = time.perf_counter(); og.query(Xq[:mq], nthreads=os.cpu_count()); row["cpu_query10k_ms_allcores"] = (time.perf_counter() - t0) * 1e3 * M / mq
+            m1 = min(M, 300)
+            t0 = time.perf_counter(); og.query(Xq[:m1], nthreads=1); row["cpu_query1_us_1thread"] = (time.perf_counter() - t0) * 1e6 / m1
         rows.append(row)
         print(json.dumps(row), flush=True)
 
