@@ -81,6 +81,9 @@ trsv_fwd_kernel(const double* __restrict__ L, int64_t ld, const double* __restri
     double acc[NR];
 #pragma unroll
     for (int p = 0; p < NR; ++p) acc[p] = 0.0;
+    // this block's right-hand side, fetched now (off the dependency chain)
+    double bi = 0.0;
+    if (tid < nr * LB_TILE) bi = B[(int64_t)i * LB_TILE + (tid & 127) + (int64_t)(tid >> 7) * ldb];
 
     for (int j = 0; j < i; ++j) {
         // issue the loads of L[i,j] before waiting on x_j
@@ -109,9 +112,9 @@ trsv_fwd_kernel(const double* __restrict__ L, int64_t ld, const double* __restri
     lb_cp_async_wait<0>();
     __syncthreads();
     // rhs block: b_i - sum
-    for (int idx = tid; idx < nr * LB_TILE; idx += 256) {
-        int p = idx >> 7, c = idx & 127;
-        xs[p][c] = B[(int64_t)i * LB_TILE + c + (int64_t)p * ldb] - (part[0][p][c] + part[1][p][c]);
+    if (tid < nr * LB_TILE) {
+        const int p = tid >> 7, c = tid & 127;
+        xs[p][c] = bi - (part[0][p][c] + part[1][p][c]);
     }
     __syncthreads();
     // x_i = invD_i * rhs (from shared memory)
@@ -157,6 +160,8 @@ trsv_bwd_kernel(const double* __restrict__ L, int64_t ld, const double* __restri
     for (int p = 0; p < NR; ++p)
 #pragma unroll
         for (int cc = 0; cc < 16; ++cc) acc[p][cc] = 0.0;
+    double bi = 0.0; // this block's right-hand side, fetched off the dependency chain
+    if (tid < nr * LB_TILE) bi = B[(int64_t)i * LB_TILE + (tid & 127) + (int64_t)(tid >> 7) * ldb];
 
     for (int j = T - 1; j > i; --j) {
         const double* Lt = L + (int64_t)j * LB_TILE + lane + ((int64_t)i * LB_TILE + warp) * ld;
@@ -193,9 +198,9 @@ trsv_bwd_kernel(const double* __restrict__ L, int64_t ld, const double* __restri
         }
     lb_cp_async_wait<0>();
     __syncthreads();
-    for (int idx = tid; idx < nr * LB_TILE; idx += 256) {
-        int p = idx >> 7, c = idx & 127;
-        xs[p][c] = B[(int64_t)i * LB_TILE + c + (int64_t)p * ldb] - red[p][c];
+    if (tid < nr * LB_TILE) {
+        const int p = tid >> 7, c = tid & 127;
+        xs[p][c] = bi - red[p][c];
     }
     __syncthreads();
     // x_i = invD_i^T * rhs : column dot products over the staged block

@@ -24,6 +24,26 @@ TILE = 128
 PAIR = 2 * TILE
 
 
+_PANEL_GROUP = None
+
+
+def panel_group():
+    """Process group for the panel broadcasts whose NCCL kernels run on a HIGH-PRIORITY stream.  The trailing update keeps
+    every SM full (two resident CTAs per SM, thousands of blocks pending); a broadcast kernel launched at default priority is
+    only scheduled once the update has drained, i.e. the exchange step would not overlap the update at all (measured round 2:
+    every broadcast ended right after the previous update, profiles/r02_dchol_timeline_n2.txt).  Collective: every rank must
+    call it (DistCholesky does, at construction).  Falls back to the default group when the option is unavailable."""
+    global _PANEL_GROUP
+    import torch.distributed as dist
+    if _PANEL_GROUP is None:
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            _PANEL_GROUP = dist.new_group(backend="nccl", pg_options=opts)
+        except Exception:
+            _PANEL_GROUP = dist.group.WORLD
+    return _PANEL_GROUP
+
+
 def padded_order(n: int) -> int:
     return (n + PAIR - 1) // PAIR * PAIR
 
@@ -75,6 +95,10 @@ class DistCholesky:
         import torch
         from . import _lib
         self._torch = torch
+        if group is None and world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_backend() == "nccl":
+                group = panel_group()
         self.rank, self.world, self.group = rank, world, group
         self.device = torch.device(device)
         self.N, self.D = X.shape
@@ -96,7 +120,7 @@ class DistCholesky:
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.main = torch.cuda.Stream(self.device)
         self.side = torch.cuda.Stream(self.device, priority=-1)
-        self.comm = torch.cuda.Stream(self.device)
+        self.comm = torch.cuda.Stream(self.device, priority=-1)
         self._h_main, self._h_side = vp(), vp()
         _lib.check(lib.lb_create(C.byref(self._h_main), dev_index, 0), "lb_create")
         _lib.check(lib.lb_create(C.byref(self._h_side), dev_index, 0), "lb_create")
