@@ -11,9 +11,11 @@ at N = 16384, D = 6, SquaredExpARD, fp64, M = 10000.
 `value`   : steps/s with inputs already resident in HBM (device-pointer ABI), CUDA events on the library's stream.
 `e2e`     : the same step through the public host API (limbo_b200.model.GP.compute + acqui.UCB.argmax_batch /
             dist.sharded_acq_argmax): host buffers in, host scalars out, copies inside the timed region.
-N > 1     : STRONG scaling of the same global job: the 10^4 candidates are sharded over the ranks, one all_gather picks the
-            argmax; the O(N^3) fit is replicated on every rank (a single N = 16384 factor does not shard without an
-            exchange step; that is config 5) and is the stated limiter.
+N > 1     : STRONG scaling of the same global job.  The fit is DISTRIBUTED (limbo_b200/dist_fit.py: block-cyclic panel
+            factorisation over the ranks, one panel broadcast per 256 columns, every rank assembles the complete factor from
+            the messages; bit-identical to the single-GPU factor), then the 10^4 candidates are sharded over the ranks and one
+            all_gather picks the argmax.  `limiter` names what bounds the step (--replicated-fit keeps the round-1 scheme:
+            every rank refits alone).
 `roofline`: the kernel with the largest share of the step, timed live with CUDA events around every launch
             (lb_profile_*); `roofline_kernels` is the per-kernel table.
 `config4` / `config5`: sub-records for the two multi-GPU splits BASELINE.json names (1M EI candidates in tf32 sharded over
@@ -58,7 +60,8 @@ def workload_config(n_gpus: int) -> dict:
         "workload": f"N={N_TRAIN}, D={DIM}, {KERNEL_NAME}, fp64, fit + {M_CAND} UCB queries + argmax (global job; candidates sharded over the GPUs)",
         "n_train": N_TRAIN, "dim": DIM, "kernel": KERNEL_NAME, "noise": NOISE,
         "global_candidates": M_CAND, "candidates_per_gpu": per,
-        "parallelism": (f"fit replicated per GPU, {M_CAND} candidates sharded x{n_gpus} (<= {per} each), one all_gather of 16-byte records for the argmax"
+        "parallelism": (f"fit distributed over {n_gpus} GPUs (1-D block-cyclic 256-column panels, one NCCL broadcast per panel, factor assembled on "
+                        f"every rank), {M_CAND} candidates sharded x{n_gpus} (<= {per} each), one all_gather of 16-byte records for the argmax"
                         if n_gpus > 1 else "single GPU"),
         "l2": "inputs larger than L2 (factor 2.1 GB, K* / V 1.3 GB vs 126 MB L2); no explicit flush",
         "hyperparams": "reference defaults: log ell_d = 0, log sigma_f = 0, noise 0.01, UCB alpha 0.5, mean::Data",
@@ -591,6 +594,15 @@ def run_ours(args) -> None:
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     gp.set_stream(stream.cuda_stream)
+    # N > 1: the fit itself is distributed over the ranks (limbo_b200/dist_fit.py) unless --replicated-fit
+    fitter = None
+    if world > 1 and not args.replicated_fit:
+        from limbo_b200 import dist_fit
+        gp.compute(X, y[:, None], compute_kernel=False)  # host-side state of the model (samples, obs_mean); no device fit
+        fitter = dist_fit.DistFit(gp, rank, world, dev)
+        if not fitter.supported(gp):
+            fitter.close()
+            fitter = None
 
     # ---------------- device-resident leg ("value") ----------------
     dX = torch.from_numpy(X).to(dev)
@@ -607,12 +619,19 @@ def run_ours(args) -> None:
     def step_dev():
         _lib.check(lib.lb_set_data_dev(h, n, d, 1, dX.data_ptr(), dY.data_ptr()), "set_data_dev")
         _lib.check(lib.lb_set_kernel(h, kid_dev, hp.ctypes.data, hp.size, NOISE), "set_kernel")
-        _lib.check(lib.lb_fit_async(h), "fit_async")
+        if fitter is not None:
+            t_f = time.perf_counter()
+            fitter.fit(gp, push=False)  # distributed K -> L (assembled on every rank) -> alpha; returns synchronised
+            fit_wall.append((time.perf_counter() - t_f) * 1e3)
+        else:
+            _lib.check(lib.lb_fit_async(h), "fit_async")
         _lib.check(lib.lb_acq_argmax_dev(h, 0, ap.ctypes.data, m_loc, dXq.data_ptr(), None, mean_const, None, dBest.data_ptr(),
                                          dIdx.data_ptr()), "acq_argmax_dev")
         if world > 1:  # one collective: (value, global index) records, reduced locally
             rec = torch.stack([dBest[0], (dIdx[0] + lo).to(torch.float64)])
             dist.all_gather(gather_buf, rec)
+
+    fit_wall: list[float] = []
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -624,9 +643,13 @@ def run_ours(args) -> None:
         step_dev()
     sync_all()
     _lib.check(lib.lb_check_info(h), "cholesky info")
+    fit_wall.clear()
 
     lib.lb_profile_enable(h, 1)
     prof_read(lib, h)
+    if fitter is not None:
+        lib.lb_profile_enable(fitter._h_main, 1)
+        prof_read(lib, fitter._h_main)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -643,6 +666,14 @@ def run_ours(args) -> None:
     clocks = sampler.stop() if rank == 0 else None
     prof = prof_read(lib, h)
     lib.lb_profile_enable(h, 0)
+    if fitter is not None:  # the trailing updates of the distributed fit run on the fitter's own handle
+        for k, v in prof_read(lib, fitter._h_main).items():
+            if k in prof:
+                prof[k]["ms_total"] += v["ms_total"]; prof[k]["launches"] += v["launches"]
+            else:
+                prof[k] = v
+        lib.lb_profile_enable(fitter._h_main, 0)
+    fit_wall_ms = float(np.mean(fit_wall)) if fit_wall else None
     tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -658,9 +689,17 @@ def run_ours(args) -> None:
     Xqp = torch.from_numpy(Xq_all).pin_memory()
     Xl, yl, Xql = Xp.numpy(), yp.numpy(), Xqp.numpy()  # pinned host buffers, one point per row
     ucb = acqui.UCB(gp2)
+    fitter2 = None
+    if fitter is not None:
+        gp2.compute(Xl, yl, compute_kernel=False)
+        fitter2 = dist_fit.DistFit(gp2, rank, world, dev)
 
     def step_e2e():
-        gp2.compute(Xl, yl)                     # host samples/observations in, H2D inside
+        if fitter2 is not None:
+            gp2.compute(Xl, yl, compute_kernel=False)  # host-side model state; the device fit is the distributed one
+            fitter2.fit(gp2)                           # H2D of samples / obs_mean inside
+        else:
+            gp2.compute(Xl, yl)                 # host samples/observations in, H2D inside
         # host candidates in, (value, global index) out; N > 1: this rank's shard + the one collective
         return lbdist.sharded_acq_argmax(ucb, Xql, rank, world, device=dev)
 
@@ -680,7 +719,11 @@ def run_ours(args) -> None:
     e2e_value = 1.0 / (float(tt.item()) / e2e_steps * 1e-3)
     h2d = n * d * 8 + n * 8 + m_loc * d * 8 + 2 * 8
     d2h = 8 + 8 + 8
+    if fitter2 is not None:
+        fitter2.close()
     del gp2
+    if fitter is not None:
+        fitter.close()
 
     # ---------------- sub-records: the multi-GPU splits BASELINE.json names ----------------
     sub4 = sub4_f16 = sub4_x3 = sub5 = None
@@ -733,9 +776,14 @@ def run_ours(args) -> None:
             "cpu_baseline": cpu,
             "cpu_lapack_batched": (cpu_lapack_sample() if (world == 1 and not args.no_cpu) else None),
             "stage_ms_per_step": stage,
-            "limiter": (f"strong scaling of one global job: the fit ({fit_ms:.1f} ms of main-stream kernels per step) is replicated on every "
-                        f"rank and does not shrink with N; only the query ({q_ms:.1f} ms here for {m_loc} of {m} candidates) shards"
-                        if world > 1 else "single GPU: fp64 DMMA pipe (query_slab_kernel + syrk_kernel)"),
+            "fit": ({"scheme": "distributed (limbo_b200/dist_fit.py)", "wall_ms_per_fit_rank0": fit_wall_ms} if (world > 1 and fit_wall_ms is not None)
+                    else {"scheme": "replicated on every rank" if world > 1 else "single GPU"}),
+            "limiter": ((f"strong scaling of one global job: distributed fit {fit_wall_ms:.1f} ms (trailing update {stage.get('syrk', 0.0):.1f} ms per GPU; the rest is the "
+                         f"owner's serial panel chain potf2 -> trsm -> column update -> potf2 -> trsm -> pack + one broadcast per 256 columns, exposed once "
+                         f"the per-GPU update is shorter than the chain) + sharded query {q_ms:.1f} ms ({m_loc} of {m} candidates)") if (world > 1 and fit_wall_ms is not None)
+                        else (f"strong scaling of one global job: the fit ({fit_ms:.1f} ms of main-stream kernels per step) is replicated on every "
+                              f"rank and does not shrink with N; only the query ({q_ms:.1f} ms here for {m_loc} of {m} candidates) shards") if world > 1
+                        else "single GPU: fp64 datapath (panel_update / panel_solve + syrk_kernel, all DMMA)"),
             "config4": sub4, "config4_fp16": sub4_f16, "config4_fp16x3": sub4_x3, "config5": sub5,
         }
         print(json.dumps(line))
@@ -786,6 +834,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
     ap.add_argument("--no-sub", action="store_true", help="skip the config4 / config5 sub-records")
+    ap.add_argument("--replicated-fit", action="store_true", help="N > 1: every rank refits alone (round-1 scheme) instead of the distributed fit")
     ap.add_argument("--workload", default="n16384_se_ard", choices=sorted(WORKLOADS) + ["config4"])
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp16"], help="--workload config4 only")
     args = ap.parse_args()

@@ -44,6 +44,22 @@ int lb_dchol_update(lb_gp* h, double* dLoc, int64_t Nd, const double* dPanel, in
  * sum_j log L_jj over this rank's columns with global index < N to *dLogdetPart (the log-det term of gp.hpp:272-274). */
 int lb_dchol_finish(lb_gp* h, double* dLoc, int64_t Nd, int64_t N, int rank, int G, int64_t ncols_local, double* dLogdetPart);
 
+/* ---- distributed FIT of one GP (limbo_b200/dist_fit.py): the factorisation above, with every rank assembling the complete
+ * factor in a regular handle from the panel messages, so that lb_query / lb_acq_argmax can then shard the candidates over the
+ * ranks with no further exchange (GP::compute, gp.hpp:88-116, spread over the GPUs; the result is bit-identical to lb_fit).
+ * Message of pair kpair:  [ 256 x 256 diagonal block (column-major, ld 256) | inv(L_kk), inv(L_k+1,k+1) (2 x 128 x 128) |
+ * rows below the pair (ld = Nd - (kpair + 2) * 128) ]:  LB_DCHOL_HEAD doubles, then what lb_dchol_panel packs. */
+#define LB_DCHOL_HEAD (256 * 256 + 2 * 128 * 128)
+/* owner: head of the message (call after lb_dchol_panel, same handle / stream; dInvD = lb_dchol_panel's scratch) */
+int lb_dchol_pack_head(lb_gp* h, const double* dCols, int64_t Nd, int kpair, const double* dInvD, double* dMsg);
+/* target handle (lb_set_data + lb_set_kernel done; its padded order must equal Nd, else LB_ERR_UNSUPPORTED -> use lb_fit) */
+int lb_dchol_adopt_begin(lb_gp* h, int64_t Nd);
+/* copy one panel message into the handle's factor and diagonal-block inverses, on cuda_stream (NULL: the handle's stream) */
+int lb_dchol_unpack(lb_gp* h, const double* dMsg, int64_t Nd, int kpair, void* cuda_stream);
+/* all messages unpacked: the handle is fitted, alpha = K^-1 obs_mean is solved locally (gp.hpp:605-611); info = the
+ * factorisation's LAPACK-style info (> 0 is returned as is) */
+int lb_dchol_adopt_end(lb_gp* h, int info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1168,6 +1168,97 @@ int lb_clone(const lb_gp* src, lb_gp** out)
     return LB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Distributed fit (limbo_b200/dist_fit.py): the factor of ONE GP is computed by all ranks together with the block-cyclic
+// panel factorisation of config 5 (potrf.cu lb_dchol_*), and every rank assembles the complete factor in its own handle
+// from the panels that travel anyway, so that prediction / acquisition can then shard over the ranks without any further
+// exchange.  The panel message of pair p is  [ head: the pair's 256 x 256 diagonal block, column-major ld 256 |
+// inv(L_kk), inv(L_k+1,k+1) : 2 x 128 x 128 | rows below the pair, ld = Nd - (kpair + 2) * 128 ]  (LB_DCHOL_HEAD doubles
+// before the rows).  The update order per tile is lb_fit's, so the assembled factor is bit-identical to lb_fit's.
+// ---------------------------------------------------------------------------------------------------------------------
+#define LB_DCHOL_HEAD (2 * LB_TILE * 2 * LB_TILE + 2 * LB_TILE * LB_TILE)
+
+namespace {
+// head of the message from the owner's pair columns (dCols: Nd x 256, ld = Nd) and its two diagonal-block inverses
+__global__ void __launch_bounds__(256)
+dchol_pack_head_kernel(const double* __restrict__ cols, int64_t ld, int64_t row0, const double* __restrict__ invD, double* __restrict__ head)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    constexpr int DIAG = 2 * LB_TILE * 2 * LB_TILE;
+    if (idx < DIAG) {
+        const int r = idx & 255, c = idx >> 8;
+        head[idx] = cols[row0 + r + (int64_t)c * ld];
+    }
+    else if (idx < LB_DCHOL_HEAD)
+        head[idx] = invD[idx - DIAG];
+}
+// message -> this rank's factor storage: L[row0 + r, row0 + c] (r < 256: head; r >= 256: rows below), invD[kpair], invD[kpair + 1]
+__global__ void __launch_bounds__(256)
+dchol_unpack_kernel(const double* __restrict__ msg, int64_t ldp, double* __restrict__ L, int64_t ld, int64_t row0, double* __restrict__ invD_pair)
+{
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; // row inside the column block, 0 .. 256 + ldp
+    const int c = blockIdx.y;
+    constexpr int DIAG = 2 * LB_TILE * 2 * LB_TILE;
+    if (r < 2 * LB_TILE) L[row0 + r + (row0 + c) * ld] = msg[r + c * 2 * LB_TILE];
+    else if (r < 2 * LB_TILE + ldp) L[row0 + r + (row0 + c) * ld] = msg[LB_DCHOL_HEAD + (r - 2 * LB_TILE) + (int64_t)c * ldp];
+    if (blockIdx.x == 0) { // the two inverse blocks: 32768 doubles over 256 columns x 256 threads
+        const int idx = c * 256 + threadIdx.x;
+        if (idx < 2 * LB_TILE * LB_TILE) invD_pair[idx] = msg[DIAG + idx];
+    }
+}
+} // namespace
+
+// the owner of pair `kpair`: writes the head of the message (after lb_dchol_panel has factored the pair; same stream)
+int lb_dchol_pack_head(lb_gp* h, const double* dCols, int64_t Nd, int kpair, const double* dInvD, double* dMsg)
+{
+    if (!h || !dCols || !dInvD || !dMsg) return LB_ERR_ARG;
+    LB_DEVICE(h);
+    dchol_pack_head_kernel<<<(LB_DCHOL_HEAD + 255) / 256, 256, 0, h->stream>>>(dCols, Nd, (int64_t)kpair * LB_TILE, dInvD, dMsg);
+    h->launches++;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+// Target handle (data and kernel already set, lb_set_data + lb_set_kernel): private factor buffers, staged samples.  The padded
+// order of the handle must equal the distributed order Nd (N a multiple of 256, or 128 < N mod 256).
+int lb_dchol_adopt_begin(lb_gp* h, int64_t Nd)
+{
+    if (!h) return LB_ERR_ARG;
+    if (!h->kernel_set || h->N == 0 || h->Np == 0 || !h->dX) return LB_ERR_STATE;
+    if (h->Np != Nd) return LB_ERR_UNSUPPORTED;
+    LB_DEVICE(h);
+    int rc;
+    if ((rc = ensure_fit_buffers(h))) return rc;
+    if ((rc = lb_launch_scale_x(h))) return rc;
+    LB_CUDA(cudaMemsetAsync(h->dInfo, 0, 2 * sizeof(int), h->stream));
+    h->fitted = false; h->linv_valid = false; h->linv_levels = 0; h->kinv_valid = false; h->linv32_valid = false;
+    return LB_OK;
+}
+// one received (or own) panel message into the handle's L / invD, on `stream` (cudaStream_t as void*; NULL = the handle's)
+int lb_dchol_unpack(lb_gp* h, const double* dMsg, int64_t Nd, int kpair, void* stream)
+{
+    if (!h || !dMsg || !h->dL || !h->dInvD || h->Np != Nd) return LB_ERR_ARG;
+    LB_DEVICE(h);
+    const int64_t row0 = (int64_t)kpair * LB_TILE, ldp = Nd - row0 - 2 * LB_TILE;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    dim3 grid((unsigned)((2 * LB_TILE + ldp + 255) / 256), 2 * LB_TILE);
+    dchol_unpack_kernel<<<grid, 256, 0, st>>>(dMsg, ldp, h->dL, Nd, row0, h->dInvD + (int64_t)kpair * LB_TILE * LB_TILE);
+    h->launches++;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+// all panels are in: the handle is fitted (info = the distributed factorisation's), alpha is solved locally (gp.hpp:605-611)
+int lb_dchol_adopt_end(lb_gp* h, int info)
+{
+    if (!h) return LB_ERR_ARG;
+    LB_DEVICE(h);
+    if (info > 0) return info;
+    h->fitted = true; h->linv_valid = false; h->linv_levels = 0; h->kinv_valid = false; h->linv32_valid = false;
+    int rc = lb_launch_solve_alpha(h);
+    if (rc) return rc;
+    return check_info(h);
+}
+
 // per-kernel-class event timing for bench.py's roofline (not part of the reference-facing header)
 int lb_profile_enable(lb_gp* h, int on)
 {

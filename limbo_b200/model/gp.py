@@ -80,6 +80,7 @@ class GP:
     # ---- device plumbing ----
     def set_stream(self, stream_ptr: int | None) -> None:
         _lib.check(self._lib.lb_set_stream(self._h, C.c_void_p(stream_ptr or 0)), "lb_set_stream")
+        self._stream_ptr = stream_ptr or 0
 
     def launch_count(self) -> int:
         return int(self._lib.lb_launch_count(self._h))

@@ -53,3 +53,15 @@ def test_two_rank_sharded_argmax_matches_unsharded():
         pytest.skip("needs 2 GPUs")
     res = _torchrun(2, "tools/dist_argmax_check.py")
     assert res["n_gpus"] == 2 and res["ok"], res
+
+
+@pytest.mark.parametrize("n,kernel", [(2048, "SquaredExpARD"), (1280, "MaternFiveHalves")])
+def test_two_rank_distributed_fit_matches_lb_fit(n, kernel):
+    """limbo_b200/dist_fit.py: the factor computed by two ranks together and assembled on every rank is the one lb_fit
+    produces (bit-identical alpha, predictions, argmax; L compared element-wise for these sizes)."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    res = _torchrun(2, "tools/dist_fit_check.py", "--n", str(n), "--m", "3000", "--kernel", kernel, "--reps", "1")
+    assert res["n_gpus"] == 2 and res["supported"] and res["info"] == 0
+    assert res["bit_identical_on_every_rank"], res
+    assert res["loglik_rel_diff"] == 0.0, res
