@@ -38,9 +38,9 @@ __device__ __forceinline__ void tile_from_index(int t, int& bi, int& bj)
 
 // KID: kernel id (compile time, so only one functor is inlined); EDGE: the tile touches the diagonal or the identity
 // padding (noise / padding predicates); interior tiles (the vast majority) skip every per-element test.
-template <int KID, bool EDGE, bool DOT>
+template <int KID, bool EDGE>
 __device__ __forceinline__ void kbuild_tile(const double* __restrict__ Xs, double* __restrict__ K, int64_t N, int64_t Np,
-    const KernParams& kp, int bi, int bj, double (*sxi)[LB_TILE], double (*sxj)[LB_TILE], uint64_t* barp, double* snorm)
+    const KernParams& kp, int bi, int bj, double (*sxi)[LB_TILE], double (*sxj)[LB_TILE], uint64_t* barp)
 {
     uint64_t& bar = *barp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -81,40 +81,6 @@ __device__ __forceinline__ void kbuild_tile(const double* __restrict__ Xs, doubl
                 lb_mbar_wait(&bar, phase);
                 phase ^= 1;
             }
-            if (DOT) {
-                // isotropic kernels on unscaled inputs (|x|^2 = O(D)): z = |x_i|^2 + |x_j|^2 - 2 x_i . x_j, one FMA per dimension
-                // and pair instead of a subtraction and an FMA.  The Matern / Exp builds are bound by the fp64 pipe (~45
-                // instructions per element), not by HBM; the cancellation costs <= 4e-16 (|x_i|^2 + |x_j|^2) absolute on z.
-                if (h == 0) {
-                    __syncthreads();
-                    double nrm = 0.0;
-                    const double* row = (tid < LB_TILE) ? &sxi[0][tid] : &sxj[0][tid - LB_TILE];
-                    for (int d = 0; d < dc; ++d) nrm = fma(row[d * LB_TILE], row[d * LB_TILE], nrm);
-                    snorm[tid] = nrm;
-                    __syncthreads();
-                }
-                for (int d = 0; d < dc; ++d) {
-                    const double2 xi = *reinterpret_cast<const double2*>(&sxi[d][r0]);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const double2 xj = *reinterpret_cast<const double2*>(&sxj[d][h * 64 + c * 8 + 2 * lj]);
-                        z[c][0] = fma(xi.x, xj.x, z[c][0]);
-                        z[c][1] = fma(xi.y, xj.x, z[c][1]);
-                        z[c][2] = fma(xi.x, xj.y, z[c][2]);
-                        z[c][3] = fma(xi.y, xj.y, z[c][3]);
-                    }
-                }
-                const double ni0 = snorm[r0], ni1 = snorm[r0 + 1];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const double nj0 = snorm[LB_TILE + h * 64 + c * 8 + 2 * lj], nj1 = snorm[LB_TILE + h * 64 + c * 8 + 2 * lj + 1];
-                    z[c][0] = fmax(fma(-2.0, z[c][0], ni0 + nj0), 0.0);
-                    z[c][1] = fmax(fma(-2.0, z[c][1], ni1 + nj0), 0.0);
-                    z[c][2] = fmax(fma(-2.0, z[c][2], ni0 + nj1), 0.0);
-                    z[c][3] = fmax(fma(-2.0, z[c][3], ni1 + nj1), 0.0);
-                }
-            }
-            else
             for (int d = 0; d < dc; ++d) {
                 const double2 xi = *reinterpret_cast<const double2*>(&sxi[d][r0]);
 #pragma unroll
@@ -162,18 +128,11 @@ kbuild_kernel(const double* __restrict__ Xs, double* __restrict__ K, int64_t N, 
     __shared__ __align__(128) double sxi[DCH][LB_TILE];
     __shared__ __align__(128) double sxj[DCH][LB_TILE];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ double snorm[2 * LB_TILE];
     int bi, bj;
     tile_from_index(blockIdx.x, bi, bj);
     const bool edge = (bi == bj) || ((int64_t)(bi + 1) * LB_TILE > N);
-    // the dot-product form of the distances: isotropic kernels (inputs not scaled by 1 / ell), all dimensions in one staging pass
-    constexpr bool ISO = (KID != LB_K_SE_ARD);
-    if (ISO && kp.D <= DCH) {
-        if (edge) kbuild_tile<KID, true, ISO>(Xs, K, N, Np, kp, bi, bj, sxi, sxj, &bar, snorm);
-        else kbuild_tile<KID, false, ISO>(Xs, K, N, Np, kp, bi, bj, sxi, sxj, &bar, snorm);
-    }
-    else if (edge) kbuild_tile<KID, true, false>(Xs, K, N, Np, kp, bi, bj, sxi, sxj, &bar, snorm);
-    else kbuild_tile<KID, false, false>(Xs, K, N, Np, kp, bi, bj, sxi, sxj, &bar, snorm);
+    if (edge) kbuild_tile<KID, true>(Xs, K, N, Np, kp, bi, bj, sxi, sxj, &bar);
+    else kbuild_tile<KID, false>(Xs, K, N, Np, kp, bi, bj, sxi, sxj, &bar);
 }
 
 } // namespace

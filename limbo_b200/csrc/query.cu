@@ -734,10 +734,10 @@ constexpr int SB = 16;
 // Tbuf[i, ct] = V[s0 + i, ct] - L[s0 + i, 0:s0] V[0:s0, ct]       grid = nrows * (Mp / 128), row tile fastest
 __global__ void __launch_bounds__(C::THREADS, 1)
 panel_update_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ V, double* __restrict__ Tbuf, int64_t ldt, int s0,
-    int nrows)
+    int nrows, int ct0)
 {
     extern __shared__ __align__(16) double smem[];
-    const int i = blockIdx.x % nrows, ct = blockIdx.x / nrows;
+    const int i = blockIdx.x % nrows, ct = ct0 + blockIdx.x / nrows;
     const double* Vc = V + (int64_t)ct * LB_TILE * ld;
     lbg::Acc<C> acc;
     lbg::load_acc<C>(acc, Vc + (int64_t)(s0 + i) * LB_TILE, ld);
@@ -748,10 +748,10 @@ panel_update_kernel(const double* __restrict__ L, int64_t ld, const double* __re
 // V[s0 + i, ct] = sum_{k <= i} Linv[s0 + i, s0 + k] Tbuf[k, ct];  normpart[(s0 + i) * Mp + c] = sum over the tile's 128 rows of V^2
 __global__ void __launch_bounds__(C::THREADS, 1)
 panel_solve_kernel(const double* __restrict__ Linv, int64_t ld, const double* __restrict__ Tbuf, int64_t ldt, double* __restrict__ V, int s0,
-    int nrows, double* __restrict__ normpart, int64_t Mp)
+    int nrows, double* __restrict__ normpart, int64_t Mp, int ct0)
 {
     extern __shared__ __align__(16) double smem[];
-    const int i = nrows - 1 - (int)(blockIdx.x % nrows), ct = blockIdx.x / nrows; // longest K ranges first
+    const int i = nrows - 1 - (int)(blockIdx.x % nrows), ct = ct0 + blockIdx.x / nrows; // longest K ranges first
     lbg::Acc<C> acc;
     acc.zero();
     lbg::mainloop<C, false, true>(acc, Linv + (int64_t)(s0 + i) * LB_TILE + (int64_t)s0 * LB_TILE * ld, ld, Tbuf + (int64_t)ct * LB_TILE * ldt, ldt,
@@ -832,14 +832,32 @@ int lb_launch_query_panel(lb_gp* h, cudaStream_t st, int64_t M, const double* dQ
         mu_kernel<<<(unsigned)M, 256, 0, st>>>(dV, h->Np, h->dAlpha, h->P, dMu);
     }
     if (launches) *launches += 2;
-    const unsigned ctiles = (unsigned)(Mp / LB_TILE);
+    // The chain update_s -> solve_s -> update_s+1 -> ... only couples tiles of the SAME candidate column tile: the column tiles
+    // are split into two groups that walk the chain on two streams, so the tail of one group's launch (a launch is 8.5 waves of
+    // 148 CTAs at M = 10^4: ncu showed the tensor pipe 93 % busy while active but 80 % of the elapsed time) is filled by the
+    // other group's CTAs instead of idle SMs.
+    const int ctiles = (int)(Mp / LB_TILE);
+    cudaStream_t sts[2] = {st, (h->side && ctiles >= 2) ? h->side : st};
+    const int ngroups = (sts[1] != st) ? 2 : 1;
+    const int split = (ngroups == 2) ? (ctiles + 1) / 2 : ctiles;
     {
         LbProfScope ps(h, st, LB_PC_QSTEP);
+        if (ngroups == 2) {
+            LB_CUDA(cudaEventRecord(h->ev[0], st));
+            LB_CUDA(cudaStreamWaitEvent(sts[1], h->ev[0], 0));
+        }
         for (int s0 = 0; s0 < T; s0 += SB) {
             const int nrows = (T - s0 < SB) ? (T - s0) : SB;
-            panel_update_kernel<<<nrows * ctiles, C::THREADS, C::PIPE_BYTES, st>>>(h->dL, ld, dV, dT, ldt, s0, nrows);
-            panel_solve_kernel<<<nrows * ctiles, C::THREADS, C::PIPE_BYTES, st>>>(h->dLinv, ld, dT, ldt, dV, s0, nrows, dNorm, Mp);
-            if (launches) *launches += 2;
+            for (int g = 0; g < ngroups; ++g) {
+                const int c0 = g == 0 ? 0 : split, nc = g == 0 ? split : ctiles - split;
+                panel_update_kernel<<<nrows * nc, C::THREADS, C::PIPE_BYTES, sts[g]>>>(h->dL, ld, dV, dT, ldt, s0, nrows, c0);
+                panel_solve_kernel<<<nrows * nc, C::THREADS, C::PIPE_BYTES, sts[g]>>>(h->dLinv, ld, dT, ldt, dV, s0, nrows, dNorm, Mp, c0);
+                if (launches) *launches += 2;
+            }
+        }
+        if (ngroups == 2) {
+            LB_CUDA(cudaEventRecord(h->ev[1], sts[1]));
+            LB_CUDA(cudaStreamWaitEvent(st, h->ev[1], 0));
         }
     }
     {

@@ -44,7 +44,8 @@ class DistFit(DistCholesky):
         self.aux = torch.cuda.Stream(self.device)  # unpacking runs beside the trailing update
 
     def supported(self, gp) -> bool:
-        return int(self._lib.lb_nb_samples(gp._h)) == self.N and ((self.N + TILE - 1) // TILE * TILE) == self.Nd
+        """the handle's padded order (multiple of 128) must equal the distributed one (multiple of 256)"""
+        return gp.nb_samples() == self.N and max(TILE, (self.N + TILE - 1) // TILE * TILE) == self.Nd
 
     def set_kernel(self, kernel_fn) -> None:
         """new hyper-parameters for the column generator (the target handle gets them through gp._push_kernel())"""
