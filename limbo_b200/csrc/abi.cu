@@ -320,7 +320,7 @@ int lb_profile_enable(lb_gp* h, int on);
 
 // Streams and events of destroyed handles are kept for the next lb_create on the same device: a likelihood
 // evaluation clones and destroys one handle (kernel_lf_opt.hpp:79), and stream / event creation is not free either.
-struct Shell { cudaStream_t own = nullptr, side = nullptr; cudaEvent_t ev[6] = {}; };
+struct Shell { cudaStream_t own = nullptr, side = nullptr; cudaEvent_t ev[LB_NEV] = {}; };
 static std::mutex g_shell_mu;
 static std::vector<Shell> g_shells[64];
 
@@ -351,13 +351,13 @@ int lb_create(lb_gp** out, int device, int precision)
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if (cudaStreamCreateWithPriority(&sh.side, cudaStreamNonBlocking, hi) != cudaSuccess) sh.side = nullptr;
-        for (int i = 0; i < 6; ++i) cudaEventCreateWithFlags(&sh.ev[i], cudaEventDisableTiming);
+        for (int i = 0; i < LB_NEV; ++i) cudaEventCreateWithFlags(&sh.ev[i], cudaEventDisableTiming);
     }
     h->ex.own = sh.own;
     h->stream = sh.own;
     h->own_stream = true;
     h->side = sh.side;
-    for (int i = 0; i < 6; ++i) h->ev[i] = sh.ev[i];
+    for (int i = 0; i < LB_NEV; ++i) h->ev[i] = sh.ev[i];
     if (lb_dalloc(h, &h->dInfo, 4 * sizeof(int)) || lb_dalloc(h, &h->ex.dMisc, (LB_MAX_HPARAMS + 16) * sizeof(double))) {
         lb_destroy(h);
         return LB_ERR_ALLOC;
@@ -384,9 +384,10 @@ int lb_destroy(lb_gp* hh)
     lb_pool_free(h->dLambda);
     lb_pool_free(h->ex.dMisc);
     if (h->ex.hPoint) cudaFreeHost(h->ex.hPoint);
+    if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); h->aux = nullptr; }
     Shell sh;
     sh.own = h->ex.own; sh.side = h->side;
-    for (int i = 0; i < 6; ++i) sh.ev[i] = h->ev[i];
+    for (int i = 0; i < LB_NEV; ++i) sh.ev[i] = h->ev[i];
     bool kept = false;
     if (sh.own && h->device >= 0 && h->device < 64) {
         std::lock_guard<std::mutex> lk(g_shell_mu);
@@ -395,7 +396,7 @@ int lb_destroy(lb_gp* hh)
     if (!kept) {
         if (sh.own) cudaStreamDestroy(sh.own);
         if (sh.side) cudaStreamDestroy(sh.side);
-        for (int i = 0; i < 6; ++i) if (sh.ev[i]) cudaEventDestroy(sh.ev[i]);
+        for (int i = 0; i < LB_NEV; ++i) if (sh.ev[i]) cudaEventDestroy(sh.ev[i]);
     }
     delete h;
     return LB_OK;

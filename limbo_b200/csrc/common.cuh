@@ -18,6 +18,7 @@
 #include <cstdio>
 
 #define LB_TILE 128
+#define LB_NEV 8 // events per handle: fork / panel x2 / a-update x2 / join / second-group fork + join
 
 // ---- status codes (include/limbo_b200.h) ----------------------------------
 #define LB_OK 0
@@ -286,7 +287,8 @@ struct lb_gp {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t side = nullptr;   // high-priority stream for the look-ahead panel factorisation
-    cudaEvent_t ev[6] = {};        // fork / panel / a-update / join events
+    cudaStream_t aux = nullptr;    // normal-priority second stream (panel query: second column group), created on first use
+    cudaEvent_t ev[LB_NEV] = {};        // fork / panel / a-update / join events
 
     int64_t N = 0;   // live samples
     int64_t Np = 0;  // padded capacity (multiple of 128)

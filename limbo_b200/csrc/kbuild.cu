@@ -38,7 +38,10 @@ __device__ __forceinline__ void tile_from_index(int t, int& bi, int& bj)
 
 // KID: kernel id (compile time, so only one functor is inlined); EDGE: the tile touches the diagonal or the identity
 // padding (noise / padding predicates); interior tiles (the vast majority) skip every per-element test.
-template <int KID, bool EDGE>
+// NC: 8-column chunks per pass (8: two passes of 64 columns, 128 registers, two CTAs per SM; 4: four passes of 32 columns, fewer
+// live accumulators -> three CTAs per SM: the kernels whose per-element arithmetic is long (Matern, Exp: ~45 fp64 instructions)
+// are bound by latency / issue, not by HBM, and want the extra warps)
+template <int KID, bool EDGE, int NC>
 __device__ __forceinline__ void kbuild_tile(const double* __restrict__ Xs, double* __restrict__ K, int64_t N, int64_t Np,
     const KernParams& kp, int bi, int bj, double (*sxi)[LB_TILE], double (*sxj)[LB_TILE], uint64_t* barp)
 {
@@ -58,17 +61,18 @@ __device__ __forceinline__ void kbuild_tile(const double* __restrict__ Xs, doubl
     uint32_t phase = 0;
     const int npass = (D + DCH - 1) / DCH;
 
-    for (int h = 0; h < 2; ++h) { // two halves of 64 columns
-        double z[8][4];
+    constexpr int NH = 16 / NC, HW = 8 * NC; // passes over the 128 columns, columns per pass
+    for (int h = 0; h < NH; ++h) {
+        double z[NC][4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+        for (int c = 0; c < NC; ++c)
 #pragma unroll
             for (int e = 0; e < 4; ++e) z[c][e] = 0.0;
 
         for (int pass = 0; pass < npass; ++pass) {
             const int d0 = pass * DCH;
             const int dc = min(DCH, D - d0);
-            if (!(npass == 1 && h == 1)) { // single-pass inputs stay resident for the 2nd half
+            if (!(npass == 1 && h >= 1)) { // single-pass inputs stay resident for the later column passes
                 __syncthreads();           // previous readers done before TMA overwrites
                 if (tid == 0) {
                     lb_fence_proxy_async();
@@ -84,8 +88,8 @@ __device__ __forceinline__ void kbuild_tile(const double* __restrict__ Xs, doubl
             for (int d = 0; d < dc; ++d) {
                 const double2 xi = *reinterpret_cast<const double2*>(&sxi[d][r0]);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const double2 xj = *reinterpret_cast<const double2*>(&sxj[d][h * 64 + c * 8 + 2 * lj]);
+                for (int c = 0; c < NC; ++c) {
+                    const double2 xj = *reinterpret_cast<const double2*>(&sxj[d][h * HW + c * 8 + 2 * lj]);
                     double q;
                     q = xi.x - xj.x; z[c][0] = fma(q, q, z[c][0]);
                     q = xi.y - xj.x; z[c][1] = fma(q, q, z[c][1]);
@@ -97,8 +101,8 @@ __device__ __forceinline__ void kbuild_tile(const double* __restrict__ Xs, doubl
 
         const int64_t gi = i0 + r0; // global rows gi, gi+1
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int64_t gj = j0 + h * 64 + c * 8 + 2 * lj; // global cols gj, gj+1
+        for (int c = 0; c < NC; ++c) {
+            const int64_t gj = j0 + h * HW + c * 8 + 2 * lj; // global cols gj, gj+1
             double v[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -122,7 +126,7 @@ __device__ __forceinline__ void kbuild_tile(const double* __restrict__ Xs, doubl
 }
 
 template <int KID>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, (KID == LB_K_SE_ARD) ? 2 : 3)
 kbuild_kernel(const double* __restrict__ Xs, double* __restrict__ K, int64_t N, int64_t Np, KernParams kp)
 {
     __shared__ __align__(128) double sxi[DCH][LB_TILE];
@@ -131,8 +135,9 @@ kbuild_kernel(const double* __restrict__ Xs, double* __restrict__ K, int64_t N, 
     int bi, bj;
     tile_from_index(blockIdx.x, bi, bj);
     const bool edge = (bi == bj) || ((int64_t)(bi + 1) * LB_TILE > N);
-    if (edge) kbuild_tile<KID, true>(Xs, K, N, Np, kp, bi, bj, sxi, sxj, &bar);
-    else kbuild_tile<KID, false>(Xs, K, N, Np, kp, bi, bj, sxi, sxj, &bar);
+    constexpr int NC = (KID == LB_K_SE_ARD) ? 8 : 4;
+    if (edge) kbuild_tile<KID, true, NC>(Xs, K, N, Np, kp, bi, bj, sxi, sxj, &bar);
+    else kbuild_tile<KID, false, NC>(Xs, K, N, Np, kp, bi, bj, sxi, sxj, &bar);
 }
 
 } // namespace

@@ -9,6 +9,7 @@
 //                                           -> acq_kernel + argmax reduction
 #include "gemm.cuh"
 #include <cfloat>
+#include <cstdlib>
 
 namespace {
 
@@ -837,9 +838,30 @@ int lb_launch_query_panel(lb_gp* h, cudaStream_t st, int64_t M, const double* dQ
     // 148 CTAs at M = 10^4: ncu showed the tensor pipe 93 % busy while active but 80 % of the elapsed time) is filled by the
     // other group's CTAs instead of idle SMs.
     const int ctiles = (int)(Mp / LB_TILE);
-    cudaStream_t sts[2] = {st, (h->side && ctiles >= 2) ? h->side : st};
+    static int split_pct = -1, use_side = -1;
+    if (split_pct < 0) {
+        const char* e = getenv("LB_PANEL_SPLIT");   // percentage of the column tiles in the first group; 100 = one stream
+        split_pct = e ? atoi(e) : 70; // measured at N = 16384, M = 10^4: one stream 85.5 ms, 50 / 60 / 70 / 80 %: 81.3 / 80.6 / 80.5 / 80.4 ms
+        if (split_pct < 1 || split_pct > 100) split_pct = 100;
+        const char* e2 = getenv("LB_PANEL_SIDE");   // 1: second group on the high-priority side stream instead of a normal-priority one
+        use_side = (e2 && atoi(e2) != 0) ? 1 : 0;
+    }
+    cudaStream_t second = st;
+    if (split_pct < 100 && ctiles >= 4) {
+        if (use_side && h->side) second = h->side;
+        else {
+            if (!h->aux && cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess) h->aux = nullptr;
+            if (h->aux) second = h->aux;
+        }
+    }
+    cudaStream_t sts[2] = {st, second};
     const int ngroups = (sts[1] != st) ? 2 : 1;
-    const int split = (ngroups == 2) ? (ctiles + 1) / 2 : ctiles;
+    int split = ctiles;
+    if (ngroups == 2) {
+        split = (ctiles * split_pct + 50) / 100;
+        if (split < 1) split = 1;
+        if (split > ctiles - 1) split = ctiles - 1;
+    }
     {
         LbProfScope ps(h, st, LB_PC_QSTEP);
         if (ngroups == 2) {
