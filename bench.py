@@ -620,6 +620,7 @@ def run_ours(args) -> None:
         _lib.check(lib.lb_set_data_dev(h, n, d, 1, dX.data_ptr(), dY.data_ptr()), "set_data_dev")
         _lib.check(lib.lb_set_kernel(h, kid_dev, hp.ctypes.data, hp.size, NOISE), "set_kernel")
         if fitter is not None:
+            torch.cuda.synchronize(dev)  # so that the wall clock below times the fit alone (fit() returns synchronised anyway)
             t_f = time.perf_counter()
             fitter.fit(gp, push=False)  # distributed K -> L (assembled on every rank) -> alpha; returns synchronised
             fit_wall.append((time.perf_counter() - t_f) * 1e3)

@@ -61,7 +61,7 @@ def test_two_rank_distributed_fit_matches_lb_fit(n, kernel):
     produces (bit-identical alpha, predictions, argmax; L compared element-wise for these sizes)."""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
-    res = _torchrun(2, "tools/dist_fit_check.py", "--n", str(n), "--m", "3000", "--kernel", kernel, "--reps", "1")
+    res = _torchrun(2, "tools/dist_fit_check.py", "--size", str(n), "--cands", "3000", "--kernel", kernel, "--reps", "1")
     assert res["n_gpus"] == 2 and res["supported"] and res["info"] == 0
     assert res["bit_identical_on_every_rank"], res
     assert res["loglik_rel_diff"] == 0.0, res

@@ -4,7 +4,7 @@ per restart.  Alone: restarts run one after another on one GPU; under torchrun: 
 them over the ranks (restart r on rank r % G) and one all_gather picks the winner.  Every objective evaluation copies the GP
 (kernel_lf_opt.hpp:79) - lb_clone shares buffers copy-on-write and the pool serves the N x N buffers, so the run reports the
 cudaMalloc count inside the timed region.  Prints one JSON line (rank 0).
-usage: [torchrun --nproc-per-node G] python tools/config3_restarts.py [--n 16384] [--restarts 20] [--iterations 5]"""
+usage: [torchrun --nproc-per-node G] python tools/config3_restarts.py [--size 16384] [--restarts 20] [--iterations 5]"""
 import argparse
 import json
 import os
@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=16384)
+    ap.add_argument("--size", type=int, default=16384)
     ap.add_argument("--dim", type=int, default=6)
     ap.add_argument("--restarts", type=int, default=20)
     ap.add_argument("--iterations", type=int, default=5)
@@ -43,7 +43,7 @@ def main():
             repeats = a.restarts
             epsilon = 1e-2
     lib = _lib.load()
-    X = synth.points(1234, a.n, a.dim)
+    X = synth.points(1234, a.size, a.dim)
     y = synth.targets(X)
     evals = {"n": 0}
 
@@ -83,11 +83,11 @@ def main():
         wall_max = float(allv[:, 0].max())
         ev_total = int(allv[:, 1].sum())
         print(json.dumps({
-            "config": f"config 3: N={a.n}, D={a.dim}, SquaredExpARD fp64, KernelLFOpt, {a.restarts} restarts x {a.iterations} Rprop iterations, {world} GPU(s)",
+            "config": f"config 3: N={a.size}, D={a.dim}, SquaredExpARD fp64, KernelLFOpt, {a.restarts} restarts x {a.iterations} Rprop iterations, {world} GPU(s)",
             "n_gpus": world, "wall_s": wall_max, "objective_evaluations_total": ev_total, "evaluations_per_s": ev_total / wall_max,
             "evaluations_per_rank": allv[:, 1].astype(int).tolist(), "cuda_mallocs_in_timed_region_per_rank": allv[:, 2].astype(int).tolist(),
             "ms_per_evaluation_rank0": 1e3 * float(allv[0, 0]) / max(1.0, float(allv[0, 1])),
-            "flops_per_evaluation": float(a.n) ** 3, "tflops_per_gpu": float(allv[0, 1]) * float(a.n) ** 3 / float(allv[0, 0]) / 1e12,
+            "flops_per_evaluation": float(a.size) ** 3, "tflops_per_gpu": float(allv[0, 1]) * float(a.size) ** 3 / float(allv[0, 0]) / 1e12,
             "h_params": gp.kernel_function().h_params().tolist(), "log_lik": gp.get_log_lik(),
             "parallelism": ("restarts sharded over ranks (ShardedRepeater: restart r on rank r % G), one all_gather of (value, restart) + one broadcast of the winner"
                             if world > 1 else "restarts sequential on one GPU")}))

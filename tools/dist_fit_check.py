@@ -1,7 +1,7 @@
 """Distributed fit of one GP (limbo_b200/dist_fit.py) under torchrun: every rank must end with the factor lb_fit produces
 (bit-identical L, alpha, predictions), and the sharded acquisition on top of it must pick the unsharded argmax.  Also times the
 distributed fit against the replicated one.  Prints one JSON line (rank 0).
-usage: torchrun --nproc-per-node G tools/dist_fit_check.py [--n 16384] [--m 10000] [--kernel SquaredExpARD]"""
+usage: torchrun --nproc-per-node G tools/dist_fit_check.py [--size 16384] [--cands 10000] [--kernel SquaredExpARD]"""
 import argparse
 import json
 import os
@@ -16,8 +16,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=16384)
-    ap.add_argument("--m", type=int, default=10000)
+    ap.add_argument("--size", type=int, default=16384)
+    ap.add_argument("--cands", type=int, default=10000)
     ap.add_argument("--dim", type=int, default=6)
     ap.add_argument("--kernel", default="SquaredExpARD")
     ap.add_argument("--reps", type=int, default=3)
@@ -30,9 +30,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from limbo_b200 import acqui, dist_fit, kernel, mean, model, synth
     from limbo_b200 import dist as lbd
-    X = synth.points(1234, a.n, a.dim)
+    X = synth.points(1234, a.size, a.dim)
     y = synth.targets(X)
-    Xq = synth.points(1235, a.m, a.dim)
+    Xq = synth.points(1235, a.cands, a.dim)
     kcls = getattr(kernel, a.kernel)
     st = torch.cuda.Stream(dev)
     torch.cuda.set_stream(st)
@@ -40,7 +40,7 @@ def main():
     gp.set_stream(st.cuda_stream)
     gp.compute(X, y[:, None], compute_kernel=False)
     fitter = dist_fit.DistFit(gp, rank, world, dev)
-    res = {"n_gpus": world, "n": a.n, "m": a.m, "kernel": a.kernel, "supported": bool(fitter.supported(gp))}
+    res = {"n_gpus": world, "n": a.size, "m": a.cands, "kernel": a.kernel, "supported": bool(fitter.supported(gp))}
     info = fitter.fit(gp)  # warm-up (communicator, attributes, allocations)
     res["info"] = info
     ts = []
@@ -58,7 +58,7 @@ def main():
     res["dist_fit_ms"] = float(t.item())
     best, idx = lbd.sharded_acq_argmax(acqui.UCB(gp), Xq, rank, world, device=dev)
     mu_d, s2_d = gp.query_batch(Xq[:2000])
-    L_d, A_d = (gp.matrixL(), gp.alpha()) if a.n <= 8192 else (None, gp.alpha())
+    L_d, A_d = (gp.matrixL(), gp.alpha()) if a.size <= 8192 else (None, gp.alpha())
     # reference: the replicated single-GPU fit of the same model
     ref = model.GP(a.dim, 1, kernel=kcls, mean=mean.Data, device=lr)
     ref.set_stream(st.cuda_stream)
