@@ -389,7 +389,7 @@ def roofline_table(prof: dict, steps: int, t_ms: float, n: int, d: int, m_local:
             row["note"] = note
         rows.append(row)
 
-    qname = ("panel_update_kernel + panel_solve_kernel (V = L^-1 K* over 2048-row super-blocks, fp64 DMMA)" if m_local >= 4096
+    qname = ("panel_update_kernel + panel_solve_kernel (V = L^-1 K* over 2048-row super-blocks, fp64 DMMA)" if m_local >= 256
              else "query_slab_kernel (fused K* + blocked TRSM + mu / sigma^2, fp64 DMMA)")
     add("qstep", qname, "tensor", float(m_local) * n * n, 1e12, peak_t, peak_t_src,
         "M N^2 flops per batch (triangular solve, 2 flops per MAC on N^2 / 2); launches of one batch are averaged")
@@ -749,7 +749,7 @@ def run_ours(args) -> None:
         if table:
             top = dict(table[0])
             cls = top["class"]
-            kname = {"qstep": ("panel_update_kernel" if m_loc >= 4096 else "query_slab_kernel"), "syrk": "syrk_kernel", "kbuild": "kbuild_kernel"}.get(cls)
+            kname = {"qstep": ("panel_update_kernel" if m_loc >= 256 else "query_slab_kernel"), "syrk": "syrk_kernel", "kbuild": "kbuild_kernel"}.get(cls)
             tr, cap = ncu_traffic(kname) if kname else (None, None)
             top["traffic"] = tr
             top["traffic_capture"] = cap

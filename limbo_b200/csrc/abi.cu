@@ -759,14 +759,16 @@ int lb_append(lb_gp* h, const double* x, const double* Yall)
     return check_info(h);
 }
 
-// batches of at least this many candidates take the panel path (LB_QUERY_PANEL_MIN overrides; the slab kernel below it
-// keeps the one-point / small-batch latency)
+// Batches of at least this many candidates take the panel path (LB_QUERY_PANEL_MIN overrides).  The slab kernel keeps the
+// one-point / small-batch latency, but its time does not shrink with the batch: every CTA streams all of L through L2 whatever
+// its slab width (N = 16384: ~88 ms for ANY batch of <= 10^4 candidates; measured on 8 GPUs, 1250 candidates per rank), while
+// the panel path scales with the number of 128-candidate column tiles.
 static int64_t g_query_panel_min = -1;
 static int64_t query_panel_min()
 {
     if (g_query_panel_min < 0) {
         const char* e = getenv("LB_QUERY_PANEL_MIN");
-        int64_t v = e ? (int64_t)atoll(e) : 4096;
+        int64_t v = e ? (int64_t)atoll(e) : 256;
         g_query_panel_min = v < 1 ? 1 : v;
     }
     return g_query_panel_min;

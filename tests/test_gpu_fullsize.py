@@ -100,7 +100,7 @@ def test_config3_batched_equals_single_and_argmax(gp16k):
     mu, s2 = gp.query_batch(Xq)
     for i in (0, 1234, 2999):
         m1, s1 = gp.query(Xq[i])
-        assert m1[0] == mu[i, 0] and s1 == s2[i]
+        assert abs(m1[0] - mu[i, 0]) <= 1e-11 * max(1.0, abs(mu[i, 0])) and abs(s1 - s2[i]) <= 1e-12  # panel path (batch) vs slab kernel (one point)
     best, idx, vals = acqui.EI(gp).argmax_batch(Xq, return_values=True)
     assert idx == int(np.argmax(vals)) and best == vals[idx]
     assert np.all(vals >= 0.0)
