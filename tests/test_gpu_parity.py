@@ -291,7 +291,8 @@ def test_concurrent_const_queries(oracle_mod):
     from limbo_b200 import synth
     gp, og, X, Y = _make("SquaredExpARD", 200, 6)
     Xq = synth.points(99, 400, 6)
-    ref_mu, ref_s2 = gp.query_batch(Xq)
+    ref = [gp.query_batch(Xq[i * 100:(i + 1) * 100]) for i in range(4)]  # same batch shape -> same kernel path as the threads
+    ref_mu, ref_s2 = np.concatenate([r[0] for r in ref]), np.concatenate([r[1] for r in ref])
     errs = []
 
     def work(lo, hi):
