@@ -431,8 +431,21 @@ def run_config4(args, torch, dist, dev, rank, world, lib, precision: str = "tf32
     ap = np.array([0.0, 0.0])  # EI parameters: f_max (refreshed per fit), jitter 0
     out = {}
 
+    fitter = None
+    if world > 1 and not args.replicated_fit:  # the fp64 fit is the distributed one (dist_fit.py); inversion + cast stay per rank
+        from limbo_b200 import dist_fit
+        gp.compute(X, y[:, None], compute_kernel=False)
+        fitter = dist_fit.DistFit(gp, rank, world, dev)
+        if not fitter.supported(gp):
+            fitter.close()
+            fitter = None
+
     def step():
-        gp.compute(X, y[:, None])                          # fp64 fit through the public API (H2D inside)
+        if fitter is not None:
+            gp.compute(X, y[:, None], compute_kernel=False)
+            fitter.fit(gp)
+        else:
+            gp.compute(X, y[:, None])                      # fp64 fit through the public API (H2D inside)
         ei._nb_samples = -1
         ei._update_f_max(acqui.first_elem)                 # ei.hpp:100-108: f_max = max_i mu(x_i), one batched pass over the N samples
         ap[0] = ei._f_max
@@ -467,6 +480,8 @@ def run_config4(args, torch, dist, dev, rank, world, lib, precision: str = "tf32
     ms = float(t.item())
     stage = {k: v["ms_total"] / steps for k, v in prof.items()}
     fit_ms = sum(stage.get(k, 0.0) for k in ("kbuild", "syrk", "trsv")) + 0.0
+    if fitter is not None:
+        fitter.close()
     inv_ms = stage.get("trtri", 0.0) + stage.get("other", 0.0)
     score_ms = stage.get("kstar", 0.0) + stage.get("qstep", 0.0) + stage.get("qreduce", 0.0)
     mp = measured_peaks()
@@ -481,8 +496,11 @@ def run_config4(args, torch, dist, dev, rank, world, lib, precision: str = "tf32
         "ms_per_step": ms, "n_gpus": world, "steps": steps, "scaling": "strong", "precision": precision,
         "stage_ms_rank0": stage, "fit_ms_rank0": fit_ms, "invert_and_cast_ms_rank0": inv_ms, "score_ms_rank0": score_ms,
         "scoring_only_candidates_per_s": m_total / (score_ms * 1e-3) if score_ms > 0 else None,
-        "limiter": (f"fp64 fit ({fit_ms:.0f} ms) + inversion/cast ({inv_ms:.0f} ms) are replicated on every rank (Amdahl); only the "
-                    f"{score_ms:.0f} ms of scoring shard"),
+        "fit_scheme": "distributed (dist_fit.py)" if fitter is not None else ("replicated" if world > 1 else "single GPU"),
+        "limiter": ((f"inversion of the factor + cast ({inv_ms:.0f} ms) are replicated on every rank (every rank scores against all of L^-1); the "
+                     f"fp64 fit is distributed, the {score_ms:.0f} ms of scoring shard") if fitter is not None else
+                    (f"fp64 fit ({fit_ms:.0f} ms) + inversion/cast ({inv_ms:.0f} ms) are replicated on every rank (Amdahl); only the "
+                     f"{score_ms:.0f} ms of scoring shard")),
         "best": {"value": best[0], "index": best[1]},
         "roofline": {"kernel": ("pair_split_gemm_norm_kernel" if precision == "fp16x3" else "pair_gemm_norm_kernel") + " (tcgen05 cta_group::2, sigma^2 GEMM)", "bound": "tensor",
                      "achieved": flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None, "peak": tens_peak, "unit": "TFLOP/s",
