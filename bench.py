@@ -744,22 +744,6 @@ def run_ours(args) -> None:
     if fitter is not None:
         fitter.close()
 
-    # ---------------- sub-records: the multi-GPU splits BASELINE.json names ----------------
-    sub4 = sub4_f16 = sub4_x3 = sub5 = None
-    if not args.no_sub and args.workload == "n16384_se_ard":
-        try:
-            sub4 = run_config4(args, torch, dist, dev, rank, world, lib, "tf32")
-            sub4_f16 = run_config4(args, torch, dist, dev, rank, world, lib, "fp16")
-            sub4_x3 = run_config4(args, torch, dist, dev, rank, world, lib, "fp16x3", steps=1)
-        except Exception as e:  # a sub-record must never take the headline down
-            sub4 = {"error": repr(e)}
-        lib.lb_pool_trim()
-        torch.cuda.empty_cache()
-        try:
-            sub5 = run_config5(args, torch, dist, dev, rank, world)
-        except Exception as e:
-            sub5 = {"error": repr(e)}
-
     if rank == 0:
         stage = {k: v["ms_total"] / steps for k, v in prof.items()}
         table = roofline_table(prof, steps, t_ms, n, d, m_loc)
@@ -803,9 +787,46 @@ def run_ours(args) -> None:
                         else (f"strong scaling of one global job: the fit ({fit_ms:.1f} ms of main-stream kernels per step) is replicated on every "
                               f"rank and does not shrink with N; only the query ({q_ms:.1f} ms here for {m_loc} of {m} candidates) shards") if world > 1
                         else "single GPU: fp64 datapath (panel_update / panel_solve + syrk_kernel, all DMMA)"),
-            "config4": sub4, "config4_fp16": sub4_f16, "config4_fp16x3": sub4_x3, "config5": sub5,
         }
-        print(json.dumps(line))
+    else:
+        line = None
+
+    # ---------------- sub-records: the multi-GPU splits BASELINE.json names ----------------
+    # Safety net: the headline is measured; whatever happens in a sub-record (a collective that never returns cannot be caught
+    # as an exception) must not cost the line.  Every rank arms the same deadline; when it fires, rank 0 prints the line with
+    # the sub-records gathered so far and every rank leaves.
+    sub = {"config4": None, "config4_fp16": None, "config4_fp16x3": None, "config5": None}
+
+    def emit():
+        if rank == 0:
+            print(json.dumps({**line, **sub}))
+            sys.stdout.flush()
+
+    def watchdog():
+        for k, v in sub.items():
+            if v is None:
+                sub[k] = {"error": f"sub-record did not finish within {args.sub_timeout} s"}
+        emit()
+        os._exit(0)
+
+    if not args.no_sub and args.workload == "n16384_se_ard":
+        timer = threading.Timer(float(args.sub_timeout), watchdog)
+        timer.daemon = True
+        timer.start()
+        try:
+            sub["config4"] = run_config4(args, torch, dist, dev, rank, world, lib, "tf32")
+            sub["config4_fp16"] = run_config4(args, torch, dist, dev, rank, world, lib, "fp16")
+            sub["config4_fp16x3"] = run_config4(args, torch, dist, dev, rank, world, lib, "fp16x3", steps=1)
+        except Exception as e:  # a sub-record must never take the headline down
+            sub["config4"] = sub["config4"] or {"error": repr(e)}
+        try:
+            lib.lb_pool_trim()
+            torch.cuda.empty_cache()
+            sub["config5"] = run_config5(args, torch, dist, dev, rank, world)
+        except Exception as e:
+            sub["config5"] = {"error": repr(e)}
+        timer.cancel()
+    emit()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -853,6 +874,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
     ap.add_argument("--no-sub", action="store_true", help="skip the config4 / config5 sub-records")
+    ap.add_argument("--sub-timeout", type=int, default=240, help="seconds after which the line is printed without the unfinished sub-records")
     ap.add_argument("--replicated-fit", action="store_true", help="N > 1: every rank refits alone (round-1 scheme) instead of the distributed fit")
     ap.add_argument("--workload", default="n16384_se_ard", choices=sorted(WORKLOADS) + ["config4"])
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp16"], help="--workload config4 only")
