@@ -306,14 +306,16 @@ PC = ["kbuild", "potf2", "trsm_panel", "syrk", "syrk_col", "trsv", "kstar", "qst
 
 
 def syrk_flops_per_fit(n: int) -> float:
-    """Algorithmic flops of the K=256 trailing updates (profile class "syrk") of one factorisation:
-    panels are taken in pairs (k, k+1); the update of the matrix right of the pair has order
-    m = (T - k - 2) * 128 and costs m (m + 1) * 256 flops (lower triangle incl. diagonal, 2 flops per MAC)."""
+    """Algorithmic flops of the main-stream trailing updates (profile class "syrk") of one factorisation: panels are taken in
+    quads (k .. k+3); the update of the matrix right of the quad has order m = (T - k - 4) * 128 and costs m (m + 1) * 512 flops
+    (lower triangle incl. diagonal, 2 flops per MAC, K = 512).  (LB_POTRF_QUAD=0, the pair scheme of round 1: K = 256.)"""
     nb, tot = 128, 0.0
     t = (n + nb - 1) // nb
-    for k in range(0, t, 2):
-        m = max(0, (t - k - 2)) * nb
-        tot += float(m) * (m + 1) * (2 * nb)
+    quad = os.environ.get("LB_POTRF_QUAD", "1") != "0"
+    g = 4 if quad else 2
+    for k in range(0, t, g):
+        m = max(0, (t - k - g)) * nb
+        tot += float(m) * (m + 1) * (g * nb)
     return tot
 
 
@@ -394,7 +396,7 @@ def roofline_table(prof: dict, steps: int, t_ms: float, n: int, d: int, m_local:
     add("qstep", qname, "tensor", float(m_local) * n * n, 1e12, peak_t, peak_t_src,
         "M N^2 flops per batch (triangular solve, 2 flops per MAC on N^2 / 2); launches of one batch are averaged")
     add("kstar", "kstar_kernel (K* = k(X, Xq), N x M)", "hbm", 8.0 * n * m_local + 8.0 * (n + m_local) * d, 1e9, peak_h, peak_h_src)
-    add("syrk", "syrk_kernel K=256 (Cholesky trailing update, fp64 DMMA)", "tensor", syrk_flops_per_fit(n), 1e12, peak_t, peak_t_src)
+    add("syrk", "syrk_kernel K=512 (Cholesky trailing update in panel quads, fp64 DMMA)", "tensor", syrk_flops_per_fit(n), 1e12, peak_t, peak_t_src)
     add("kbuild", "kbuild_kernel (N x N kernel matrix)", "hbm", 8.0 * n * n + 8.0 * n * d, 1e9, peak_h, peak_h_src)
     add("trsv", "trsv_fwd/bwd_kernel (alpha = L^-T L^-1 obs_mean)", "hbm", 2 * 4.0 * n * n, 1e9, peak_h, peak_h_src,
         "4 N^2 bytes per direction (lower triangle of L read once)")

@@ -334,7 +334,106 @@ static inline int syrk_tiles(int T, int j0, int nc)
     return n;
 }
 
-// Right-looking factorisation in pairs of 128-column panels with look-ahead:
+// Right-looking factorisation with look-ahead, panels in QUADS of 128-column block columns (two pairs):
+//   side stream : pair(k)  = potf2(k) trsm(k) syrk[k -> col k+1] potf2(k+1) trsm(k+1)
+//                 a_in     = K=256 update of block columns k+2, k+3 with pair(k)            (inside the quad)
+//                 pair(k+2)
+//   main stream : a(q)     = K=512 update of the NEXT quad's four block columns with all four panels of this quad
+//                 b(q)     = K=512 update of everything right of them
+// quad(q+1) only needs a(q), so the latency-bound panel chain runs under b(q).  K=512 instead of the K=256 of round 1: every
+// trailing tile is loaded / stored half as often per flop (the C-tile prologue and store epilogue are what keeps a short-K GEMM
+// below the long-K kernels of this library: 0.76-0.84 against 0.90-0.92).  A tile's accumulator runs through the same sequence
+// of DMMAs as with two K=256 passes (the store / load in between does not round), so the factor is bit-identical to the
+// pair-wise distributed factorisation below (tests/test_gpu_dist_fit.py, tests/test_gpu_multirank.py).
+// LB_POTRF_QUAD=0 restores the pair scheme.
+static int launch_pair_panel(lb_gp* h, cudaStream_t side, int k, int T, int64_t ld)
+{
+    {
+        LbProfScope ps(h, side, LB_PC_POTF2);
+        potf2_inv_kernel<<<1, 256, POTF2_SMEM, side>>>(h->dL, ld, k, h->dInvD, h->dInfo, 1);
+    }
+    h->launches++;
+    if (k + 1 < T) {
+        {
+            LbProfScope ps(h, side, LB_PC_TRSM_PANEL);
+            trsm_panel_kernel<<<T - k - 1, lbg::CfgWide::THREADS, lbg::CfgWide::PIPE_BYTES, side>>>(h->dL, ld, k, h->dInvD);
+        }
+        {
+            LbProfScope ps(h, side, LB_PC_SYRK_COL);
+            LB_SYRK_LAUNCH((T - k - 1) * SYRK_SPLIT, side, h->dL, ld, k, 1, k + 1, 1, T);
+        }
+        {
+            LbProfScope ps(h, side, LB_PC_POTF2);
+            potf2_inv_kernel<<<1, 256, POTF2_SMEM, side>>>(h->dL, ld, k + 1, h->dInvD, h->dInfo, 1);
+        }
+        h->launches += 3;
+        if (k + 2 < T) {
+            LbProfScope ps(h, side, LB_PC_TRSM_PANEL);
+            trsm_panel_kernel<<<T - k - 2, lbg::CfgWide::THREADS, lbg::CfgWide::PIPE_BYTES, side>>>(h->dL, ld, k + 1, h->dInvD);
+            h->launches++;
+        }
+    }
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+static int launch_potrf_quads(lb_gp* h)
+{
+    const int T = (int)(h->Np / LB_TILE);
+    const int64_t ld = h->Np;
+    cudaStream_t main = h->stream, side = h->side ? h->side : h->stream;
+    LB_CUDA(cudaMemsetAsync(h->dInfo, 0, 2 * sizeof(int), main));
+    if (side != main) {
+        LB_CUDA(cudaEventRecord(h->ev[0], main)); // inputs (K) ready
+        LB_CUDA(cudaStreamWaitEvent(side, h->ev[0], 0));
+    }
+    int rc, q = 0;
+    for (int k = 0; k < T; k += 4, ++q) {
+        // ---- quad(q) on the side stream ----
+        if ((rc = launch_pair_panel(h, side, k, T, ld))) return rc;
+        if (k + 2 < T) {
+            const int nc2 = (T - (k + 2) < 2) ? (T - (k + 2)) : 2;
+            {
+                LbProfScope ps(h, side, LB_PC_SYRK_COL);
+                LB_SYRK_LAUNCH(syrk_tiles(T, k + 2, nc2) * SYRK_SPLIT, side, h->dL, ld, k, 2, k + 2, nc2, T);
+            }
+            h->launches++;
+            if ((rc = launch_pair_panel(h, side, k + 2, T, ld))) return rc;
+        }
+        if (k + 4 >= T) break;
+        if (side != main) {
+            LB_CUDA(cudaEventRecord(h->ev[1 + (q & 1)], side));
+            LB_CUDA(cudaStreamWaitEvent(main, h->ev[1 + (q & 1)], 0));
+        }
+        // ---- a(q): the next quad's block columns, K = 512 ----
+        const int j0 = k + 4;
+        const int nca = (T - j0 < 4) ? (T - j0) : 4;
+        {
+            LbProfScope ps(h, main, LB_PC_SYRK);
+            LB_SYRK_LAUNCH(syrk_tiles(T, j0, nca) * SYRK_SPLIT, main, h->dL, ld, k, 4, j0, nca, T);
+        }
+        h->launches++;
+        if (side != main) {
+            LB_CUDA(cudaEventRecord(h->ev[3 + (q & 1)], main));
+            LB_CUDA(cudaStreamWaitEvent(side, h->ev[3 + (q & 1)], 0));
+        }
+        // ---- b(q): the rest of the trailing matrix, K = 512 ----
+        const int ncb = T - j0 - nca;
+        if (ncb > 0) {
+            LbProfScope ps(h, main, LB_PC_SYRK);
+            LB_SYRK_LAUNCH(syrk_tiles(T, j0 + nca, ncb) * SYRK_SPLIT, main, h->dL, ld, k, 4, j0 + nca, ncb, T);
+            h->launches++;
+        }
+    }
+    if (side != main) { // join
+        LB_CUDA(cudaEventRecord(h->ev[5], side));
+        LB_CUDA(cudaStreamWaitEvent(main, h->ev[5], 0));
+    }
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+// Pair scheme of round 1 (K = 256 trailing updates), kept behind LB_POTRF_QUAD=0:
 //   side stream : panel(p)  = potf2(k) trsm(k) syrk[k -> col k+1] potf2(k+1) trsm(k+1)
 //   main stream : a(p)      = K=256 update of the next pair's two block columns (k+2, k+3)
 //                 b(p)      = K=256 update of everything right of them
@@ -343,6 +442,9 @@ int lb_launch_potrf(lb_gp* h)
 {
     int rc = set_attrs();
     if (rc) return rc;
+    static int quad = -1;
+    if (quad < 0) { const char* e = getenv("LB_POTRF_QUAD"); quad = (e && atoi(e) == 0) ? 0 : 1; }
+    if (quad) return launch_potrf_quads(h);
     const int T = (int)(h->Np / LB_TILE);
     const int64_t ld = h->Np;
     cudaStream_t main = h->stream, side = h->side ? h->side : h->stream;
