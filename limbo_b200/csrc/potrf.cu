@@ -296,6 +296,7 @@ int set_attrs()
     LB_CUDA(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::CfgWide::PIPE_BYTES));
     LB_CUDA(cudaFuncSetAttribute(syrk_kernel<SyrkCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg::PIPE_BYTES));
     LB_CUDA(cudaFuncSetAttribute(syrk_kernel<SyrkCfgDF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg::PIPE_BYTES));
+    LB_CUDA(cudaFuncSetAttribute(syrk_kernel<lbg::CfgWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lbg::CfgWide::PIPE_BYTES));
     return LB_OK;
 }
 
@@ -408,6 +409,8 @@ static int launch_potrf_quads(lb_gp* h)
         // ---- a(q): the next quad's block columns, K = 512 ----
         const int j0 = k + 4;
         const int nca = (T - j0 < 4) ? (T - j0) : 4;
+        static int wide = -1; // experiment: 128 x 128 tiles, 512 threads, one CTA per SM for the K = 512 main-stream updates
+        if (wide < 0) { const char* e = getenv("LB_SYRK_WIDE"); wide = (e && atoi(e) != 0) ? 1 : 0; }
         {
             LbProfScope ps(h, main, LB_PC_SYRK);
             LB_SYRK_LAUNCH(syrk_tiles(T, j0, nca) * SYRK_SPLIT, main, h->dL, ld, k, 4, j0, nca, T);
@@ -421,7 +424,11 @@ static int launch_potrf_quads(lb_gp* h)
         const int ncb = T - j0 - nca;
         if (ncb > 0) {
             LbProfScope ps(h, main, LB_PC_SYRK);
-            LB_SYRK_LAUNCH(syrk_tiles(T, j0 + nca, ncb) * SYRK_SPLIT, main, h->dL, ld, k, 4, j0 + nca, ncb, T);
+            if (wide)
+                syrk_kernel<lbg::CfgWide><<<syrk_tiles(T, j0 + nca, ncb), lbg::CfgWide::THREADS, lbg::CfgWide::PIPE_BYTES, main>>>(h->dL, ld, k, 4, j0 + nca,
+                    ncb, T);
+            else
+                LB_SYRK_LAUNCH(syrk_tiles(T, j0 + nca, ncb) * SYRK_SPLIT, main, h->dL, ld, k, 4, j0 + nca, ncb, T);
             h->launches++;
         }
     }

@@ -1,6 +1,7 @@
-"""Small end-to-end case for compute-sanitizer (memcheck / racecheck / synccheck): fit, append, query (fused and
-multi-launch), acquisition, log-lik, gradient, LOO value / gradient, K^-1 obs_mean, SE-ARD with Lambda columns, tf32 and fp16
-queries, and the multi-GPU Cholesky blocks at world = 1."""
+"""Small end-to-end case for compute-sanitizer (memcheck / racecheck / synccheck): fit (quad-panel Cholesky), append, query
+(panel path, fused slab kernel, multi-launch, one-point kernel), acquisition, log-lik, gradient, LOO value / gradient,
+K^-1 obs_mean, SE-ARD with Lambda columns, Matern K build / gradient, tf32 / fp16 / fp16x3 queries, copy-on-write clones, and
+the multi-GPU Cholesky blocks and the distributed fit at world = 1."""
 import ctypes as C
 import os
 import sys
@@ -14,7 +15,7 @@ N, D, M = 300, 6, 700
 X = synth.points(1, N + 2, D)
 y = synth.targets(X)
 Xq = synth.points(2, M, D)
-for prec in ("fp64", "tf32", "fp16"):
+for prec in ("fp64", "tf32", "fp16", "fp16x3"):
     gp = model.GP(D, 1, kernel=kernel.SquaredExpARD, mean=mean.Data, precision=prec)
     gp.compute(X[:N], y[:N, None])
     gp.add_sample(X[N], y[N:N + 1])
@@ -24,6 +25,16 @@ for prec in ("fp64", "tf32", "fp16"):
     print(acqui.EI(gp).argmax_batch(Xq))
     if prec == "fp64":
         lib = _lib.load()
+        m1, v1 = gp.query(Xq[0])  # one-point kernel
+        lib.lb_debug_set_query_panel_min(1 << 40)  # the same batch on the fused slab kernel
+        mu_s, s2_s = gp.query_batch(Xq)
+        lib.lb_debug_set_query_panel_min(0)
+        assert np.abs(mu - mu_s).max() < 1e-10 and np.abs(s2 - s2_s).max() < 1e-10 and abs(v1 - s2_s[0]) < 1e-12
+        c = gp.copy()  # copy-on-write clone: refit with other hyper-parameters, the source stays intact
+        c.kernel_function().set_h_params(c.kernel_function().h_params() - 0.2)
+        c.recompute(False)
+        assert np.array_equal(gp.query_batch(Xq[:100])[1], s2_s[:100])
+        del c
         lib.lb_debug_force_unfused_query.argtypes = [C.c_void_p, C.c_int]
         lib.lb_debug_force_unfused_query(gp._h, 1)
         mu2, s22 = gp.query_batch(Xq)
@@ -47,7 +58,16 @@ gl.kernel_function().set_h_params(hp)
 gl.compute(X[:N], y[:N, None])
 print("lambda", gl.compute_log_lik(), gl.compute_kernel_grad_log_lik()[:3], gl.query_batch(Xq[:50])[1].sum())
 
-from limbo_b200 import dist_chol  # noqa: E402
+gm = model.GP(D, 1, kernel=kernel.MaternFiveHalves, mean=mean.Data)
+gm.compute(X[:N], y[:N, None])
+print("matern", gm.compute_log_lik(), gm.compute_kernel_grad_log_lik(), gm.query_batch(Xq)[1].sum())
+
+from limbo_b200 import dist_chol, dist_fit  # noqa: E402
+gd = model.GP(D, 1, kernel=kernel.SquaredExpARD, mean=mean.Data)
+gd.compute(X[:256], y[:256, None], compute_kernel=False)
+fitter = dist_fit.DistFit(gd, 0, 1, "cuda:0")
+print("dist_fit", fitter.fit(gd), gd.compute_log_lik())
+fitter.close()
 dc = dist_chol.DistCholesky(X[:N], gp.kernel_function(), 0, 1, "cuda:0")
 dc.build()
 print("dchol", dc.factor())
