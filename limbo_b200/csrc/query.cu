@@ -729,25 +729,30 @@ LbOncePerDevice g_attr_once2;
 // ===========================================================================
 namespace panel {
 
-using C = lbg::CfgWide;
 constexpr int SB = 16;
+constexpr int LB_PANEL_DUAL_ROUNDS = 4; // fewer than this many full rounds of 128 x 128 tiles per launch: use 128 x 64 tiles
 
-// Tbuf[i, ct] = V[s0 + i, ct] - L[s0 + i, 0:s0] V[0:s0, ct]       grid = nrows * (Mp / 128), row tile fastest
-__global__ void __launch_bounds__(C::THREADS, 1)
+// Tile configuration: CfgWide (128 x 128, one CTA per SM) for large batches; CfgDual (128 x 64, two CTAs per SM) when a launch
+// has few tiles - a launch of 16 x ctiles Wide tiles on 148 SMs is ceil(tiles / 148) full rounds, while with two co-resident
+// half-width CTAs the last, partly filled round costs half as much (M = 1250 per GPU on 8 GPUs: 160 Wide tiles = 2 rounds).
+// Tbuf[i, ct] = V[s0 + i, ct] - L[s0 + i, 0:s0] V[0:s0, ct]       grid = nrows * (Mp / BN), row tile fastest
+template <typename C>
+__global__ void __launch_bounds__(C::THREADS, (C::THREADS == 256) ? 2 : 1)
 panel_update_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ V, double* __restrict__ Tbuf, int64_t ldt, int s0,
     int nrows, int ct0)
 {
     extern __shared__ __align__(16) double smem[];
     const int i = blockIdx.x % nrows, ct = ct0 + blockIdx.x / nrows;
-    const double* Vc = V + (int64_t)ct * LB_TILE * ld;
+    const double* Vc = V + (int64_t)ct * C::BN * ld;
     lbg::Acc<C> acc;
     lbg::load_acc<C>(acc, Vc + (int64_t)(s0 + i) * LB_TILE, ld);
     if (s0 > 0) lbg::mainloop<C, false, true, true>(acc, L + (int64_t)(s0 + i) * LB_TILE, ld, Vc, ld, s0 * LB_TILE, smem);
-    lbg::store_acc<C>(acc, Tbuf + (int64_t)i * LB_TILE + (int64_t)ct * LB_TILE * ldt, ldt);
+    lbg::store_acc<C>(acc, Tbuf + (int64_t)i * LB_TILE + (int64_t)ct * C::BN * ldt, ldt);
 }
 
 // V[s0 + i, ct] = sum_{k <= i} Linv[s0 + i, s0 + k] Tbuf[k, ct];  normpart[(s0 + i) * Mp + c] = sum over the tile's 128 rows of V^2
-__global__ void __launch_bounds__(C::THREADS, 1)
+template <typename C>
+__global__ void __launch_bounds__(C::THREADS, (C::THREADS == 256) ? 2 : 1)
 panel_solve_kernel(const double* __restrict__ Linv, int64_t ld, const double* __restrict__ Tbuf, int64_t ldt, double* __restrict__ V, int s0,
     int nrows, double* __restrict__ normpart, int64_t Mp, int ct0)
 {
@@ -755,14 +760,14 @@ panel_solve_kernel(const double* __restrict__ Linv, int64_t ld, const double* __
     const int i = nrows - 1 - (int)(blockIdx.x % nrows), ct = ct0 + blockIdx.x / nrows; // longest K ranges first
     lbg::Acc<C> acc;
     acc.zero();
-    lbg::mainloop<C, false, true>(acc, Linv + (int64_t)(s0 + i) * LB_TILE + (int64_t)s0 * LB_TILE * ld, ld, Tbuf + (int64_t)ct * LB_TILE * ldt, ldt,
+    lbg::mainloop<C, false, true>(acc, Linv + (int64_t)(s0 + i) * LB_TILE + (int64_t)s0 * LB_TILE * ld, ld, Tbuf + (int64_t)ct * C::BN * ldt, ldt,
         (i + 1) * LB_TILE, smem);
-    lbg::store_acc<C>(acc, V + (int64_t)(s0 + i) * LB_TILE + (int64_t)ct * LB_TILE * ld, ld);
+    lbg::store_acc<C>(acc, V + (int64_t)(s0 + i) * LB_TILE + (int64_t)ct * C::BN * ld, ld);
     // column norms of the tile: per thread (2 m16 tiles x 2 row halves), then the 8 row lanes, then the 4 row warps
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;
-    double* sRed = smem; // [4][128]
+    double* sRed = smem; // [4][BN]
 #pragma unroll
     for (int nt = 0; nt < C::NT; ++nt)
 #pragma unroll
@@ -775,12 +780,12 @@ panel_solve_kernel(const double* __restrict__ Linv, int64_t ld, const double* __
             }
 #pragma unroll
             for (int o = 4; o < 32; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-            if (g == 0) sRed[wm * LB_TILE + wn * (C::BN / C::WN) + nt * 8 + 2 * t + e] = sq;
+            if (g == 0) sRed[wm * C::BN + wn * (C::BN / C::WN) + nt * 8 + 2 * t + e] = sq;
         }
     __syncthreads();
-    if (threadIdx.x < LB_TILE) {
-        const double sum = ((sRed[threadIdx.x] + sRed[LB_TILE + threadIdx.x]) + sRed[2 * LB_TILE + threadIdx.x]) + sRed[3 * LB_TILE + threadIdx.x];
-        normpart[(int64_t)(s0 + i) * Mp + (int64_t)ct * LB_TILE + threadIdx.x] = sum;
+    if ((int)threadIdx.x < C::BN) {
+        const double sum = ((sRed[threadIdx.x] + sRed[C::BN + threadIdx.x]) + sRed[2 * C::BN + threadIdx.x]) + sRed[3 * C::BN + threadIdx.x];
+        normpart[(int64_t)(s0 + i) * Mp + (int64_t)ct * C::BN + threadIdx.x] = sum;
     }
 }
 
@@ -812,9 +817,13 @@ int lb_launch_query_panel(lb_gp* h, cudaStream_t st, int64_t M, const double* dQ
     long long* launches)
 {
     using namespace panel;
+    using CW = lbg::CfgWide;
+    using CD = lbg::CfgDual;
     if (g_once.need()) {
-        LB_CUDA(cudaFuncSetAttribute(panel_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::PIPE_BYTES));
-        LB_CUDA(cudaFuncSetAttribute(panel_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::PIPE_BYTES));
+        LB_CUDA(cudaFuncSetAttribute(panel_update_kernel<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW::PIPE_BYTES));
+        LB_CUDA(cudaFuncSetAttribute(panel_solve_kernel<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW::PIPE_BYTES));
+        LB_CUDA(cudaFuncSetAttribute(panel_update_kernel<CD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CD::PIPE_BYTES));
+        LB_CUDA(cudaFuncSetAttribute(panel_solve_kernel<CD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CD::PIPE_BYTES));
     }
     const int T = (int)(h->Np / LB_TILE);
     const int64_t ld = h->Np, ldt = (int64_t)SB * LB_TILE;
@@ -862,6 +871,12 @@ int lb_launch_query_panel(lb_gp* h, cudaStream_t st, int64_t M, const double* dQ
         if (split < 1) split = 1;
         if (split > ctiles - 1) split = ctiles - 1;
     }
+    static int cfg_mode = -1; // LB_PANEL_CFG: 0 = auto (default), 1 = always 128 x 128 tiles, 2 = always 128 x 64 tiles
+    if (cfg_mode < 0) { const char* e = getenv("LB_PANEL_CFG"); cfg_mode = e ? atoi(e) : 0; }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const bool dual = cfg_mode == 2 || (cfg_mode == 0 && (int64_t)SB * ctiles < LB_PANEL_DUAL_ROUNDS * sms);
+    const int wmul = dual ? 2 : 1; // 64-wide column tiles per 128 candidates
     {
         LbProfScope ps(h, st, LB_PC_QSTEP);
         if (ngroups == 2) {
@@ -871,9 +886,15 @@ int lb_launch_query_panel(lb_gp* h, cudaStream_t st, int64_t M, const double* dQ
         for (int s0 = 0; s0 < T; s0 += SB) {
             const int nrows = (T - s0 < SB) ? (T - s0) : SB;
             for (int g = 0; g < ngroups; ++g) {
-                const int c0 = g == 0 ? 0 : split, nc = g == 0 ? split : ctiles - split;
-                panel_update_kernel<<<nrows * nc, C::THREADS, C::PIPE_BYTES, sts[g]>>>(h->dL, ld, dV, dT, ldt, s0, nrows, c0);
-                panel_solve_kernel<<<nrows * nc, C::THREADS, C::PIPE_BYTES, sts[g]>>>(h->dLinv, ld, dT, ldt, dV, s0, nrows, dNorm, Mp, c0);
+                const int c0 = (g == 0 ? 0 : split) * wmul, nc = (g == 0 ? split : ctiles - split) * wmul;
+                if (dual) {
+                    panel_update_kernel<CD><<<nrows * nc, CD::THREADS, CD::PIPE_BYTES, sts[g]>>>(h->dL, ld, dV, dT, ldt, s0, nrows, c0);
+                    panel_solve_kernel<CD><<<nrows * nc, CD::THREADS, CD::PIPE_BYTES, sts[g]>>>(h->dLinv, ld, dT, ldt, dV, s0, nrows, dNorm, Mp, c0);
+                }
+                else {
+                    panel_update_kernel<CW><<<nrows * nc, CW::THREADS, CW::PIPE_BYTES, sts[g]>>>(h->dL, ld, dV, dT, ldt, s0, nrows, c0);
+                    panel_solve_kernel<CW><<<nrows * nc, CW::THREADS, CW::PIPE_BYTES, sts[g]>>>(h->dLinv, ld, dT, ldt, dV, s0, nrows, dNorm, Mp, c0);
+                }
                 if (launches) *launches += 2;
             }
         }

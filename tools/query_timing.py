@@ -1,7 +1,10 @@
+"""Times lb_acq_argmax_dev (UCB) for M candidates at N=16384 (panel / slab path as the library chooses).
+usage: python tools/query_timing.py [M]"""
 import ctypes as C, os, sys, numpy as np, torch
 sys.path.insert(0, os.getcwd())
 from limbo_b200 import _lib, kernel, mean, model, synth
-N, D, M = 16384, 6, 10000
+N, D = 16384, 6
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 X = synth.points(1234, N, D); y = synth.targets(X); Xq = synth.points(1235, M, D)
 st = torch.cuda.Stream(); torch.cuda.set_stream(st)
 gp = model.GP(D, 1, kernel=kernel.SquaredExpARD, mean=mean.Data); gp.set_stream(st.cuda_stream)
@@ -16,4 +19,4 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(st)
 for _ in range(5): q()
 e1.record(st); torch.cuda.synchronize()
-print(os.environ.get("LB_PANEL_SPLIT"), os.environ.get("LB_PANEL_SIDE"), "query ms", e0.elapsed_time(e1) / 5, "best", dB.item(), dI.item())
+print("M", M, "cfg", os.environ.get("LB_PANEL_CFG"), "split", os.environ.get("LB_PANEL_SPLIT"), "query ms", e0.elapsed_time(e1) / 5, "best", dB.item(), dI.item())
