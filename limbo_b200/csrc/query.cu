@@ -730,11 +730,10 @@ LbOncePerDevice g_attr_once2;
 namespace panel {
 
 constexpr int SB = 16;
-constexpr int LB_PANEL_DUAL_ROUNDS = 4; // fewer than this many full rounds of 128 x 128 tiles per launch: use 128 x 64 tiles
 
-// Tile configuration: CfgWide (128 x 128, one CTA per SM) for large batches; CfgDual (128 x 64, two CTAs per SM) when a launch
-// has few tiles - a launch of 16 x ctiles Wide tiles on 148 SMs is ceil(tiles / 148) full rounds, while with two co-resident
-// half-width CTAs the last, partly filled round costs half as much (M = 1250 per GPU on 8 GPUs: 160 Wide tiles = 2 rounds).
+// Tile configuration: CfgDual (128 x 64, two CTAs per SM) by default - a launch of 16 x ctiles tiles is a few rounds of the
+// machine, and with two co-resident half-width CTAs the last, partly filled round costs half as much as with CfgWide
+// (128 x 128, one CTA per SM); one CTA's C-tile prologue / epilogue also hides under the other's DMMA stream.
 // Tbuf[i, ct] = V[s0 + i, ct] - L[s0 + i, 0:s0] V[0:s0, ct]       grid = nrows * (Mp / BN), row tile fastest
 template <typename C>
 __global__ void __launch_bounds__(C::THREADS, (C::THREADS == 256) ? 2 : 1)
@@ -871,11 +870,12 @@ int lb_launch_query_panel(lb_gp* h, cudaStream_t st, int64_t M, const double* dQ
         if (split < 1) split = 1;
         if (split > ctiles - 1) split = ctiles - 1;
     }
-    static int cfg_mode = -1; // LB_PANEL_CFG: 0 = auto (default), 1 = always 128 x 128 tiles, 2 = always 128 x 64 tiles
+    // LB_PANEL_CFG=1: 128 x 128 tiles (CfgWide); default 128 x 64 tiles, two CTAs per SM.  Measured at N = 16384 (ms per batch,
+    // Wide / Dual): M = 1250: 13.6 / 13.1, 2500: 23.1 / 21.9, 5000: 42.6 / 39.8, 10^4: 80.4 / 78.3 (same bits: the tile shape does not
+    // change any element's accumulation order).
+    static int cfg_mode = -1;
     if (cfg_mode < 0) { const char* e = getenv("LB_PANEL_CFG"); cfg_mode = e ? atoi(e) : 0; }
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    const bool dual = cfg_mode == 2 || (cfg_mode == 0 && (int64_t)SB * ctiles < LB_PANEL_DUAL_ROUNDS * sms);
+    const bool dual = cfg_mode != 1;
     const int wmul = dual ? 2 : 1; // 64-wide column tiles per 128 candidates
     {
         LbProfScope ps(h, st, LB_PC_QSTEP);
