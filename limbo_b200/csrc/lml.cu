@@ -160,6 +160,10 @@ __device__ __forceinline__ void tile_from_index(int t, int& bi, int& bj)
 // exponentials use the branch-free lb_exp_nonpos (<= 3e-16 relative, inside the 1e-9 bar of the gradient).
 constexpr int GRAD_PMAX = 4; // outputs staged in shared memory (more: global loads)
 
+// columns per pass: 4 chunks of 8 (four passes over the 128 columns of a tile) keep the live accumulators small enough for three
+// CTAs per SM (the kernel is bound by latency / instruction issue, not by the fp64 pipe: 36 % active at two CTAs per SM)
+constexpr int GNC = 2, GNH = 16 / GNC, GHW = 8 * GNC;
+
 template <int KID, bool EDGE>
 __device__ __forceinline__ void grad_tile(const double* __restrict__ Xs, const double* __restrict__ Kinv, const double* __restrict__ alpha, int P,
     int64_t N, int64_t Np, const KernParams& kp, int optimize_noise, int nh, double* __restrict__ part, int bi, int bj,
@@ -206,30 +210,30 @@ __device__ __forceinline__ void grad_tile(const double* __restrict__ Xs, const d
     };
 
     double g_sf = 0.0, g_l = 0.0, g_noise = 0.0;
-    for (int h = 0; h < 2; ++h) {
-        double z[8][4];
+    for (int h = 0; h < GNH; ++h) { // GNH passes of GHW columns
+        double z[GNC][4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+        for (int c = 0; c < GNC; ++c)
 #pragma unroll
             for (int e = 0; e < 4; ++e) z[c][e] = 0.0;
         // the K^-1 values of this half: issued before the distance sweep so that their latency hides under it
         const int64_t gi = i0 + r0;
-        double2 kv[8][2];
+        double2 kv[GNC][2];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int64_t gj = j0 + h * 64 + c * 8 + 2 * lj;
+        for (int c = 0; c < GNC; ++c) {
+            const int64_t gj = j0 + h * GHW + c * 8 + 2 * lj;
             kv[c][0] = __ldcs(reinterpret_cast<const double2*>(&Kinv[gi + gj * Np]));
             kv[c][1] = __ldcs(reinterpret_cast<const double2*>(&Kinv[gi + (gj + 1) * Np]));
         }
         for (int pass = 0; pass < npass; ++pass) {
             int dc = D;
-            if (!(npass == 1 && h == 1)) dc = stage(pass);
+            if (!(npass == 1 && h >= 1)) dc = stage(pass);
             else dc = min(DCH, D);
             for (int d = 0; d < dc; ++d) {
                 const double2 xi = *reinterpret_cast<const double2*>(&sxi[d][r0]);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const double2 xj = *reinterpret_cast<const double2*>(&sxj[d][h * 64 + c * 8 + 2 * lj]);
+                for (int c = 0; c < GNC; ++c) {
+                    const double2 xj = *reinterpret_cast<const double2*>(&sxj[d][h * GHW + c * 8 + 2 * lj]);
                     double q;
                     q = xi.x - xj.x; z[c][0] = fma(q, q, z[c][0]);
                     q = xi.y - xj.x; z[c][1] = fma(q, q, z[c][1]);
@@ -239,10 +243,10 @@ __device__ __forceinline__ void grad_tile(const double* __restrict__ Xs, const d
             }
         }
         // weights w_ij * f_ij and the parameter-independent factors
-        double wk[8][4]; // SE-ARD: w * f * k
+        double wk[GNC][4]; // SE-ARD: w * f * k
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int cl = h * 64 + c * 8 + 2 * lj; // local column
+        for (int c = 0; c < GNC; ++c) {
+            const int cl = h * GHW + c * 8 + 2 * lj; // local column
             const int64_t gj = j0 + cl;
             const double kin[4] = {kv[c][0].x, kv[c][0].y, kv[c][1].x, kv[c][1].y};
 #pragma unroll
@@ -309,8 +313,8 @@ __device__ __forceinline__ void grad_tile(const double* __restrict__ Xs, const d
                         const double2 xi = *reinterpret_cast<const double2*>(&sxi[d][r0]);
                         double s = 0.0;
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const double2 xj = *reinterpret_cast<const double2*>(&sxj[d][h * 64 + c * 8 + 2 * lj]);
+                        for (int c = 0; c < GNC; ++c) {
+                            const double2 xj = *reinterpret_cast<const double2*>(&sxj[d][h * GHW + c * 8 + 2 * lj]);
                             double q;
                             q = xi.x - xj.x; s = fma(wk[c][0], q * q, s);
                             q = xi.y - xj.x; s = fma(wk[c][1], q * q, s);
@@ -364,7 +368,7 @@ __device__ __forceinline__ void grad_tile(const double* __restrict__ Xs, const d
 }
 
 template <int KID>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 grad_kernel(const double* __restrict__ Xs, const double* __restrict__ Kinv, const double* __restrict__ alpha, int P,
     int64_t N, int64_t Np, KernParams kp, int optimize_noise, int nh, double* __restrict__ part)
 {
