@@ -404,7 +404,15 @@ def roofline_table(prof: dict, steps: int, t_ms: float, n: int, d: int, m_local:
         peak_t_src, "latency bound (128-pivot chain), side stream, hidden by look-ahead")
     add("trsm_panel", "trsm_panel_kernel (panel solve)", "tensor", sum(2.0 * 128 ** 3 * (n // 128 - k - 1) for k in range(n // 128)), 1e12, peak_t,
         peak_t_src, "side stream, runs under the trailing update")
-    add("syrk_col", "syrk_kernel K=128 (look-ahead column update)", "tensor", sum(2.0 * 128 ** 3 * (n // 128 - k - 1) for k in range(0, n // 128, 2)), 1e12,
+    tt = n // 128
+    quad = os.environ.get("LB_POTRF_QUAD", "1") != "0"
+    col_flops = sum(2.0 * 128 ** 3 * (tt - k - 1) for k in range(0, tt, 2))  # block column k+1 updated with panel k (K = 128)
+    if quad:  # inside a quad: block columns k+2, k+3 updated with the pair (k, k+1), K = 256
+        for k in range(0, tt, 4):
+            for j in (k + 2, k + 3):
+                if j < tt:
+                    col_flops += 2.0 * 128 * 128 * 256 * (tt - j)
+    add("syrk_col", "syrk_kernel K=128 / K=256 (look-ahead column updates inside a panel quad)", "tensor", col_flops, 1e12,
         peak_t, peak_t_src, "side stream")
     rows.sort(key=lambda r: -r["share_of_step"])
     return rows

@@ -23,7 +23,8 @@ def test_library_exports_every_declared_symbol(lib):
     # the multi-GPU building blocks (include/limbo_b200_dist.h)
     hdr2 = open(os.path.join(ROOT, "include", "limbo_b200_dist.h")).read()
     declared2 = sorted(set(re.findall(r"\b(lb_dchol_[a-z_0-9]+)\s*\(", hdr2)))
-    assert declared2 == ["lb_dchol_build", "lb_dchol_finish", "lb_dchol_panel", "lb_dchol_set_points", "lb_dchol_update"]
+    assert declared2 == ["lb_dchol_adopt_begin", "lb_dchol_adopt_end", "lb_dchol_build", "lb_dchol_finish", "lb_dchol_pack_head", "lb_dchol_panel",
+                         "lb_dchol_set_points", "lb_dchol_unpack", "lb_dchol_update"]
     for name in declared2:
         assert hasattr(lib, name), name
 
