@@ -1262,6 +1262,66 @@ int lb_dchol_adopt_end(lb_gp* h, int info)
     return check_info(h);
 }
 
+// ---- inversion of the factor spread over G GPUs, for the reduced-precision candidate path (limbo_b200_dist.h) --------------------
+size_t lb_linv_columns_scratch_doubles(const lb_gp* h, int G);
+int lb_launch_linv_columns(lb_gp* h, cudaStream_t st, int rank, int G, double* dWork, long long* launches);
+size_t lb_dinv_chunk_bytes_impl(const lb_gp* h, int G);
+int lb_dinv_absmax(lb_gp* h, const double* dV, int G, double* out);
+int lb_dinv_pack_impl(lb_gp* h, const double* dV, int rank, int G, double absmax_all, void* dChunk);
+int lb_dinv_adopt_impl(lb_gp* h, int G, const void* dAll, double absmax_all);
+
+static int dinv_check(const lb_gp* h, int rank, int G)
+{
+    if (!h || G < 1 || rank < 0 || rank >= G) return LB_ERR_ARG;
+    if (!h->fitted || h->N == 0) return LB_ERR_STATE;
+    if (h->precision != LB_PREC_TF32 && h->precision != LB_PREC_FP16 && h->precision != LB_PREC_FP16X3) return LB_ERR_UNSUPPORTED;
+    return LB_OK;
+}
+
+long long lb_dinv_chunk_bytes(const lb_gp* h, int G)
+{
+    int rc = dinv_check(h, 0, G);
+    return rc ? (long long)rc : (long long)lb_dinv_chunk_bytes_impl(h, G);
+}
+
+int lb_dinv_columns(lb_gp* hc, int rank, int G, double* absmax_host)
+{
+    int rc = dinv_check(hc, rank, G);
+    if (rc) return rc;
+    if (!absmax_host) return LB_ERR_ARG;
+    lb_gp_full* h = full(hc);
+    LB_DEVICE(h);
+    std::lock_guard<std::mutex> lock(h->ex.qmutex);
+    QueryWs& w = h->ex.ws;
+    if ((rc = ensure(h, &w.dV, &w.v_bytes, sizeof(double) * lb_linv_columns_scratch_doubles(h, G)))) return rc;
+    if ((rc = lb_launch_linv_columns(h, h->stream, rank, G, w.dV, &h->launches))) return rc;
+    return lb_dinv_absmax(h, w.dV, G, absmax_host);
+}
+
+int lb_dinv_pack(lb_gp* hc, int rank, int G, double absmax_all, void* dChunk)
+{
+    int rc = dinv_check(hc, rank, G);
+    if (rc) return rc;
+    if (!dChunk) return LB_ERR_ARG;
+    lb_gp_full* h = full(hc);
+    LB_DEVICE(h);
+    std::lock_guard<std::mutex> lock(h->ex.qmutex);
+    QueryWs& w = h->ex.ws;
+    if (!w.dV || w.v_bytes < sizeof(double) * lb_linv_columns_scratch_doubles(h, G)) return LB_ERR_STATE; // lb_dinv_columns first
+    return lb_dinv_pack_impl(h, w.dV, rank, G, absmax_all, dChunk);
+}
+
+int lb_dinv_adopt(lb_gp* hc, int G, const void* dAll, double absmax_all)
+{
+    int rc = dinv_check(hc, 0, G);
+    if (rc) return rc;
+    if (!dAll) return LB_ERR_ARG;
+    lb_gp_full* h = full(hc);
+    LB_DEVICE(h);
+    std::lock_guard<std::mutex> lock(h->ex.qmutex);
+    return lb_dinv_adopt_impl(h, G, dAll, absmax_all);
+}
+
 // per-kernel-class event timing for bench.py's roofline (not part of the reference-facing header)
 int lb_profile_enable(lb_gp* h, int on)
 {

@@ -735,33 +735,53 @@ constexpr int SB = 16;
 // machine, and with two co-resident half-width CTAs the last, partly filled round costs half as much as with CfgWide
 // (128 x 128, one CTA per SM); one CTA's C-tile prologue / epilogue also hides under the other's DMMA stream.
 // Tbuf[i, ct] = V[s0 + i, ct] - L[s0 + i, 0:s0] V[0:s0, ct]       grid = nrows * (Mp / BN), row tile fastest
-template <typename C>
+//
+// INV = true: the right-hand sides are identity columns, V = L^-1[:, column tiles c = inv_rank + t * inv_G] (the inversion of the
+// factor spread over inv_G GPUs by 128-column tiles, lb_launch_linv_columns).  Column tile c is zero above row tile c: super-blocks
+// above it are skipped and the K range starts at the super-block that holds it.
+template <typename C, bool INV>
 __global__ void __launch_bounds__(C::THREADS, (C::THREADS == 256) ? 2 : 1)
 panel_update_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ V, double* __restrict__ Tbuf, int64_t ldt, int s0,
-    int nrows, int ct0)
+    int nrows, int ct0, int inv_rank, int inv_G)
 {
     extern __shared__ __align__(16) double smem[];
     const int i = blockIdx.x % nrows, ct = ct0 + blockIdx.x / nrows;
+    int kb = 0;
+    if (INV) {
+        const int c = inv_rank + (ct * C::BN / LB_TILE) * inv_G;
+        if (c >= s0 + nrows) return; // (also the padding slots c >= T)
+        kb = c / SB * SB;
+    }
     const double* Vc = V + (int64_t)ct * C::BN * ld;
     lbg::Acc<C> acc;
     lbg::load_acc<C>(acc, Vc + (int64_t)(s0 + i) * LB_TILE, ld);
-    if (s0 > 0) lbg::mainloop<C, false, true, true>(acc, L + (int64_t)(s0 + i) * LB_TILE, ld, Vc, ld, s0 * LB_TILE, smem);
+    if (s0 > kb)
+        lbg::mainloop<C, false, true, true>(acc, L + (int64_t)(s0 + i) * LB_TILE + (int64_t)kb * LB_TILE * ld, ld, Vc + (int64_t)kb * LB_TILE, ld,
+            (s0 - kb) * LB_TILE, smem);
     lbg::store_acc<C>(acc, Tbuf + (int64_t)i * LB_TILE + (int64_t)ct * C::BN * ldt, ldt);
 }
 
 // V[s0 + i, ct] = sum_{k <= i} Linv[s0 + i, s0 + k] Tbuf[k, ct];  normpart[(s0 + i) * Mp + c] = sum over the tile's 128 rows of V^2
-template <typename C>
+template <typename C, bool INV>
 __global__ void __launch_bounds__(C::THREADS, (C::THREADS == 256) ? 2 : 1)
 panel_solve_kernel(const double* __restrict__ Linv, int64_t ld, const double* __restrict__ Tbuf, int64_t ldt, double* __restrict__ V, int s0,
-    int nrows, double* __restrict__ normpart, int64_t Mp, int ct0)
+    int nrows, double* __restrict__ normpart, int64_t Mp, int ct0, int inv_rank, int inv_G)
 {
     extern __shared__ __align__(16) double smem[];
     const int i = nrows - 1 - (int)(blockIdx.x % nrows), ct = ct0 + blockIdx.x / nrows; // longest K ranges first
+    int k0 = 0; // first row tile of Tbuf that is not zero
+    if (INV) {
+        const int c = inv_rank + (ct * C::BN / LB_TILE) * inv_G;
+        if (c >= s0 + nrows) return;
+        if (c > s0) k0 = c - s0;
+        if (i < k0) return; // rows above the column tile stay zero (the buffer is cleared before the first super-block)
+    }
     lbg::Acc<C> acc;
     acc.zero();
-    lbg::mainloop<C, false, true>(acc, Linv + (int64_t)(s0 + i) * LB_TILE + (int64_t)s0 * LB_TILE * ld, ld, Tbuf + (int64_t)ct * C::BN * ldt, ldt,
-        (i + 1) * LB_TILE, smem);
+    lbg::mainloop<C, false, true>(acc, Linv + (int64_t)(s0 + i) * LB_TILE + (int64_t)(s0 + k0) * LB_TILE * ld, ld,
+        Tbuf + (int64_t)k0 * LB_TILE + (int64_t)ct * C::BN * ldt, ldt, (i + 1 - k0) * LB_TILE, smem);
     lbg::store_acc<C>(acc, V + (int64_t)(s0 + i) * LB_TILE + (int64_t)ct * C::BN * ld, ld);
+    if (INV) return;
     // column norms of the tile: per thread (2 m16 tiles x 2 row halves), then the 8 row lanes, then the 4 row warps
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -819,10 +839,10 @@ int lb_launch_query_panel(lb_gp* h, cudaStream_t st, int64_t M, const double* dQ
     using CW = lbg::CfgWide;
     using CD = lbg::CfgDual;
     if (g_once.need()) {
-        LB_CUDA(cudaFuncSetAttribute(panel_update_kernel<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW::PIPE_BYTES));
-        LB_CUDA(cudaFuncSetAttribute(panel_solve_kernel<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW::PIPE_BYTES));
-        LB_CUDA(cudaFuncSetAttribute(panel_update_kernel<CD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CD::PIPE_BYTES));
-        LB_CUDA(cudaFuncSetAttribute(panel_solve_kernel<CD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CD::PIPE_BYTES));
+        LB_CUDA(cudaFuncSetAttribute(panel_update_kernel<CW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW::PIPE_BYTES));
+        LB_CUDA(cudaFuncSetAttribute(panel_solve_kernel<CW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW::PIPE_BYTES));
+        LB_CUDA(cudaFuncSetAttribute(panel_update_kernel<CD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CD::PIPE_BYTES));
+        LB_CUDA(cudaFuncSetAttribute(panel_solve_kernel<CD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CD::PIPE_BYTES));
     }
     const int T = (int)(h->Np / LB_TILE);
     const int64_t ld = h->Np, ldt = (int64_t)SB * LB_TILE;
@@ -888,12 +908,12 @@ int lb_launch_query_panel(lb_gp* h, cudaStream_t st, int64_t M, const double* dQ
             for (int g = 0; g < ngroups; ++g) {
                 const int c0 = (g == 0 ? 0 : split) * wmul, nc = (g == 0 ? split : ctiles - split) * wmul;
                 if (dual) {
-                    panel_update_kernel<CD><<<nrows * nc, CD::THREADS, CD::PIPE_BYTES, sts[g]>>>(h->dL, ld, dV, dT, ldt, s0, nrows, c0);
-                    panel_solve_kernel<CD><<<nrows * nc, CD::THREADS, CD::PIPE_BYTES, sts[g]>>>(h->dLinv, ld, dT, ldt, dV, s0, nrows, dNorm, Mp, c0);
+                    panel_update_kernel<CD, false><<<nrows * nc, CD::THREADS, CD::PIPE_BYTES, sts[g]>>>(h->dL, ld, dV, dT, ldt, s0, nrows, c0, 0, 1);
+                    panel_solve_kernel<CD, false><<<nrows * nc, CD::THREADS, CD::PIPE_BYTES, sts[g]>>>(h->dLinv, ld, dT, ldt, dV, s0, nrows, dNorm, Mp, c0, 0, 1);
                 }
                 else {
-                    panel_update_kernel<CW><<<nrows * nc, CW::THREADS, CW::PIPE_BYTES, sts[g]>>>(h->dL, ld, dV, dT, ldt, s0, nrows, c0);
-                    panel_solve_kernel<CW><<<nrows * nc, CW::THREADS, CW::PIPE_BYTES, sts[g]>>>(h->dLinv, ld, dT, ldt, dV, s0, nrows, dNorm, Mp, c0);
+                    panel_update_kernel<CW, false><<<nrows * nc, CW::THREADS, CW::PIPE_BYTES, sts[g]>>>(h->dL, ld, dV, dT, ldt, s0, nrows, c0, 0, 1);
+                    panel_solve_kernel<CW, false><<<nrows * nc, CW::THREADS, CW::PIPE_BYTES, sts[g]>>>(h->dLinv, ld, dT, ldt, dV, s0, nrows, dNorm, Mp, c0, 0, 1);
                 }
                 if (launches) *launches += 2;
             }
@@ -908,6 +928,60 @@ int lb_launch_query_panel(lb_gp* h, cudaStream_t st, int64_t M, const double* dQ
         panel_finish_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(dNorm, T, Mp, M, h->kp.sf2, h->kp.noise, dS2);
     }
     if (launches) ++*launches;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+// ---- inversion of the factor spread over G GPUs by 128-column tiles (config 4 on several GPUs: every rank scores its candidates
+// against all of L^-1, gp.hpp:618-624, but computes only its own columns of it) --------------------------------------------------------
+// Column tile t of the work buffer (t = 0 .. nt-1, nt = ceil(T / G)) holds L^-1[:, c] for the global tile c = rank + t * G: the blocked
+// solve of the panel path with identity right-hand sides, started at the super-block that holds c.  Flops: sum_c (T - c)^2 tiles,
+// i.e. N^3 / (3 G) per rank up to the super-block granularity.
+namespace panel {
+__global__ void __launch_bounds__(128)
+identity_cols_kernel(double* __restrict__ V, int64_t ld, int rank, int G, int T)
+{
+    const int c = rank + (int)blockIdx.x * G;
+    if (c >= T) return;
+    V[(int64_t)c * LB_TILE + threadIdx.x + ((int64_t)blockIdx.x * LB_TILE + threadIdx.x) * ld] = 1.0;
+}
+LbOncePerDevice g_once_inv;
+} // namespace panel
+
+int64_t lb_linv_columns_width(const lb_gp* h, int G) { return ((h->Np / LB_TILE + G - 1) / G) * LB_TILE; }
+
+size_t lb_linv_columns_scratch_doubles(const lb_gp* h, int G)
+{
+    const int64_t Mp = lb_linv_columns_width(h, G);
+    return (size_t)(h->Np * Mp + (int64_t)panel::SB * LB_TILE * Mp);
+}
+
+int lb_launch_linv_columns(lb_gp* h, cudaStream_t st, int rank, int G, double* dWork, long long* launches)
+{
+    using namespace panel;
+    using CD = lbg::CfgDual;
+    if (g_once_inv.need()) {
+        LB_CUDA(cudaFuncSetAttribute(panel_update_kernel<CD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CD::PIPE_BYTES));
+        LB_CUDA(cudaFuncSetAttribute(panel_solve_kernel<CD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CD::PIPE_BYTES));
+    }
+    const int T = (int)(h->Np / LB_TILE);
+    const int nt = (T + G - 1) / G;
+    const int64_t ld = h->Np, ldt = (int64_t)SB * LB_TILE, Mp = (int64_t)nt * LB_TILE;
+    double* dV = dWork;
+    double* dT = dV + ld * Mp;
+    int rc = lb_launch_linv_levels(h, SB); // inverse of the 16-tile diagonal blocks, on every rank (1.2 ms at N = 16384)
+    if (rc) return rc;
+    LbProfScope ps(h, st, LB_PC_TRTRI);
+    LB_CUDA(cudaMemsetAsync(dV, 0, sizeof(double) * (size_t)(ld * Mp), st));
+    identity_cols_kernel<<<nt, 128, 0, st>>>(dV, ld, rank, G, T);
+    const int nc = nt * (LB_TILE / CD::BN);
+    for (int s0 = 0; s0 < T; s0 += SB) {
+        const int nrows = (T - s0 < SB) ? (T - s0) : SB;
+        panel_update_kernel<CD, true><<<nrows * nc, CD::THREADS, CD::PIPE_BYTES, st>>>(h->dL, ld, dV, dT, ldt, s0, nrows, 0, rank, G);
+        panel_solve_kernel<CD, true><<<nrows * nc, CD::THREADS, CD::PIPE_BYTES, st>>>(h->dLinv, ld, dT, ldt, dV, s0, nrows, nullptr, Mp, 0, rank, G);
+        if (launches) *launches += 2;
+    }
+    if (launches) *launches += 1;
     LB_CUDA(cudaGetLastError());
     return LB_OK;
 }

@@ -1270,6 +1270,74 @@ linv_to_rowmajor_kernel(const double* __restrict__ Linv, int64_t ld, void* __res
     }
 }
 
+// ---- inversion spread over G GPUs (query.cu: lb_launch_linv_columns): pack this rank's columns, adopt everybody's ----------------
+// V: Np x ldr column-major, local column tile t = global tile c = rank + t * G.  Chunk of a rank (what the all_gather moves):
+//   [ hi plane: Np x ldr row-major (fp16, or fp32 holding tf32) | lo plane (split mode only) | w: ldr doubles = |L^-1 e_k|^2 ]
+template <bool F16>
+__global__ void __launch_bounds__(256)
+linv_cols_pack_kernel(const double* __restrict__ V, int64_t ld, int rank, int G, int T, void* __restrict__ R_, int64_t ldr, double scale,
+    void* __restrict__ Rlo_)
+{
+    __shared__ double tile[32][33];
+    const int64_t n0 = (int64_t)blockIdx.x * 32, l0 = (int64_t)blockIdx.y * 32; // rows, local columns
+    const int64_t c = rank + (l0 / LB_TILE) * G;                                  // global column tile
+    const int64_t k0 = c * LB_TILE + (l0 % LB_TILE);                              // global column of local column l0
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int kk = ty; kk < 32; kk += 8) tile[kk][tx] = (c < T && k0 + kk <= n0 + tx) ? V[n0 + tx + (l0 + kk) * ld] * scale : 0.0;
+    __syncthreads();
+    for (int nn = ty; nn < 32; nn += 8) {
+        const double v = tile[tx][nn];
+        if (F16) {
+            const __half hi = __float2half_rn((float)v);
+            reinterpret_cast<__half*>(R_)[(n0 + nn) * ldr + l0 + tx] = hi;
+            if (Rlo_) reinterpret_cast<__half*>(Rlo_)[(n0 + nn) * ldr + l0 + tx] = __float2half_rn((float)((v - (double)__half2float(hi)) * 2048.0));
+        }
+        else reinterpret_cast<float*>(R_)[(n0 + nn) * ldr + l0 + tx] = tf32_rna((float)v);
+    }
+}
+
+// w[l] = sum_n V[n, l]^2 (rows above the diagonal are zeros): one block per local column
+__global__ void __launch_bounds__(256)
+colnorm2_cols_kernel(const double* __restrict__ V, int64_t ld, double* __restrict__ w)
+{
+    __shared__ double red[8];
+    const double* col = V + (int64_t)blockIdx.x * ld;
+    double s = 0.0;
+    for (int64_t n = threadIdx.x; n < ld; n += 256) s = fma(col[n], col[n], s);
+    s = lb_warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        w[blockIdx.x] = t;
+    }
+}
+
+// out[n, c * 128 + kk] = plane of rank (c mod G), row n, local column (c / G) * 128 + kk; 16-byte pieces, one block per row
+__global__ void __launch_bounds__(256)
+linv_unpermute_kernel(const char* __restrict__ all, size_t chunk_bytes, size_t plane_off, int G, int T, int64_t Np, int64_t ldr, int esz,
+    char* __restrict__ out)
+{
+    const int64_t n = blockIdx.x;
+    const int tile_bytes = LB_TILE * esz, per_tile = tile_bytes / 16;
+    for (int idx = threadIdx.x; idx < T * per_tile; idx += 256) {
+        const int c = idx / per_tile, q = idx - c * per_tile;
+        const char* src = all + (size_t)(c % G) * chunk_bytes + plane_off + ((size_t)n * ldr + (size_t)(c / G) * LB_TILE) * esz + (size_t)q * 16;
+        char* dst = out + ((size_t)n * Np + (size_t)c * LB_TILE) * esz + (size_t)q * 16;
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+linvw_unpermute_kernel(const char* __restrict__ all, size_t chunk_bytes, size_t w_off, int G, int64_t Np, double* __restrict__ w)
+{
+    const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k >= Np) return;
+    const int64_t c = k / LB_TILE, kk = k % LB_TILE;
+    w[k] = reinterpret_cast<const double*>(all + (size_t)(c % G) * chunk_bytes + w_off)[(c / G) * LB_TILE + kk];
+}
+
 // sigma^2 from fp64 norms (split-operand mode): no rounding-bias term
 __global__ void __launch_bounds__(256)
 sigma2_split_kernel(const double* __restrict__ norm2, int64_t M, double kvv, double noise, double norm_unscale, double* __restrict__ s2)
@@ -1376,6 +1444,110 @@ int lb_tf32_prepare(lb_gp* h)
     }
     colnorm2_kernel<<<(unsigned)Np, 256, 0, h->stream>>>(h->dLinv, Np, h->dLinvW); // weights of the rounding-bias correction
     h->launches++;
+    LB_CUDA(cudaGetLastError());
+    h->linv32_valid = true;
+    return LB_OK;
+}
+
+// ---- the same copy assembled from the column chunks of G ranks (lb_dinv_* in abi.cu; limbo_b200/dist_inv.py) --------------------
+int64_t lb_linv_columns_width(const lb_gp* h, int G);
+
+static size_t dinv_plane_bytes(const lb_gp* h, int G)
+{
+    const bool f16 = (h->precision == 2) || (h->precision == 3);
+    return (size_t)h->Np * (size_t)lb_linv_columns_width(h, G) * (f16 ? 2 : 4);
+}
+
+size_t lb_dinv_chunk_bytes_impl(const lb_gp* h, int G)
+{
+    return dinv_plane_bytes(h, G) * (h->precision == 3 ? 2 : 1) + sizeof(double) * (size_t)lb_linv_columns_width(h, G);
+}
+
+// max |V| over this rank's columns (host value; synchronises the handle's stream)
+int lb_dinv_absmax(lb_gp* h, const double* dV, int G, double* out)
+{
+    using namespace tf32q;
+    int rc;
+    if ((rc = lb_ensure_scratch(h, sizeof(double) * 1024))) return rc;
+    absmax_kernel<<<1024, 256, 0, h->stream>>>(dV, h->Np * lb_linv_columns_width(h, G), h->dScratch);
+    h->launches++;
+    double part[1024];
+    LB_CUDA(cudaMemcpyAsync(part, h->dScratch, sizeof(part), cudaMemcpyDeviceToHost, h->stream));
+    LB_CUDA(cudaStreamSynchronize(h->stream));
+    double mx = 0.0;
+    for (double v : part) mx = v > mx ? v : mx;
+    *out = mx;
+    return LB_OK;
+}
+
+// the fp16 scale lb_tf32_prepare derives from max |L^-1| (1 for tf32)
+static int dinv_scale(const lb_gp* h, double absmax, double* scale)
+{
+    *scale = 1.0;
+    if (h->precision == 2 || h->precision == 3) {
+        if (!(absmax > 0.0) || !std::isfinite(absmax)) return LB_ERR_STATE;
+        *scale = std::ldexp(1.0, 14 - (int)std::ceil(std::log2(absmax)));
+    }
+    return LB_OK;
+}
+
+int lb_dinv_pack_impl(lb_gp* h, const double* dV, int rank, int G, double absmax_all, void* dChunk)
+{
+    using namespace tf32q;
+    const bool split = (h->precision == 3), f16 = (h->precision == 2) || split;
+    const int64_t Np = h->Np, ldr = lb_linv_columns_width(h, G);
+    const int T = (int)(Np / LB_TILE);
+    double scale;
+    int rc = dinv_scale(h, absmax_all, &scale);
+    if (rc) return rc;
+    char* base = reinterpret_cast<char*>(dChunk);
+    const size_t plane = dinv_plane_bytes(h, G);
+    dim3 grid((unsigned)(Np / 32), (unsigned)(ldr / 32));
+    LbProfScope ps(h, h->stream, LB_PC_OTHER);
+    if (f16) linv_cols_pack_kernel<true><<<grid, 256, 0, h->stream>>>(dV, Np, rank, G, T, base, ldr, scale, split ? base + plane : nullptr);
+    else linv_cols_pack_kernel<false><<<grid, 256, 0, h->stream>>>(dV, Np, rank, G, T, base, ldr, 1.0, nullptr);
+    colnorm2_cols_kernel<<<(unsigned)ldr, 256, 0, h->stream>>>(dV, Np, reinterpret_cast<double*>(base + plane * (split ? 2 : 1)));
+    h->launches += 2;
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+int lb_dinv_adopt_impl(lb_gp* h, int G, const void* dAll, double absmax_all)
+{
+    using namespace tf32q;
+    const bool split = (h->precision == 3), f16 = (h->precision == 2) || split;
+    const int cl = lb_tf32_pair_mode() ? 2 : lb_tf32_cluster_size();
+    const int64_t Np = h->Np, Nr = (Np + BN * cl - 1) / (BN * cl) * (BN * cl), ldr = lb_linv_columns_width(h, G);
+    const int T = (int)(Np / LB_TILE);
+    const size_t esz = split ? 4 : (f16 ? 2 : 4), el = f16 ? 2 : 4;
+    double scale;
+    int rc = dinv_scale(h, absmax_all, &scale);
+    if (rc) return rc;
+    if (!h->dLinv32 || h->linv32_rows != Nr) {
+        lb_dfree_sync(h, h->dLinv32);
+        h->dLinv32 = nullptr;
+        LB_ALLOC(h, h->dLinv32, esz * Nr * Np);
+        h->linv32_rows = Nr;
+    }
+    if (!h->dLinvW || h->linvw_np != Np) {
+        lb_dfree_sync(h, h->dLinvW);
+        h->dLinvW = nullptr;
+        LB_ALLOC(h, h->dLinvW, sizeof(double) * Np);
+        h->linvw_np = Np;
+    }
+    h->linv32_scale = scale;
+    const size_t chunk = lb_dinv_chunk_bytes_impl(h, G), plane = dinv_plane_bytes(h, G);
+    const char* all = reinterpret_cast<const char*>(dAll);
+    char* out = reinterpret_cast<char*>(h->dLinv32);
+    LbProfScope ps(h, h->stream, LB_PC_OTHER);
+    if (Nr > Np) { // padding rows of both planes
+        LB_CUDA(cudaMemsetAsync(out + el * Np * Np, 0, el * (Nr - Np) * Np, h->stream));
+        if (split) LB_CUDA(cudaMemsetAsync(out + el * Nr * Np + el * Np * Np, 0, el * (Nr - Np) * Np, h->stream));
+    }
+    linv_unpermute_kernel<<<(unsigned)Np, 256, 0, h->stream>>>(all, chunk, 0, G, T, Np, ldr, (int)el, out);
+    if (split) linv_unpermute_kernel<<<(unsigned)Np, 256, 0, h->stream>>>(all, chunk, plane, G, T, Np, ldr, (int)el, out + el * Nr * Np);
+    linvw_unpermute_kernel<<<(unsigned)((Np + 255) / 256), 256, 0, h->stream>>>(all, chunk, plane * (split ? 2 : 1), G, Np, h->dLinvW);
+    h->launches += split ? 3 : 2;
     LB_CUDA(cudaGetLastError());
     h->linv32_valid = true;
     return LB_OK;
