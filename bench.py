@@ -442,13 +442,20 @@ def run_config4(args, torch, dist, dev, rank, world, lib, precision: str = "tf32
     out = {}
 
     fitter = None
-    if world > 1 and not args.replicated_fit:  # the fp64 fit is the distributed one (dist_fit.py); inversion + cast stay per rank
+    if world > 1 and not args.replicated_fit:  # the fp64 fit is the distributed one (dist_fit.py)
         from limbo_b200 import dist_fit
         gp.compute(X, y[:, None], compute_kernel=False)
         fitter = dist_fit.DistFit(gp, rank, world, dev)
         if not fitter.supported(gp):
             fitter.close()
+    if dinv is not None:
+        dinv.close()
             fitter = None
+
+    dinv = None
+    if world > 1 and not args.replicated_inverse:  # every rank inverts its column tiles of the factor, one all_gather (dist_inv.py)
+        from limbo_b200 import dist_inv
+        dinv = dist_inv.DistInverse(gp, rank, world, dev)
 
     def step():
         if fitter is not None:
@@ -456,6 +463,8 @@ def run_config4(args, torch, dist, dev, rank, world, lib, precision: str = "tf32
             fitter.fit(gp)
         else:
             gp.compute(X, y[:, None])                      # fp64 fit through the public API (H2D inside)
+        if dinv is not None:
+            dinv.prepare(gp)
         ei._nb_samples = -1
         ei._update_f_max(acqui.first_elem)                 # ei.hpp:100-108: f_max = max_i mu(x_i), one batched pass over the N samples
         ap[0] = ei._f_max
@@ -517,7 +526,10 @@ def run_config4(args, torch, dist, dev, rank, world, lib, precision: str = "tf32
         "stage_ms_rank0": stage, "fit_ms_rank0": fit_ms, "invert_and_cast_ms_rank0": inv_ms, "score_ms_rank0": score_ms,
         "scoring_only_candidates_per_s": m_total / (score_ms * 1e-3) if score_ms > 0 else None,
         "fit_scheme": "distributed (dist_fit.py)" if fitter is not None else ("replicated" if world > 1 else "single GPU"),
-        "limiter": ((f"inversion of the factor + cast ({inv_ms:.0f} ms) are replicated on every rank (every rank scores against all of L^-1); the "
+        "inverse_scheme": "column tiles per rank + one all_gather (dist_inv.py)" if dinv is not None else ("replicated" if world > 1 else "single GPU"),
+        "limiter": ((f"distributed fp64 fit {fit_ms:.0f} ms (wall-timed on rank 0 in one extra step; its serial panel chain) + inversion by column "
+                     f"tiles, cast and all_gather ({inv_ms:.0f} ms of kernels on rank 0) + {score_ms:.0f} ms of sharded scoring") if (fitter is not None and dinv is not None) else
+                    (f"inversion of the factor + cast ({inv_ms:.0f} ms) are replicated on every rank (every rank scores against all of L^-1); the "
                      f"fp64 fit is distributed ({fit_ms:.0f} ms, wall-timed on rank 0 in one extra step), the {score_ms:.0f} ms of scoring shard") if fitter is not None else
                     (f"fp64 fit ({fit_ms:.0f} ms) + inversion/cast ({inv_ms:.0f} ms) are replicated on every rank (Amdahl); only the "
                      f"{score_ms:.0f} ms of scoring shard")),
@@ -925,6 +937,8 @@ def main() -> None:
     ap.add_argument("--no-sub", action="store_true", help="skip the config4 / config5 sub-records")
     ap.add_argument("--sub-timeout", type=int, default=240, help="seconds after which the line is printed without the unfinished sub-records")
     ap.add_argument("--replicated-fit", action="store_true", help="N > 1: every rank refits alone (round-1 scheme) instead of the distributed fit")
+    ap.add_argument("--replicated-inverse", action="store_true",
+                    help="N > 1, config 4: every rank inverts the whole factor (round-1 scheme) instead of its column tiles + one all_gather")
     ap.add_argument("--workload", default="n16384_se_ard", choices=sorted(WORKLOADS) + ["config4"])
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp16"], help="--workload config4 only")
     args = ap.parse_args()

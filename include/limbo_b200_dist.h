@@ -60,6 +60,25 @@ int lb_dchol_unpack(lb_gp* h, const double* dMsg, int64_t Nd, int kpair, void* c
  * factorisation's LAPACK-style info (> 0 is returned as is) */
 int lb_dchol_adopt_end(lb_gp* h, int info);
 
+/* ---- inversion of the factor spread over G GPUs, for the reduced-precision candidate path (LB_PREC_TF32 / FP16 / FP16X3,
+ * BASELINE.json config 4; limbo_b200/dist_inv.py).  sigma^2(v) = k(v,v) - |L^-1 k(v)|^2 (gp.hpp:618-624) is scored against a
+ * reduced-precision copy of ALL of L^-1 on every rank (the candidates are sharded, lb_acq_argmax), but the inverse itself is
+ * independent per column: rank r computes the 128-column tiles c = r, r + G, r + 2G, ... (N^3 / (3 G) flops, blocked forward
+ * solve of identity columns on the fp64 tensor cores), casts them, and one all_gather of the chunks gives every rank the whole
+ * copy.  Chunk of a rank = [ hi plane: Np x W row-major, W = 128 * ceil(Np / 128 / G), fp16 or fp32(tf32) | lo plane (FP16X3) |
+ * W doubles |L^-1 e_k|^2 (weights of the rounding-bias term) ]; local column tile t is global tile r + t * G.
+ * The handle must be fitted (lb_fit or lb_dchol_adopt_end); no other call on it between lb_dinv_columns and lb_dinv_pack. */
+/* bytes of one chunk (> 0), or a negative LB_ERR_* (LB_ERR_UNSUPPORTED for an fp64 handle) */
+long long lb_dinv_chunk_bytes(const lb_gp* h, int G);
+/* compute this rank's columns of L^-1 (kept in the handle's query workspace); *absmax_host = max |.| over them (the fp16 scale
+ * needs the maximum over ALL ranks: reduce it before lb_dinv_pack).  Synchronises the handle's stream. */
+int lb_dinv_columns(lb_gp* h, int rank, int G, double* absmax_host);
+/* cast this rank's columns into dChunk (device, lb_dinv_chunk_bytes) with the scale derived from absmax_all */
+int lb_dinv_pack(lb_gp* h, int rank, int G, double absmax_all, void* dChunk);
+/* dAll = the G chunks in rank order (device): assemble the handle's reduced-precision L^-1; after this lb_query / lb_acq_argmax
+ * score without inverting anything */
+int lb_dinv_adopt(lb_gp* h, int G, const void* dAll, double absmax_all);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,12 @@ int lb_launch_loo_grad(lb_gp* h, int optimize_noise, double* dGrad);
 int lb_launch_kinv_obs(lb_gp* h, double* dOut);
 int lb_query_fused_supported(const lb_gp* h);
 size_t lb_query_panel_scratch_doubles(const lb_gp* h, int64_t Mp);
+size_t lb_linv_columns_scratch_doubles(const lb_gp* h, int G);
+int lb_launch_linv_columns(lb_gp* h, cudaStream_t st, int rank, int G, double* dWork, long long* launches);
+size_t lb_dinv_chunk_bytes_impl(const lb_gp* h, int G);
+int lb_dinv_absmax(lb_gp* h, const double* dV, int G, double* out);
+int lb_dinv_pack_impl(lb_gp* h, const double* dV, int rank, int G, double absmax_all, void* dChunk);
+int lb_dinv_adopt_impl(lb_gp* h, int G, const void* dAll, double absmax_all);
 int lb_launch_query_point(const lb_gp* h, cudaStream_t st, const double* x_host, double* dQs, double* dVscratch, double* dOutMapped,
     long long* launches);
 int lb_launch_query_panel(lb_gp* h, cudaStream_t st, int64_t M, const double* dQs, int64_t Mp, double* dWork, double* dMu, double* dS2,
@@ -1263,12 +1269,6 @@ int lb_dchol_adopt_end(lb_gp* h, int info)
 }
 
 // ---- inversion of the factor spread over G GPUs, for the reduced-precision candidate path (limbo_b200_dist.h) --------------------
-size_t lb_linv_columns_scratch_doubles(const lb_gp* h, int G);
-int lb_launch_linv_columns(lb_gp* h, cudaStream_t st, int rank, int G, double* dWork, long long* launches);
-size_t lb_dinv_chunk_bytes_impl(const lb_gp* h, int G);
-int lb_dinv_absmax(lb_gp* h, const double* dV, int G, double* out);
-int lb_dinv_pack_impl(lb_gp* h, const double* dV, int rank, int G, double absmax_all, void* dChunk);
-int lb_dinv_adopt_impl(lb_gp* h, int G, const void* dAll, double absmax_all);
 
 static int dinv_check(const lb_gp* h, int rank, int G)
 {

@@ -65,3 +65,14 @@ def test_two_rank_distributed_fit_matches_lb_fit(n, kernel):
     assert res["n_gpus"] == 2 and res["supported"] and res["info"] == 0
     assert res["bit_identical_on_every_rank"], res
     assert res["loglik_rel_diff"] == 0.0, res
+
+
+@pytest.mark.parametrize("precision", ["fp16", "fp16x3"])
+def test_two_rank_distributed_inverse_matches_replicated(precision):
+    """limbo_b200/dist_inv.py: each rank inverts its column tiles of the factor, one all_gather assembles the reduced-precision
+    copy; variances agree with the replicated inversion and the sharded EI argmax is the unsharded one."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    res = _torchrun(2, "tools/dist_inv_check.py", "--size", "4500", "--cands", "6000", "--dim", "6", "--precision", precision, "--reps", "1")
+    assert res["n_gpus"] == 2 and res["supported"]
+    assert res["ok_on_every_rank"], res

@@ -1,7 +1,7 @@
 """Small end-to-end case for compute-sanitizer (memcheck / racecheck / synccheck): fit (quad-panel Cholesky), append, query
 (panel path, fused slab kernel, multi-launch, one-point kernel), acquisition, log-lik, gradient, LOO value / gradient,
 K^-1 obs_mean, SE-ARD with Lambda columns, Matern K build / gradient, tf32 / fp16 / fp16x3 queries, copy-on-write clones, and
-the multi-GPU Cholesky blocks and the distributed fit at world = 1."""
+the multi-GPU Cholesky blocks, the distributed fit and the inversion by column tiles at world = 1."""
 import ctypes as C
 import os
 import sys
@@ -23,6 +23,13 @@ for prec in ("fp64", "tf32", "fp16", "fp16x3"):
     mu, s2 = gp.query_batch(Xq)
     print(prec, "query ok", float(mu.sum()), float(s2.sum()))
     print(acqui.EI(gp).argmax_batch(Xq))
+    if prec != "fp64":  # inversion by column tiles (one rank) + cast + adoption, then the same scoring
+        from limbo_b200 import dist_inv
+        di = dist_inv.DistInverse(gp, 0, 1, "cuda:0")
+        gp.recompute(False)
+        di.prepare(gp)
+        print(prec, "column inverse", float(np.abs(gp.query_batch(Xq)[1] - s2).max()))
+        di.close()
     if prec == "fp64":
         lib = _lib.load()
         m1, v1 = gp.query(Xq[0])  # one-point kernel
