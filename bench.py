@@ -448,8 +448,6 @@ def run_config4(args, torch, dist, dev, rank, world, lib, precision: str = "tf32
         fitter = dist_fit.DistFit(gp, rank, world, dev)
         if not fitter.supported(gp):
             fitter.close()
-    if dinv is not None:
-        dinv.close()
             fitter = None
 
     dinv = None
@@ -511,6 +509,8 @@ def run_config4(args, torch, dist, dev, rank, world, lib, precision: str = "tf32
         fit_ms = (time.perf_counter() - tf) * 1e3
         sync_all()
         fitter.close()
+    if dinv is not None:
+        dinv.close()
     inv_ms = stage.get("trtri", 0.0) + stage.get("other", 0.0)
     score_ms = stage.get("kstar", 0.0) + stage.get("qstep", 0.0) + stage.get("qreduce", 0.0)
     mp = measured_peaks()
