@@ -22,9 +22,10 @@ def test_library_exports_every_declared_symbol(lib):
         assert hasattr(lib, name), name
     # the multi-GPU building blocks (include/limbo_b200_dist.h)
     hdr2 = open(os.path.join(ROOT, "include", "limbo_b200_dist.h")).read()
-    declared2 = sorted(set(re.findall(r"\b(lb_dchol_[a-z_0-9]+)\s*\(", hdr2)))
+    declared2 = sorted(set(re.findall(r"\b(lb_d(?:chol|inv)_[a-z_0-9]+)\s*\(", hdr2)))
     assert declared2 == ["lb_dchol_adopt_begin", "lb_dchol_adopt_end", "lb_dchol_build", "lb_dchol_finish", "lb_dchol_pack_head", "lb_dchol_panel",
-                         "lb_dchol_set_points", "lb_dchol_unpack", "lb_dchol_update"]
+                         "lb_dchol_set_points", "lb_dchol_unpack", "lb_dchol_update", "lb_dinv_adopt", "lb_dinv_chunk_bytes", "lb_dinv_columns",
+                         "lb_dinv_pack"]
     for name in declared2:
         assert hasattr(lib, name), name
 

@@ -10,13 +10,28 @@ import subprocess
 import sys
 
 
+def short_name(sig: str) -> str:
+    """'void panel::panel_update_kernel<lbg::Cfg<64, 2, 16, 0>, (bool)0>(const double *, ...)' -> 'panel_update_kernel<Cfg<64,2,16,0>,0>'"""
+    sig = sig.replace("(bool)", "")
+    depth, cut = 0, len(sig)
+    for i, ch in enumerate(sig):
+        depth += ch == "<"
+        depth -= ch == ">"
+        if ch == "(" and depth == 0:
+            cut = i
+            break
+    sig = sig[:cut]
+    m = re.match(r"([^<]*)(<.*>)?", sig)
+    return m.group(1).split("::")[-1].split()[-1] + (m.group(2) or "").replace("lbg::", "").replace(" ", "")
+
+
 def launches(path):
     rows = [r for r in csv.reader(open(path)) if len(r) > 10]
     hdr = rows[0]
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     agg = collections.defaultdict(lambda: [0, 0.0])
     for r in rows[1:]:
-        name = re.sub(r"\(.*", "", r[ki]).split("::")[-1]
+        name = short_name(r[ki])
         v = float(r[vi].replace(",", ""))
         v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(r[ui], 1e-6)
         agg[name][0] += 1
@@ -24,8 +39,8 @@ def launches(path):
     tot = sum(v[1] for v in agg.values())
     print(f"# ncu --metrics gpu__time_duration.sum --clock-control none  ({path}); cold-cache, serialised: compare shares")
     for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
-        print(f"{k:34s} launches={v[0]:5d} total_ms={v[1]:10.3f} share={v[1] / tot:6.3f}")
-    print(f"{'TOTAL':34s} launches={sum(v[0] for v in agg.values()):5d} total_ms={tot:10.3f}")
+        print(f"{k:52s} launches={v[0]:5d} total_ms={v[1]:10.3f} share={v[1] / tot:6.3f}")
+    print(f"{'TOTAL':52s} launches={sum(v[0] for v in agg.values()):5d} total_ms={tot:10.3f}")
 
 
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
