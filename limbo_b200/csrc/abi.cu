@@ -390,7 +390,8 @@ int lb_destroy(lb_gp* hh)
     lb_pool_free(h->dLambda);
     lb_pool_free(h->ex.dMisc);
     if (h->ex.hPoint) cudaFreeHost(h->ex.hPoint);
-    if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); h->aux = nullptr; }
+    for (cudaStream_t* ps : {&h->aux, &h->aux2, &h->aux3})
+        if (*ps) { cudaStreamSynchronize(*ps); cudaStreamDestroy(*ps); *ps = nullptr; }
     Shell sh;
     sh.own = h->ex.own; sh.side = h->side;
     for (int i = 0; i < LB_NEV; ++i) sh.ev[i] = h->ev[i];

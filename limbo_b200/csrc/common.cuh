@@ -288,6 +288,7 @@ struct lb_gp {
     bool own_stream = false;
     cudaStream_t side = nullptr;   // high-priority stream for the look-ahead panel factorisation
     cudaStream_t aux = nullptr;    // normal-priority second stream (panel query: second column group), created on first use
+    cudaStream_t aux2 = nullptr, aux3 = nullptr; // third / fourth column group of the panel query for small batches (created on first use)
     cudaEvent_t ev[LB_NEV] = {};        // fork / panel / a-update / join events
 
     int64_t N = 0;   // live samples

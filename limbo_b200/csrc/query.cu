@@ -874,22 +874,6 @@ int lb_launch_query_panel(lb_gp* h, cudaStream_t st, int64_t M, const double* dQ
         const char* e2 = getenv("LB_PANEL_SIDE");   // 1: second group on the high-priority side stream instead of a normal-priority one
         use_side = (e2 && atoi(e2) != 0) ? 1 : 0;
     }
-    cudaStream_t second = st;
-    if (split_pct < 100 && ctiles >= 4) {
-        if (use_side && h->side) second = h->side;
-        else {
-            if (!h->aux && cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess) h->aux = nullptr;
-            if (h->aux) second = h->aux;
-        }
-    }
-    cudaStream_t sts[2] = {st, second};
-    const int ngroups = (sts[1] != st) ? 2 : 1;
-    int split = ctiles;
-    if (ngroups == 2) {
-        split = (ctiles * split_pct + 50) / 100;
-        if (split < 1) split = 1;
-        if (split > ctiles - 1) split = ctiles - 1;
-    }
     // LB_PANEL_CFG=1: 128 x 128 tiles (CfgWide); default 128 x 64 tiles, two CTAs per SM.  Measured at N = 16384 (ms per batch,
     // Wide / Dual): M = 1250: 13.6 / 13.1, 2500: 23.1 / 21.9, 5000: 42.6 / 39.8, 10^4: 80.4 / 78.3 (same bits: the tile shape does not
     // change any element's accumulation order).
@@ -897,16 +881,54 @@ int lb_launch_query_panel(lb_gp* h, cudaStream_t st, int64_t M, const double* dQ
     if (cfg_mode < 0) { const char* e = getenv("LB_PANEL_CFG"); cfg_mode = e ? atoi(e) : 0; }
     const bool dual = cfg_mode != 1;
     const int wmul = dual ? 2 : 1; // 64-wide column tiles per 128 candidates
+    // Groups of column tiles, each walking the chain on its own stream.  Large batches: two groups (split_pct / rest).  Small batches
+    // (a launch of all column tiles is under ~4 rounds of the machine: M = 1250 is 320 CTAs for 296 slots, i.e. one full round and
+    // one nearly empty): up to four equal groups, so that a launch is a fraction of a round and the groups, drifting apart, keep the
+    // SMs full.  LB_PANEL_GROUPS=<1..4> forces the count.  Measured at N = 16384 (ms per batch, 1 / 2 / 3 / 4 groups): M = 640: 10.6 / 9.7 /
+    // 8.6 / 8.3, 1250: 14.8 / 13.3 / 12.9 / 12.5, 2500: 24.2 / 22.1 / 21.3 / 20.7, 5000: 42.6 / 40.0 / 39.8 / 39.8, 10^4: 83.6 / 78.3 / 78.4 / 78.3
+    // (profiles/r02_panel_groups.txt); results do not depend on the grouping (every tile's arithmetic is unchanged).
+    static int force_groups = -1;
+    if (force_groups < 0) { const char* e = getenv("LB_PANEL_GROUPS"); force_groups = e ? atoi(e) : 0; }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int slots = sms * (dual ? 2 : 1);
+    int ngroups = 1;
+    if (split_pct < 100 && ctiles >= 4) ngroups = ((int64_t)ctiles * wmul * SB < (int64_t)4 * slots) ? 4 : 2;
+    if (force_groups >= 1 && force_groups <= 4) ngroups = force_groups;
+    if (ngroups > ctiles) ngroups = ctiles;
+    cudaStream_t sts[4] = {st, st, st, st};
+    if (ngroups >= 2) {
+        if (use_side && h->side && ngroups == 2) sts[1] = h->side;
+        else {
+            cudaStream_t* extra[3] = {&h->aux, &h->aux2, &h->aux3};
+            for (int g = 1; g < ngroups; ++g) {
+                if (!*extra[g - 1] && cudaStreamCreateWithFlags(extra[g - 1], cudaStreamNonBlocking) != cudaSuccess) *extra[g - 1] = nullptr;
+                if (!*extra[g - 1]) { ngroups = g; break; } // no stream: fewer groups
+                sts[g] = *extra[g - 1];
+            }
+        }
+    }
+    int gbeg[5] = {0, ctiles, ctiles, ctiles, ctiles}; // first column tile (128 wide) of each group
+    if (ngroups == 2) {
+        int split = (ctiles * split_pct + 50) / 100;
+        if (split < 1) split = 1;
+        if (split > ctiles - 1) split = ctiles - 1;
+        gbeg[1] = split;
+    }
+    else
+        for (int g = 1; g < ngroups; ++g) gbeg[g] = (int)((int64_t)ctiles * g / ngroups);
+    gbeg[ngroups] = ctiles;
     {
         LbProfScope ps(h, st, LB_PC_QSTEP);
-        if (ngroups == 2) {
+        if (ngroups >= 2) {
             LB_CUDA(cudaEventRecord(h->ev[0], st));
-            LB_CUDA(cudaStreamWaitEvent(sts[1], h->ev[0], 0));
+            for (int g = 1; g < ngroups; ++g) LB_CUDA(cudaStreamWaitEvent(sts[g], h->ev[0], 0));
         }
         for (int s0 = 0; s0 < T; s0 += SB) {
             const int nrows = (T - s0 < SB) ? (T - s0) : SB;
             for (int g = 0; g < ngroups; ++g) {
-                const int c0 = (g == 0 ? 0 : split) * wmul, nc = (g == 0 ? split : ctiles - split) * wmul;
+                const int c0 = gbeg[g] * wmul, nc = (gbeg[g + 1] - gbeg[g]) * wmul;
+                if (nc <= 0) continue;
                 if (dual) {
                     panel_update_kernel<CD, false><<<nrows * nc, CD::THREADS, CD::PIPE_BYTES, sts[g]>>>(h->dL, ld, dV, dT, ldt, s0, nrows, c0, 0, 1);
                     panel_solve_kernel<CD, false><<<nrows * nc, CD::THREADS, CD::PIPE_BYTES, sts[g]>>>(h->dLinv, ld, dT, ldt, dV, s0, nrows, dNorm, Mp, c0, 0, 1);
@@ -918,9 +940,9 @@ int lb_launch_query_panel(lb_gp* h, cudaStream_t st, int64_t M, const double* dQ
                 if (launches) *launches += 2;
             }
         }
-        if (ngroups == 2) {
-            LB_CUDA(cudaEventRecord(h->ev[1], sts[1]));
-            LB_CUDA(cudaStreamWaitEvent(st, h->ev[1], 0));
+        for (int g = 1; g < ngroups; ++g) { // join (ev[1..3]; the fit's uses of these events are complete: same stream order)
+            LB_CUDA(cudaEventRecord(h->ev[g], sts[g]));
+            LB_CUDA(cudaStreamWaitEvent(st, h->ev[g], 0));
         }
     }
     {

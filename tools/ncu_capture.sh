@@ -6,8 +6,8 @@
 set -u
 mkdir -p gpurun_out /tmp/ncu
 NCU="ncu --set full --clock-control none --import-source on -f"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file /tmp/ncu/launches.csv python tools/profile_step.py 16384 10000 > /tmp/ncu/a.log 2>&1
-python tools/ncu_summary.py launches /tmp/ncu/launches.csv > gpurun_out/r02_launches.txt 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r02_launches.csv python tools/profile_step.py 16384 10000 > /tmp/ncu/a.log 2>&1
+python tools/ncu_summary.py launches gpurun_out/r02_launches.csv > gpurun_out/r02_launches.txt 2>&1
 cap() { # name, kernel regex, skip, command...
   local name=$1 rx=$2 skip=$3; shift 3
   if [ -n "${LB_NCU_ONLY:-}" ] && [[ " $LB_NCU_ONLY " != *" $name "* ]]; then return; fi

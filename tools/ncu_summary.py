@@ -12,7 +12,7 @@ import sys
 
 def short_name(sig: str) -> str:
     """'void panel::panel_update_kernel<lbg::Cfg<64, 2, 16, 0>, (bool)0>(const double *, ...)' -> 'panel_update_kernel<Cfg<64,2,16,0>,0>'"""
-    sig = sig.replace("(bool)", "")
+    sig = sig.replace("(bool)", "").replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
     depth, cut = 0, len(sig)
     for i, ch in enumerate(sig):
         depth += ch == "<"
@@ -22,7 +22,8 @@ def short_name(sig: str) -> str:
             break
     sig = sig[:cut]
     m = re.match(r"([^<]*)(<.*>)?", sig)
-    return m.group(1).split("::")[-1].split()[-1] + (m.group(2) or "").replace("lbg::", "").replace(" ", "")
+    base = (m.group(1).split("::")[-1].split() or ["?"])[-1]
+    return base + (m.group(2) or "").replace("lbg::", "").replace(" ", "")
 
 
 def launches(path):
