@@ -17,6 +17,26 @@ import ctypes as C
 from . import _lib
 
 
+TILE = 128
+
+
+def owned_tiles(T: int, rank: int, world: int) -> list[int]:
+    """global 128-column tiles of L^-1 computed by `rank` (tile-cyclic: local tile t is global tile rank + t * world)"""
+    return list(range(rank, T, world))
+
+
+def chunk_layout(Np: int, world: int, precision: str) -> dict:
+    """Byte layout of one rank's chunk (what the all_gather moves; include/limbo_b200_dist.h, lb_dinv_pack):
+    [ hi plane: Np x W row-major | lo plane (fp16x3 only) | W float64 column weights |L^-1 e_k|^2 ],  W = 128 * ceil(T / world)."""
+    T = Np // TILE
+    W = TILE * ((T + world - 1) // world)
+    elem = 4 if precision == "tf32" else 2          # tf32 values travel as fp32 words
+    planes = 2 if precision == "fp16x3" else 1
+    plane_bytes = Np * W * elem
+    return {"width": W, "elem_bytes": elem, "planes": planes, "plane_bytes": plane_bytes, "weights_offset": planes * plane_bytes,
+            "chunk_bytes": planes * plane_bytes + 8 * W}
+
+
 def bind(lib):
     vp, i32, f64 = C.c_void_p, C.c_int, C.c_double
     lib.lb_dinv_chunk_bytes.argtypes = [vp, i32]

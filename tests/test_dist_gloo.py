@@ -7,6 +7,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -232,3 +233,98 @@ def test_dist_cholesky_world2_gloo(tmp_path):
     assert all(r["err"] < 1e-11 for r in recs), recs
     assert sum(r["ncols"] for r in recs) == 768 and sum(r["n_panel"] for r in recs) == 3
     assert all(r["n_bcast"] == 2 for r in recs)
+
+
+# ---- inversion of the factor by column tiles (limbo_b200/dist_inv.py): chunk layout + all_gather + un-permutation, executed with
+# NumPy over gloo (the CUDA side is tests/test_gpu_dist_inv.py and tests/test_gpu_multirank.py) ------------------------------------
+WORKER_DINV = r"""
+import sys, json
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from limbo_b200 import dist_inv
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=int(sys.argv[4]))
+rank, world = dist.get_rank(), dist.get_world_size()
+precision = sys.argv[5]
+TILE = 128
+N = 5 * TILE
+rng = np.random.default_rng(3)
+A = rng.standard_normal((N, N)); K = A @ A.T / N + np.eye(N)
+L = np.linalg.cholesky(K)
+lay = dist_inv.chunk_layout(N, world, precision)
+W, T = lay["width"], N // TILE
+mine = dist_inv.owned_tiles(T, rank, world)
+# this rank's columns of L^-1: forward solves of identity columns (the columns of a triangular inverse are independent)
+from scipy.linalg import solve_triangular
+V = np.zeros((N, W))
+for t, c in enumerate(mine):
+    E = np.zeros((N, TILE)); E[c * TILE:(c + 1) * TILE] = np.eye(TILE)
+    V[:, t * TILE:(t + 1) * TILE] = solve_triangular(L, E, lower=True)
+amax = torch.tensor([np.abs(V).max()], dtype=torch.float64)
+dist.all_reduce(amax, op=dist.ReduceOp.MAX)                      # the fp16 scale needs the maximum over all ranks
+scale = 1.0 if precision == "tf32" else 2.0 ** (14 - int(np.ceil(np.log2(amax.item()))))
+chunk = np.zeros(lay["chunk_bytes"], dtype=np.uint8)
+et = np.float32 if precision == "tf32" else np.float16
+hi = (V * scale).astype(et)
+chunk[:lay["plane_bytes"]] = hi.view(np.uint8).reshape(-1)
+if lay["planes"] == 2:
+    lo = ((V * scale - hi.astype(np.float64)) * 2048.0).astype(np.float16)
+    chunk[lay["plane_bytes"]:2 * lay["plane_bytes"]] = lo.view(np.uint8).reshape(-1)
+chunk[lay["weights_offset"]:] = (V ** 2).sum(0).view(np.uint8)
+everything = torch.zeros(world * lay["chunk_bytes"], dtype=torch.uint8)
+dist.all_gather_into_tensor(everything, torch.from_numpy(chunk))
+allb = everything.numpy()
+# un-permute (lb_dinv_adopt): global tile c lives in the chunk of rank c mod world at local tile c // world
+out = np.zeros((N, N), dtype=et); w = np.zeros(N)
+for c in range(T):
+    base = (c % world) * lay["chunk_bytes"]
+    plane = allb[base:base + lay["plane_bytes"]].view(et).reshape(N, W)
+    out[:, c * TILE:(c + 1) * TILE] = plane[:, (c // world) * TILE:(c // world + 1) * TILE]
+    ww = allb[base + lay["weights_offset"]:base + lay["chunk_bytes"]].view(np.float64)
+    w[c * TILE:(c + 1) * TILE] = ww[(c // world) * TILE:(c // world + 1) * TILE]
+Linv = np.linalg.inv(L)
+ref = (np.tril(Linv) * scale).astype(et)
+err = float(np.abs(out.astype(np.float64) - ref.astype(np.float64)).max()) / float(np.abs(ref).max())
+werr = float(np.abs(w - (np.tril(Linv) ** 2).sum(0)).max())
+print(json.dumps({"rank": rank, "rel_err": err, "w_err": werr, "tiles": mine, "scale": scale, "upper_zero": bool((np.triu(out.astype(np.float64), 1) == 0).all())}))
+dist.destroy_process_group()
+"""
+
+
+def test_chunk_layout_and_tile_ownership():
+    from limbo_b200 import dist_inv
+    for T in (1, 5, 8, 128):
+        for w in (1, 2, 3, 8):
+            tiles = [dist_inv.owned_tiles(T, r, w) for r in range(w)]
+            assert sorted(c for ts in tiles for c in ts) == list(range(T))          # a partition of the column tiles
+            assert all(c % w == r for r, ts in enumerate(tiles) for c in ts)
+            lay = dist_inv.chunk_layout(T * 128, w, "fp16")
+            assert lay["width"] == 128 * max(len(ts) for ts in tiles)
+    lay = dist_inv.chunk_layout(16384, 4, "fp16x3")
+    assert lay == {"width": 4096, "elem_bytes": 2, "planes": 2, "plane_bytes": 16384 * 4096 * 2, "weights_offset": 2 * 16384 * 4096 * 2,
+                   "chunk_bytes": 2 * 16384 * 4096 * 2 + 8 * 4096}
+    assert dist_inv.chunk_layout(16384, 2, "tf32")["chunk_bytes"] == 16384 * 8192 * 4 + 8 * 8192
+
+
+
+@pytest.mark.parametrize("precision", ["fp16", "fp16x3", "tf32"])
+def test_column_tile_inverse_world2_gloo(tmp_path, precision):
+    """every rank inverts its column tiles, one all_gather, un-permutation: the assembled reduced-precision L^-1 equals the cast of
+    the whole inverse (up to the last bit of the storage type: the two fp64 results differ by rounding before the cast)"""
+    import json
+    port = _free_port()
+    script = tmp_path / "worker_dinv.py"
+    script.write_text(WORKER_DINV)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r), "2", precision], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True, env=env) for r in range(2)]
+    outs = [p.communicate(timeout=180) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e[-2000:]
+    recs = [json.loads(o.strip().splitlines()[-1]) for o, _ in outs]
+    assert recs[0]["tiles"] == [0, 2, 4] and recs[1]["tiles"] == [1, 3]
+    for r in recs:
+        assert r["upper_zero"] and r["w_err"] <= 1e-9
+        assert r["rel_err"] <= (2.0 ** -10 if precision != "tf32" else 2.0 ** -22), r  # at most one unit in the last place of the storage type
+    assert recs[0]["scale"] == recs[1]["scale"]
